@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""HEAL-SWIN hot-path benchmark (BASELINE.json metric: HEALPix pixels/s, forward+backward, N_side=256).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [...]
+
+One "step" = one training step of the HEAL-SWIN-UNet (BASELINE.json configs[1]) on one batch of
+synthetic spheres: forward, loss, backward, (DDP gradient all-reduce for N>1,) Adam update.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+
+* ``value``  : pixels/s with the batch already resident in HBM (device-timed, CUDA events).
+* ``e2e``    : the same step driven from pinned HOST buffers (H2D of the batch and D2H of the loss
+               inside the timed region).
+* ``roofline``: the windowed-attention forward kernel at the stage-0 shape, algorithmic bytes /
+               CUDA-event duration measured live in the timed region.
+* ``cpu_baseline`` / ``--impl reference``: the CPU oracle port of the reference's models_torch
+               forward+backward (oracle/hp_oracle.py) on the host cores -- a reported baseline only.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "healpix_pixels_per_sec_fwd_bwd_nside256"
+UNIT = "pixels/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch (BASELINE configs[1]: 8)")
+    ap.add_argument("--nside", type=int, default=256)
+    ap.add_argument("--base-pix", type=int, default=12)
+    ap.add_argument("--shift", default=None, help="nest_roll | nest_grid_shift | ring_shift (default by base_pix)")
+    ap.add_argument("--embed-dim", type=int, default=96)
+    ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--no-cos", action="store_true")
+    ap.add_argument("--v1-norm", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0)
+    return ap.parse_args()
+
+
+def model_kwargs(a):
+    shift = a.shift or ("nest_roll" if a.base_pix == 12 else "ring_shift")
+    heads = [max(1, a.embed_dim // 32 * 2**i) for i in range(4)]
+    return dict(patch_size=4, window_size=64, shift_size=4, shift_strategy=shift, rel_pos_bias="flat",
+                embed_dim=a.embed_dim, depths=[2, 2, 6, 2], num_heads=heads, use_cos_attn=not a.no_cos,
+                use_v2_norm_placement=not a.v1_norm,
+                dim_in=a.base_pix * a.nside * a.nside, f_in=3, f_out=a.classes, base_pix=a.base_pix)
+
+
+def workload_name(a, kw):
+    return (f"HEAL-SWIN-UNet N_side={a.nside} base_pix={a.base_pix} window=64 C={a.embed_dim} depths=[2,2,6,2] "
+            f"{kw['f_out']}-class seg, {kw['shift_strategy']}, cos_attn={kw['use_cos_attn']}, "
+            f"v2_norm={kw['use_v2_norm_placement']}, batch={a.batch}/GPU")
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU oracle timing
+def cpu_oracle_steps(kw, steps, warmup, budget_s):
+    """fwd+bwd of the oracle port on the host cores, B=1 full-size sphere per step."""
+    import torch
+
+    from oracle import hp_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.HPConfig(**kw)
+    sd = {k: v.requires_grad_(v.is_floating_point()) for k, v in O.synth_state_dict(cfg, seed=0).items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, kw["f_in"], kw["dim_in"], generator=g)
+    times = []
+
+    def one():
+        for v in sd.values():
+            v.grad = None
+        t0 = time.perf_counter()
+        O.hp_unet_forward(x, sd, cfg).float().mean().backward()
+        return time.perf_counter() - t0
+
+    t_first = one() if warmup > 0 else None
+    est = t_first if t_first is not None else 20.0
+    done_warm = 1 if warmup > 0 else 0
+    while done_warm < warmup and est * (done_warm + 1 + steps) < budget_s:
+        est = one()
+        done_warm += 1
+    k = max(1, min(steps, int(budget_s / max(est, 1e-3)) - done_warm))
+    for _ in range(k):
+        times.append(one())
+    t = statistics.median(times)
+    return {"value": kw["dim_in"] / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"B=1 full-size sphere ({kw['dim_in']} px) fwd+bwd, {k} timed step(s) after {done_warm} warm-up, "
+                      f"median {t:.2f} s/step, torch CPU fp32 {torch.get_num_threads()} threads"}, k, done_warm, t
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    kw = model_kwargs(a)
+    base, k, w, t = cpu_oracle_steps(kw, a.steps, a.warmup, a.cpu_budget_s)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": k, "warmup": w, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, kw) + " [CPU sample: batch=1]", "requested_steps": a.steps,
+                   "requested_warmup": a.warmup,
+                   "note": "CPU oracle port of the reference models_torch fwd+bwd (the Python reference cannot travel "
+                           "to the GPU box); steps clamped to the CPU time budget"},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from heal_swin_b200 import _lib, ops
+    from tests.util import build_product_model
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.check(_lib.lib.hs_device_info(None, None, None, None, 0))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    # remaining library GEMMs (cuBLAS through torch) run in TF32 like the reference's own container did
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+
+    kw = model_kwargs(a)
+    torch.manual_seed(0)
+    model = build_product_model(kw, None, dev)
+    with torch.no_grad():  # the reference zero-initialises the bias tables; give them signal
+        gen = torch.Generator(device="cpu").manual_seed(1)
+        for n, p in model.named_parameters():
+            if n.endswith("relative_position_bias_table"):
+                p.copy_((torch.randn(p.shape, generator=gen) * 0.02).to(dev))
+    model.train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    B, npix = a.batch, kw["dim_in"]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host_x = torch.randn(B, kw["f_in"], npix, generator=gen).pin_memory()
+    host_t = torch.randint(0, kw["f_out"], (B, npix), generator=gen).pin_memory()
+    dev_x, dev_t = host_x.to(dev), host_t.to(dev)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+
+    def step(x, t):
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(net(x), t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(a.warmup):
+        step(dev_x, dev_t)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.STATS.reset()
+    ops.STATS.timing = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step(dev_x, dev_t)
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    launches = ops.STATS.launches
+    kernel_ms = ops.STATS.elapsed_ms()
+    ops.STATS.timing = False
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end from pinned host buffers (H2D batch, D2H loss each step)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        x = host_x.to(dev, non_blocking=True)
+        t = host_t.to(dev, non_blocking=True)
+        loss = step(x, t)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    final_loss = float(host_loss)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pix_per_step = world * B * npix
+    value = pix_per_step * a.steps / (ms_dev * 1e-3)
+    e2e = pix_per_step * a.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the windowed-attention forward kernel at the stage-0 shape
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback (B200_PROFILING.md)")
+    roofline = None
+    fwd = {k[1]: v for k, v in kernel_ms.items() if k[0] == "window_attn_fwd"}
+    if fwd:
+        tag = max(fwd, key=lambda t: t[0] * t[1] * t[2])  # stage 0: most tokens
+        Bq, Nq, Cq, Hq, wsq = tag
+        alg_bytes = Bq * Nq * (3 * Cq + Cq) * 4  # read q,k,v + write o, fp32 (4*ws*d*elt per window-head)
+        avg_ms = statistics.mean(fwd[tag])
+        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
+        roofline = {"kernel": "hs_window_attn_fwd (attention core, stage-0 shape)", "bound": "hbm",
+                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "avg_launch_ms": avg_ms, "launches_timed": len(fwd[tag]),
+                    "shape": {"B": Bq, "N": Nq, "C": Cq, "H": Hq, "ws": wsq}}
+    kernel_share = {f"{k[0]}{list(k[1])}": sum(v) / ms_dev for k, v in kernel_ms.items()}
+
+    cpu_base = None
+    if world == 1 and not a.no_cpu_baseline:
+        cpu_base, _, _, _ = cpu_oracle_steps(kw, 1, 1, min(a.cpu_budget_s, 60.0))
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": workload_name(a, kw), "global_batch": world * B, "pixels_per_sample": npix,
+                   "parallelism": f"dp{world}", "step": "fwd + CE loss + bwd + (NCCL grad all-reduce) + Adam",
+                   "l2_policy": "inputs larger than L2 (activations 0.6-2.4 GB per tensor at stage 0), no flush needed",
+                   "final_loss": final_loss},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
+                "h2d_bytes_per_step": host_x.numel() * 4 + host_t.numel() * 8, "d2h_bytes_per_step": 4},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernel_share_of_step": kernel_share,
+        "cpu_baseline": cpu_base,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

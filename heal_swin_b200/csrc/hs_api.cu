@@ -1,0 +1,22 @@
+// C-ABI entry points of the device kernels: argument validation + kernel-family dispatch.
+#include "hs_common.h"
+#include "hs_kernels.h"
+
+extern "C" {
+
+int hs_window_attn_fwd(const float* qkv, const int32_t* src, const uint8_t* groups, const float* mask,
+                       const float* bias, const float* logit_scale, float scale, float* out, int B,
+                       int64_t N, int C, int H, int ws, uint32_t flags, void* stream) {
+  return hs::window_attn_fwd_simt(qkv, src, groups, mask, bias, logit_scale, scale, out, B, N, C, H, ws,
+                                  flags, (cudaStream_t)stream);
+}
+
+int hs_window_attn_bwd(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
+                       const float* mask, const float* bias, const float* logit_scale, float scale,
+                       float* dqkv, float* dbias, float* dlogit_scale, int B, int64_t N, int C, int H,
+                       int ws, uint32_t flags, void* stream) {
+  return hs::window_attn_bwd_simt(qkv, dout, src, groups, mask, bias, logit_scale, scale, dqkv, dbias,
+                                  dlogit_scale, B, N, C, H, ws, flags, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,16 @@
+// Internal kernel-family entry points (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace hs {
+
+int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* groups, const float* mask,
+                         const float* bias, const float* logit_scale, float scale, float* out, int B,
+                         int64_t N, int C, int H, int ws, uint32_t flags, cudaStream_t stream);
+int window_attn_bwd_simt(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
+                         const float* mask, const float* bias, const float* logit_scale, float scale,
+                         float* dqkv, float* dbias, float* dlogit, int B, int64_t N, int C, int H, int ws,
+                         uint32_t flags, cudaStream_t stream);
+
+}  // namespace hs

@@ -1,0 +1,478 @@
+"""Drop-in mirror of heal_swin/models_torch/swin_hp_transformer.py on the B200 engine.
+
+Same class names, constructor signatures, parameter / buffer names and shapes as the reference
+(SURVEY.md 8b), so Lightning wrappers, optimizers, DDP bucketing and checkpoints keep working.
+What differs is what ``forward`` launches: the shift -> window-partition -> attention ->
+window-reverse -> shift-back chain is one kernel with the HEALPix permutation folded into its
+loads/stores (csrc/), fed by compact int32 / uint8 tables instead of the (nW, ws, ws) fp32 mask.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import List, Literal, Optional
+
+import torch
+import torch.nn as nn
+import torch.utils.checkpoint as checkpoint
+
+from .. import hp_index, ops
+from ..data_spec import DataSpec
+from . import hp_shifting
+from .hp_windowing import window_partition, window_reverse, get_nest_win_idcs  # noqa: F401 (re-export)
+
+
+class DropPath(nn.Module):
+    """Stochastic depth (timm 0.4.12 ``DropPath`` as used at swin_hp_transformer.py:261)."""
+
+    def __init__(self, drop_prob=None):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if not self.training or not self.drop_prob:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
+        return x * (mask / keep)
+
+
+class Mlp(nn.Module):
+    """swin_hp_transformer.py:21-44"""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+
+class WindowAttention(nn.Module):
+    """Window multi-head self attention with relative position bias   [swin_hp_transformer.py:47-174]
+
+    ``window_size`` is the flat number of tokens per window (a power of 2; a power of 4 with
+    ``rel_pos_bias="flat"``).
+    """
+
+    def __init__(self, dim, window_size, num_heads, rel_pos_bias=None, qkv_bias=True, qk_scale=None,
+                 attn_drop=0.0, proj_drop=0.0, use_cos_attn=False):
+        super().__init__()
+        self.dim = dim
+        self.window_size = window_size
+        self.num_heads = num_heads
+        self.use_cos_attn = use_cos_attn
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        self.rel_pos_bias = rel_pos_bias
+
+        if use_cos_attn:  # :84-87
+            self.logit_scale = nn.Parameter(torch.log(10 * torch.ones((num_heads, 1, 1))), requires_grad=True)
+        if rel_pos_bias == "flat":  # :89-114; zero-initialised like the reference (:121 is commented out)
+            side = 2 * window_size**0.5 - 1
+            self.relative_position_bias_table = nn.Parameter(torch.zeros((int(side * side), num_heads)))
+            index = hp_index.rel_pos_index(window_size)
+            self.register_buffer("relative_position_index", index)
+            self.register_buffer("_hs_rel_index", index.to(torch.int32).reshape(-1).contiguous(), persistent=False)
+
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.softmax = nn.Softmax(dim=-1)
+
+    def _core(self, qkv, window_size, src, groups, dense_mask):
+        if self.training and self.attn_drop.p > 0.0:
+            raise NotImplementedError(
+                "attention-probability dropout (attn_drop > 0 in training mode) is not implemented in the "
+                "fused attention kernel yet; set attn_drop_rate=0.")
+        table = self.relative_position_bias_table if self.rel_pos_bias is not None else None
+        rel_index = self._hs_rel_index if table is not None else None
+        logit_scale = self.logit_scale if self.use_cos_attn else None
+        return ops.window_attention_core(qkv, table, logit_scale, src, groups, dense_mask, rel_index,
+                                         self.scale, self.num_heads, window_size, self.use_cos_attn)
+
+    def forward_tokens(self, x, window_size, src=None, groups=None):
+        """Fused path used by SwinTransformerBlock: x is the (B, N, C) token tensor in its natural
+        (unshifted) order; ``src``/``groups`` are the block's shift tables (None = no shift)."""
+        out = self._core(self.qkv(x), window_size, src, groups, None)
+        return self.proj_drop(self.proj(out))
+
+    def forward(self, x, mask=None):
+        """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:124-174]"""
+        B_, n, C = x.shape
+        qkv = self.qkv(x)
+        if mask is not None:
+            nW = mask.shape[0]
+            assert B_ % nW == 0
+            qkv = qkv.reshape(B_ // nW, nW * n, 3 * C)
+        out = self._core(qkv, n, None, None, mask)
+        return self.proj_drop(self.proj(out.reshape(B_, n, C)))
+
+    def extra_repr(self) -> str:
+        return f"dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}"
+
+
+class SwinTransformerBlock(nn.Module):
+    """Swin block on the HEALPix grid   [swin_hp_transformer.py:193-340]"""
+
+    def __init__(self, dim, input_resolution, base_pix, num_heads, window_size=4, shift_size=0,
+                 shift_strategy="nest_roll", rel_pos_bias=None, mlp_ratio=4.0, qkv_bias=True, qk_scale=None,
+                 drop=0.0, attn_drop=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=nn.LayerNorm,
+                 use_v2_norm_placement=False, use_cos_attn=False):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.mlp_ratio = mlp_ratio
+        self.use_v2_norm_placement = use_v2_norm_placement
+        if self.input_resolution <= self.window_size:  # :243-246
+            self.shift_size = 0
+            self.window_size = self.input_resolution
+
+        self.norm1 = norm_layer(dim)
+        # NB (:249-251) the attention module keeps the configured window size for its bias table
+        self.attn = WindowAttention(dim, window_size=window_size, num_heads=num_heads, rel_pos_bias=rel_pos_bias,
+                                    qkv_bias=qkv_bias, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop,
+                                    use_cos_attn=use_cos_attn)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm2 = norm_layer(dim)
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
+
+        nside = hp_index.nside_of(input_resolution, base_pix)  # :271-274
+        if self.shift_size > 0:  # :277-304
+            if shift_strategy == "nest_roll":
+                self.shifter = hp_shifting.NestRollShift(self.shift_size, self.input_resolution, self.window_size)
+            elif shift_strategy == "nest_grid_shift":
+                self.shifter = hp_shifting.NestGridShift(nside, base_pix, self.window_size)
+            elif shift_strategy == "ring_shift":
+                self.shifter = hp_shifting.RingShift(nside, base_pix, self.window_size, self.shift_size)
+            else:
+                raise KeyError(shift_strategy)
+        else:
+            self.shifter = hp_shifting.NoShift()
+
+        # checkpoint-compatible buffer (:306-308); the kernels read the compact tables below instead
+        self.register_buffer("attn_mask", self.shifter.get_mask())
+        if self.shifter.shift_idcs is not None:
+            self.register_buffer("_hs_src", self.shifter.shift_idcs.to(torch.int32).contiguous(), persistent=False)
+            self.register_buffer("_hs_groups", self.shifter.groups.to(torch.uint8).contiguous(), persistent=False)
+        else:
+            self._hs_src = None
+            self._hs_groups = None
+
+    def forward(self, x):
+        B, N, C = x.shape
+        assert N == self.input_resolution, f"got {N} tokens, block was built for {self.input_resolution}"
+        shortcut = x
+        if not self.use_v2_norm_placement:
+            x = self.norm1(x)
+        # shift + partition + W-MSA/SW-MSA + reverse + shift back, one kernel chain   [:319-330]
+        x = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups)
+        if self.use_v2_norm_placement:  # :333-338
+            x = shortcut + self.drop_path(self.norm1(x))
+            x = x + self.drop_path(self.norm2(self.mlp(x)))
+        else:
+            x = shortcut + self.drop_path(x)
+            x = x + self.drop_path(self.mlp(self.norm2(x)))
+        return x
+
+    def extra_repr(self) -> str:
+        return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"
+                f" window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
+
+
+SwinHPTransformerBlock = SwinTransformerBlock  # the name BASELINE.json uses
+
+
+class PatchMerging(nn.Module):
+    """4 nested siblings -> 1 token: view (B, N/4, 4C) -> LayerNorm -> Linear(4C -> 2C)   [:364-395]"""
+
+    def __init__(self, dim, dim_scale=2, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.reduction = nn.Linear(4 * dim, dim_scale * dim, bias=False)
+        self.norm = norm_layer(4 * dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        assert N % 4 == 0, f"x size {N} is not divisible by 4 as necessary for patching."
+        # cat(x[:,0::4], ..., x[:,3::4]) on the channel axis is a plain view in nested order
+        x = x.contiguous().view(B, N // 4, 4 * C)
+        return self.reduction(self.norm(x))
+
+    def extra_repr(self) -> str:
+        return f"dim={self.dim}"
+
+
+PatchMerge = PatchMerging
+
+
+class PatchExpand(nn.Module):
+    """1 token -> 4 nested children: Linear(C -> 2C) -> view (B, 4N, C/2) -> LayerNorm   [:407-430]"""
+
+    def __init__(self, dim, dim_scale=2, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.expand = nn.Linear(dim, dim_scale * dim, bias=False) if dim_scale != 1 else nn.Identity()
+        self.norm = norm_layer(dim * dim_scale // 4)
+
+    def forward(self, x):
+        x = self.expand(x)
+        B, N, C = x.shape
+        return self.norm(x.contiguous().view(B, 4 * N, C // 4))
+
+
+PatchExpanding = PatchExpand  # the name BASELINE.json uses
+
+
+class FinalPatchExpand_X4(nn.Module):
+    """[:433-452]"""
+
+    def __init__(self, patch_size, dim, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.dim = dim
+        self.patch_size = patch_size
+        self.expand = nn.Linear(dim, patch_size * dim, bias=False)
+        self.output_dim = dim
+        self.norm = norm_layer(self.output_dim)
+
+    def forward(self, x):
+        x = self.expand(x)
+        B, N, C = x.shape
+        return self.norm(x.contiguous().view(B, N * self.patch_size, C // self.patch_size))
+
+
+def _make_blocks(dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size, shift_strategy,
+                 rel_pos_bias, mlp_ratio, qkv_bias, qk_scale, drop, attn_drop, drop_path, norm_layer,
+                 use_v2_norm_placement, use_cos_attn):
+    # even blocks W-MSA, odd blocks SW-MSA   [:508-531, :614-637]
+    return nn.ModuleList([
+        SwinTransformerBlock(
+            dim=dim, input_resolution=input_resolution, num_heads=num_heads, window_size=window_size,
+            base_pix=base_pix, shift_size=0 if (i % 2 == 0) else shift_size, shift_strategy=shift_strategy,
+            rel_pos_bias=rel_pos_bias, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale, drop=drop,
+            attn_drop=attn_drop, drop_path=drop_path[i] if isinstance(drop_path, list) else drop_path,
+            norm_layer=norm_layer, use_v2_norm_placement=use_v2_norm_placement, use_cos_attn=use_cos_attn)
+        for i in range(depth)])
+
+
+class BasicLayer(nn.Module):
+    """One encoder stage: ``depth`` blocks (+ PatchMerging)   [:455-547]"""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size, shift_strategy,
+                 rel_pos_bias, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 norm_layer=nn.LayerNorm, downsample=None, use_checkpoint=False, use_v2_norm_placement=False,
+                 use_cos_attn=False):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = _make_blocks(dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size,
+                                   shift_strategy, rel_pos_bias, mlp_ratio, qkv_bias, qk_scale, drop, attn_drop,
+                                   drop_path, norm_layer, use_v2_norm_placement, use_cos_attn)
+        self.downsample = downsample(dim=dim, norm_layer=norm_layer) if downsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = checkpoint.checkpoint(blk, x) if self.use_checkpoint else blk(x)
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return x
+
+    def extra_repr(self) -> str:
+        return f"dim={self.dim}, input_resolution={self.input_resolution}, depth={self.depth}"
+
+
+class BasicLayer_up(nn.Module):
+    """One decoder stage: ``depth`` blocks (+ PatchExpand)   [:561-653]"""
+
+    def __init__(self, dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size, shift_strategy,
+                 rel_pos_bias, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop=0.0, attn_drop=0.0, drop_path=0.0,
+                 norm_layer=nn.LayerNorm, upsample=None, use_checkpoint=False, use_v2_norm_placement=False,
+                 use_cos_attn=False):
+        super().__init__()
+        self.dim = dim
+        self.input_resolution = input_resolution
+        self.depth = depth
+        self.use_checkpoint = use_checkpoint
+        self.blocks = _make_blocks(dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size,
+                                   shift_strategy, rel_pos_bias, mlp_ratio, qkv_bias, qk_scale, drop, attn_drop,
+                                   drop_path, norm_layer, use_v2_norm_placement, use_cos_attn)
+        self.upsample = PatchExpand(dim=dim, dim_scale=2, norm_layer=norm_layer) if upsample is not None else None
+
+    def forward(self, x):
+        for blk in self.blocks:
+            x = checkpoint.checkpoint(blk, x) if self.use_checkpoint else blk(x)
+        if self.upsample is not None:
+            x = self.upsample(x)
+        return x
+
+
+class PatchEmbed(nn.Module):
+    """Conv1d(k = s = patch_size) over the nested pixel axis   [:656-694]"""
+
+    def __init__(self, config, data_spec):
+        super().__init__()
+        assert config.patch_size % 4 == 0, "required for valid nside in deeper layers"
+        self.config = config
+        self.data_spec = data_spec
+        self.num_patches = data_spec.dim_in // config.patch_size
+        self.proj = nn.Conv1d(data_spec.f_in, config.embed_dim, kernel_size=config.patch_size,
+                              stride=config.patch_size)
+        self.norm = config.patch_embed_norm_layer if config.patch_embed_norm_layer is not None else None
+
+    def forward(self, x):
+        B, C, N = x.shape
+        assert N == self.data_spec.dim_in, f"Input image size ({N}) doesn't match model ({self.data_spec.dim_in})."
+        x = self.proj(x).transpose(1, 2)
+        if self.norm is not None:
+            x = self.norm(x)
+        return x
+
+
+class UnetDecoder(nn.Module):
+    """[:704-791]"""
+
+    def __init__(self, config, data_spec, dpr):
+        super().__init__()
+        self.config = config
+        self.num_layers = len(config.depths)
+        self.num_features = int(config.embed_dim * 2 ** (self.num_layers - 1))
+        num_patches = data_spec.dim_in // config.patch_size
+        self.layers_up = nn.ModuleList()
+        self.concat_back_dim = nn.ModuleList()
+        for i_layer in range(self.num_layers):
+            down_idx = self.num_layers - 1 - i_layer
+            width = int(config.embed_dim * 2**down_idx)
+            if i_layer == 0:
+                self.concat_back_dim.append(nn.Identity())
+                self.layers_up.append(PatchExpand(dim=width, dim_scale=2, norm_layer=config.norm_layer))
+                continue
+            self.concat_back_dim.append(nn.Linear(2 * width, width))
+            lo, hi = sum(config.depths[:down_idx]), sum(config.depths[: down_idx + 1])
+            self.layers_up.append(BasicLayer_up(
+                dim=width, input_resolution=num_patches // (4**down_idx), depth=config.depths[down_idx],
+                num_heads=config.num_heads[down_idx], window_size=config.window_size, base_pix=data_spec.base_pix,
+                shift_size=config.shift_size, shift_strategy=config.shift_strategy, rel_pos_bias=config.rel_pos_bias,
+                mlp_ratio=config.mlp_ratio, qkv_bias=config.qkv_bias, qk_scale=config.qk_scale,
+                use_cos_attn=config.use_cos_attn, drop=config.drop_rate, attn_drop=config.attn_drop_rate,
+                drop_path=dpr[lo:hi], norm_layer=config.norm_layer,
+                use_v2_norm_placement=config.use_v2_norm_placement,
+                upsample=PatchExpand if down_idx > 0 else None, use_checkpoint=config.use_checkpoint))
+        self.up = FinalPatchExpand_X4(patch_size=config.patch_size, dim=config.embed_dim)
+        self.output = nn.Conv1d(in_channels=config.embed_dim, out_channels=data_spec.f_out, kernel_size=1, bias=False)
+        self.norm_up = config.norm_layer(config.embed_dim)
+
+    def forward(self, x, x_downsample):
+        for inx, layer_up in enumerate(self.layers_up):
+            if inx > 0:
+                x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
+                x = self.concat_back_dim[inx](x)
+            x = layer_up(x)
+        x = self.up(self.norm_up(x))
+        return self.output(x.permute(0, 2, 1))
+
+
+@dataclass
+class SwinHPTransformerConfig:
+    """[:794-818] -- same fields, same defaults"""
+
+    patch_size: int = 4
+    window_size: int = 4
+    shift_size: int = 2
+    shift_strategy: Literal["nest_roll", "nest_grid_shift", "ring_shift"] = "nest_roll"
+    rel_pos_bias: Optional[Literal["flat"]] = None
+    embed_dim: int = 96
+    patch_embed_norm_layer: Optional[Literal[nn.LayerNorm]] = None
+    depths: List[int] = field(default_factory=lambda: [2, 2, 2, 2])
+    num_heads: List[int] = field(default_factory=lambda: [3, 6, 12, 24])
+    mlp_ratio: float = 4.0
+    qkv_bias: bool = True
+    qk_scale: Optional[float] = None
+    use_cos_attn: bool = False
+    drop_rate: float = 0.0
+    attn_drop_rate: float = 0.0
+    drop_path_rate: float = 0.1
+    norm_layer: Literal[nn.LayerNorm] = nn.LayerNorm
+    use_v2_norm_placement: bool = False
+    ape: bool = False
+    patch_norm: bool = True
+    use_checkpoint: bool = False
+    dev_mode: bool = False
+    decoder_class: Literal[UnetDecoder] = UnetDecoder
+
+
+class SwinHPTransformerSys(nn.Module):
+    """HEAL-SWIN-UNet   [:821-955]: forward(x: (B, f_in, N_pix)) -> (B, f_out, N_pix)"""
+
+    def __init__(self, config: SwinHPTransformerConfig, data_spec: DataSpec, **kwargs):
+        super().__init__()
+        self.config = config
+        self.data_spec = data_spec
+        self.num_layers = len(config.depths)
+        self.num_features = int(config.embed_dim * 2 ** (self.num_layers - 1))
+        self.num_features_up = int(config.embed_dim * 2)
+
+        self.patch_embed = PatchEmbed(config, data_spec=data_spec)
+        num_patches = self.patch_embed.num_patches
+        if config.ape:
+            self.absolute_pos_embed = nn.Parameter(torch.zeros(1, num_patches, config.embed_dim))
+            nn.init.trunc_normal_(self.absolute_pos_embed, std=0.02)
+        self.pos_drop = nn.Dropout(p=config.drop_rate)
+
+        dpr = [v.item() for v in torch.linspace(0, config.drop_path_rate, sum(config.depths))]  # :871-873
+        self.layers = nn.ModuleList()
+        for i_layer in range(self.num_layers):
+            lo, hi = sum(config.depths[:i_layer]), sum(config.depths[: i_layer + 1])
+            self.layers.append(BasicLayer(
+                dim=int(config.embed_dim * 2**i_layer), input_resolution=num_patches // (4**i_layer),
+                depth=config.depths[i_layer], num_heads=config.num_heads[i_layer], window_size=config.window_size,
+                base_pix=data_spec.base_pix, shift_size=config.shift_size, shift_strategy=config.shift_strategy,
+                rel_pos_bias=config.rel_pos_bias, mlp_ratio=config.mlp_ratio, qkv_bias=config.qkv_bias,
+                qk_scale=config.qk_scale, use_cos_attn=config.use_cos_attn, drop=config.drop_rate,
+                attn_drop=config.attn_drop_rate, drop_path=dpr[lo:hi], norm_layer=config.norm_layer,
+                use_v2_norm_placement=config.use_v2_norm_placement,
+                downsample=PatchMerging if (i_layer < self.num_layers - 1) else None,
+                use_checkpoint=config.use_checkpoint))
+        self.decoder = config.decoder_class(config, data_spec, dpr)
+        out_channels = self.num_features * (1 if config.decoder_class == UnetDecoder else 2)
+        self.norm = config.norm_layer(out_channels)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):  # :912-919
+        if isinstance(m, nn.Linear):
+            nn.init.trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {"absolute_pos_embed"}
+
+    @torch.jit.ignore
+    def no_weight_decay_keywords(self):
+        return {"relative_position_bias_table"}
+
+    def forward_features(self, x):  # :930-946
+        x = self.patch_embed(x)
+        if self.config.ape:
+            x = x + self.absolute_pos_embed
+        x = self.pos_drop(x)
+        x_downsample = []
+        for layer in self.layers:
+            x_downsample.append(x)
+            x = layer(x)
+        return self.norm(x), x_downsample
+
+    def forward(self, x):  # :948-955
+        x, x_downsample = self.forward_features(x)
+        return self.decoder(x, x_downsample)

@@ -1,0 +1,140 @@
+"""torch.autograd.Function wrappers around the C-ABI device kernels.
+
+PyTorch is only the plumbing here (device memory, streams, autograd graph); every op below
+launches hand-written CUDA from libhealswin_b200 on torch's current stream and raises if the
+tensors are not on a CUDA device.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, lib, ptr, require_cuda
+
+
+class _Stats:
+    """Launch accounting for bench.py: how many of this library's kernels were launched, and
+    (when ``timing`` is on) CUDA-event pairs around named launches on the launching stream."""
+
+    def __init__(self):
+        self.launches = 0
+        self.timing = False
+        self.events = {}
+
+    def reset(self):
+        self.launches = 0
+        self.events = {}
+
+    def launch(self, name, fn, *args, tag=None):
+        self.launches += 1
+        if self.timing and tag is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            check(fn(*args))
+            b.record()
+            self.events.setdefault((name, tag), []).append((a, b))
+        else:
+            check(fn(*args))
+
+    def elapsed_ms(self):
+        """{(name, tag): [ms, ...]} -- call after torch.cuda.synchronize()."""
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.events.items()}
+
+
+STATS = _Stats()
+
+
+def _f32c(t):
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class GatherRows(torch.autograd.Function):
+    """out[b, p] = x[b, idx[p]] (shifter.shift / shift_back); backward gathers with the inverse."""
+
+    @staticmethod
+    def forward(ctx, x, idx_i32, inv_i32):
+        require_cuda(x, idx_i32)
+        x = _f32c(x)
+        B, N, Cc = x.shape
+        out = torch.empty_like(x)
+        STATS.launch("gather_rows", lib.hs_gather_rows, ptr(x), ptr(idx_i32), ptr(out), B, N, Cc, current_stream())
+        ctx.inv = inv_i32
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _f32c(g)
+        B, N, Cc = g.shape
+        out = torch.empty_like(g)
+        STATS.launch("gather_rows", lib.hs_gather_rows, ptr(g), ptr(ctx.inv), ptr(out), B, N, Cc, current_stream())
+        return out, None, None
+
+
+class WindowAttnCore(torch.autograd.Function):
+    """shift -> window_partition -> softmax(q k^T [cos] + bias + mask) v -> window_reverse -> shift_back
+    on a packed (B, N, 3C) qkv tensor (swin_hp_transformer.py:136-171, 319-330)."""
+
+    @staticmethod
+    def forward(ctx, qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
+                scale, num_heads, window_size, use_cos):
+        require_cuda(qkv)
+        qkv = _f32c(qkv)
+        B, N, C3 = qkv.shape
+        Cc = C3 // 3
+        H, ws = int(num_heads), int(window_size)
+        stream = current_stream()
+        bias = None
+        if bias_table is not None:
+            table = _f32c(bias_table)
+            T = table.shape[0]
+            assert rel_index_i32.numel() == ws * ws, (
+                f"relative position index is {tuple(rel_index_i32.shape)} but the window has {ws} tokens"
+            )
+            bias = torch.empty((H, ws, ws), device=qkv.device, dtype=torch.float32)
+            STATS.launch("rel_bias_expand", lib.hs_rel_bias_expand, ptr(table), ptr(rel_index_i32), ptr(bias), T, H, ws, stream)
+        ls = _f32c(logit_scale.reshape(-1)) if (use_cos and logit_scale is not None) else None
+        mask = _f32c(dense_mask) if dense_mask is not None else None
+        out = torch.empty((B, N, Cc), device=qkv.device, dtype=torch.float32)
+        flags = _lib.ATTN_COS if use_cos else 0
+        STATS.launch("window_attn_fwd", lib.hs_window_attn_fwd, ptr(qkv), ptr(src), ptr(groups), ptr(mask), ptr(bias),
+                     ptr(ls), C.c_float(scale), ptr(out), B, N, Cc, H, ws, flags, stream, tag=(B, N, Cc, H, ws))
+        ctx.save_for_backward(qkv, bias, ls, src, groups, mask, rel_index_i32)
+        ctx.meta = (scale, H, ws, flags, bias_table is not None,
+                    None if bias_table is None else tuple(bias_table.shape),
+                    None if logit_scale is None else tuple(logit_scale.shape))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, bias, ls, src, groups, mask, rel_index = ctx.saved_tensors
+        scale, H, ws, flags, has_table, table_shape, ls_shape = ctx.meta
+        dout = _f32c(dout)
+        B, N, C3 = qkv.shape
+        Cc = C3 // 3
+        stream = current_stream()
+        dqkv = torch.empty_like(qkv)
+        need_table = has_table and ctx.needs_input_grad[1]
+        need_ls = (ls is not None) and ctx.needs_input_grad[2]
+        dbias = torch.zeros((H, ws, ws), device=qkv.device, dtype=torch.float32) if need_table else None
+        dls = torch.zeros((H,), device=qkv.device, dtype=torch.float32) if need_ls else None
+        STATS.launch("window_attn_bwd", lib.hs_window_attn_bwd, ptr(qkv), ptr(dout), ptr(src), ptr(groups), ptr(mask),
+                     ptr(bias), ptr(ls), C.c_float(scale), ptr(dqkv), ptr(dbias), ptr(dls), B, N, Cc, H, ws,
+                     flags, stream, tag=(B, N, Cc, H, ws))
+        dtable = None
+        if need_table:
+            dtable = torch.zeros(table_shape, device=qkv.device, dtype=torch.float32)
+            STATS.launch("rel_bias_reduce", lib.hs_rel_bias_reduce, ptr(dbias), ptr(rel_index), ptr(dtable),
+                         table_shape[0], H, ws, stream)
+        if need_ls:
+            dls = dls.reshape(ls_shape)
+        return dqkv, dtable, dls, None, None, None, None, None, None, None, None
+
+
+def window_attention_core(qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
+                          scale, num_heads, window_size, use_cos):
+    return WindowAttnCore.apply(qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
+                                float(scale), num_heads, window_size, bool(use_cos))

@@ -1,0 +1,127 @@
+/*
+ * healswin_b200 -- C ABI of the B200-native HEAL-SWIN hot path.
+ *
+ * The reference (JanEGerken/HEAL-SWIN) has no FFI: its boundary for this path is
+ * the Python module surface heal_swin.models_torch.{hp_windowing,hp_shifting,
+ * swin_hp_transformer}.  This header is what a binding for that
+ * boundary binds to; every entry point cites the reference code it replaces.
+ * heal_swin_b200/_lib.py is the ctypes binding; INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from hs_last_error() (thread-local, never NULL).  Nothing calls
+ *     exit()/abort().
+ *   - "host" pointers are plain CPU memory, "dev" pointers are CUDA device memory of
+ *     the current device.  All device entry points take the CUDA stream explicitly
+ *     (cudaStream_t passed as void*), keep no mutable global state and are
+ *     re-entrant (forward runs on the main thread, backward on the autograd thread).
+ *   - tensors are dense row-major fp32 unless said otherwise.
+ */
+#ifndef HEALSWIN_B200_H
+#define HEALSWIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HS_OK 0
+#define HS_ERR_ARG 1      /* bad argument: the Python shim raises AssertionError  */
+#define HS_ERR_CUDA 2     /* CUDA runtime / launch failure: RuntimeError          */
+#define HS_ERR_UNSUPPORTED 3 /* shape outside what the kernels implement: RuntimeError */
+
+/* shift strategies, swin_hp_transformer.py:277-304 */
+#define HS_SHIFT_NONE 0       /* hp_shifting.NoShift           hp_shifting.py:31-39   */
+#define HS_SHIFT_NEST_ROLL 1  /* hp_shifting.NestRollShift     hp_shifting.py:42-73   */
+#define HS_SHIFT_NEST_GRID 2  /* hp_shifting.NestGridShift     hp_shifting.py:76-306  */
+#define HS_SHIFT_RING 3       /* hp_shifting.RingShift         hp_shifting.py:309-404 */
+
+/* flags of the attention kernels */
+#define HS_ATTN_COS 1u /* cosine attention, swin_hp_transformer.py:142-147 */
+
+const char* hs_last_error(void);
+int hs_version(void);
+/* 0 when the current CUDA device is sm_100 (B200); fills name (may be NULL) */
+int hs_device_info(int* sm_major, int* sm_minor, int* num_sms, char* name, int name_len);
+
+/* ------------------------------------------------------------------ index layer (host) */
+
+/* hp_windowing.get_nest_win_idcs, hp_windowing.py:43-62.  out: S*S int64, S = floor(sqrt(ws)) */
+int hs_nest_win_idcs(int window_size, int64_t* out_host);
+/* WindowAttention.relative_position_index buffer, swin_hp_transformer.py:98-114. out: ws*ws int64 */
+int hs_rel_pos_index(int window_size, int64_t* out_host);
+/* healpy.pixelfunc.nest2ring / ring2nest as called at hp_shifting.py:329,333 */
+int hs_nest2ring(int64_t nside, const int64_t* in_host, int64_t* out_host, int64_t n);
+int hs_ring2nest(int64_t nside, const int64_t* in_host, int64_t* out_host, int64_t n);
+/*
+ * Shifter tables for one block, swin_hp_transformer.py:271-308 + hp_shifting.py.
+ *   shift_idcs[p]  : shifted[p] = x[shift_idcs[p]]        (NestGridShift/RingShift.shift_idcs; roll closed form)
+ *   back_idcs[p]   : x'[p] = shifted'[back_idcs[p]]       (back_shift_idcs = argsort(shift_idcs))
+ *   groups[p]      : mask group id of shifted pixel p     (get_mask(get_attn_mask=False))
+ * N = base_pix * nside^2 entries each; any output may be NULL.  nside is the nside of the
+ * *current* resolution (sqrt(input_resolution / base_pix), swin_hp_transformer.py:272).
+ */
+int hs_shift_tables(int strategy, int64_t nside, int base_pix, int window_size, int shift_size,
+                    int64_t* shift_idcs_host, int64_t* back_idcs_host, int8_t* groups_host);
+/* hp_shifting.get_attn_mask_from_mask, hp_shifting.py:10-28: (N,) ids -> (N/ws, ws, ws) in {0,-100} */
+int hs_attn_mask_from_groups(const int8_t* groups_host, int64_t N, int window_size, float* mask_host);
+
+/* ------------------------------------------------------------------ device kernels */
+
+/*
+ * Row gather out[b][p][:] = x[b][idx[p]][:], x/out (B, N, C) fp32, idx (N) int32: the standalone form
+ * of shifter.shift (idx = shift_idcs) / shifter.shift_back (idx = back_shift_idcs),
+ * hp_shifting.py:69-73, 302-306, 400-404.  Bit-exact (pure data movement).
+ */
+int hs_gather_rows(const float* x_dev, const int32_t* idx_dev, float* out_dev, int B, int64_t N, int C,
+                   void* stream);
+
+/*
+ * Relative-position bias, swin_hp_transformer.py:152-159:
+ *   bias[h][i][j] = table[index[i][j]][h]           table: (T, H) fp32, index: (ws*ws) int32, bias: (H, ws, ws)
+ * and its adjoint dtable[t][h] += sum_{index[i][j]==t} dbias[h][i][j]  (dtable must be zero-filled or hold
+ * the running gradient).
+ */
+int hs_rel_bias_expand(const float* table_dev, const int32_t* index_dev, float* bias_dev,
+                       int T, int H, int ws, void* stream);
+int hs_rel_bias_reduce(const float* dbias_dev, const int32_t* index_dev, float* dtable_dev,
+                       int T, int H, int ws, void* stream);
+
+/*
+ * Windowed (shifted) multi-head self-attention core with the HEALPix shift, window
+ * partition and window reverse folded into its loads and stores.  Replaces, in one kernel,
+ * shifter.shift -> window_partition -> WindowAttention.forward[:142-171] -> window_reverse ->
+ * shifter.shift_back (swin_hp_transformer.py:319-330, 136-171; hp_windowing.py:6-40;
+ * hp_shifting.py:69-73, 302-306, 400-404).
+ *
+ *   qkv   (B, N, 3*C)   output of the qkv Linear on the UNSHIFTED token order; row layout [3][H][D]
+ *   src   (N) int32     window w, slot j holds token src[w*ws + j] (shift_idcs); NULL = identity.
+ *                       The output row of that slot is written back to the same token, which is
+ *                       exactly shift_back o window_reverse.
+ *   groups (N) uint8    mask group id per *shifted* slot, NULL = no mask.  logits get -100 where ids differ
+ *   mask  (nW, ws, ws)  optional dense additive mask (WindowAttention.forward(x, mask) API), may be NULL
+ *   bias  (H, ws, ws)   expanded relative position bias or NULL
+ *   logit_scale (H)     raw parameter (cos attention: logits *= exp(min(ls, log 100))); else NULL
+ *   scale               q scaling for the non-cos path (head_dim^-0.5 or qk_scale)
+ *   out   (B, N, C)     attention output in the UNSHIFTED token order, row layout [H][D]
+ */
+int hs_window_attn_fwd(const float* qkv_dev, const int32_t* src_dev, const uint8_t* groups_dev,
+                       const float* mask_dev, const float* bias_dev, const float* logit_scale_dev,
+                       float scale, float* out_dev, int B, int64_t N, int C, int H, int ws,
+                       uint32_t flags, void* stream);
+/*
+ * Adjoint of hs_window_attn_fwd.  dqkv (B, N, 3C) is fully overwritten.  dbias (H, ws, ws) and
+ * dlogit_scale (H) are accumulated into (+=), either may be NULL.
+ */
+int hs_window_attn_bwd(const float* qkv_dev, const float* dout_dev, const int32_t* src_dev,
+                       const uint8_t* groups_dev, const float* mask_dev, const float* bias_dev,
+                       const float* logit_scale_dev, float scale, float* dqkv_dev, float* dbias_dev,
+                       float* dlogit_scale_dev, int B, int64_t N, int C, int H, int ws,
+                       uint32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEALSWIN_B200_H */
