@@ -7,6 +7,9 @@ extern "C" {
 int hs_window_attn_fwd(const float* qkv, const int32_t* src, const uint8_t* groups, const float* mask,
                        const float* bias, const float* logit_scale, float scale, float* out, int B,
                        int64_t N, int C, int H, int ws, uint32_t flags, void* stream) {
+  if (!(flags & HS_ATTN_NO_TC) && hs::window_attn_tc_supported(qkv, out, mask, B, N, C, H, ws))
+    return hs::window_attn_fwd_tc(qkv, src, groups, bias, logit_scale, scale, out, B, N, C, H, flags,
+                                  (cudaStream_t)stream);
   return hs::window_attn_fwd_simt(qkv, src, groups, mask, bias, logit_scale, scale, out, B, N, C, H, ws,
                                   flags, (cudaStream_t)stream);
 }

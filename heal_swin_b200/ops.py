@@ -5,6 +5,7 @@ launches hand-written CUDA from libhealswin_b200 on torch's current stream and r
 tensors are not on a CUDA device.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -42,6 +43,21 @@ class _Stats:
 
 
 STATS = _Stats()
+
+# Precision of the attention matmuls (q k^T and p v).  "tf32": tcgen05 tensor-core kernels, TF32 operands with
+# fp32 accumulation (what torch.backends.cuda.matmul.allow_tf32 gives the reference's q @ k^T / attn @ v on GPU);
+# "fp32": exact-fp32 CUDA-core kernels (also used automatically for shapes the tensor-core kernels do not cover).
+_ATTN_PRECISION = os.environ.get("HEALSWIN_ATTN_PRECISION", "tf32")
+
+
+def set_attention_precision(mode: str) -> None:
+    global _ATTN_PRECISION
+    assert mode in ("tf32", "fp32"), mode
+    _ATTN_PRECISION = mode
+
+
+def get_attention_precision() -> str:
+    return _ATTN_PRECISION
 
 
 def _f32c(t):
@@ -99,7 +115,7 @@ class WindowAttnCore(torch.autograd.Function):
         ls = _f32c(logit_scale.reshape(-1)) if (use_cos and logit_scale is not None) else None
         mask = _f32c(dense_mask) if dense_mask is not None else None
         out = torch.empty((B, N, Cc), device=qkv.device, dtype=torch.float32)
-        flags = _lib.ATTN_COS if use_cos else 0
+        flags = (_lib.ATTN_COS if use_cos else 0) | (_lib.ATTN_NO_TC if _ATTN_PRECISION == "fp32" else 0)
         STATS.launch("window_attn_fwd", lib.hs_window_attn_fwd, ptr(qkv), ptr(src), ptr(groups), ptr(mask), ptr(bias),
                      ptr(ls), C.c_float(scale), ptr(out), B, N, Cc, H, ws, flags, stream, tag=(B, N, Cc, H, ws))
         ctx.save_for_backward(qkv, bias, ls, src, groups, mask, rel_index_i32)

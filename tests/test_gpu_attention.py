@@ -15,6 +15,17 @@ FWD_TOL = 2e-5
 BWD_TOL = 1e-4
 
 
+@pytest.fixture(autouse=True)
+def _exact_fp32_kernels():
+    """This file checks the exact-fp32 CUDA-core kernels (tolerances are reduction-order only); the
+    tcgen05 TF32 kernels have their own file (test_gpu_attention_tc.py) with the TF32 tolerance."""
+    from heal_swin_b200 import ops
+
+    ops.set_attention_precision("fp32")
+    yield
+    ops.set_attention_precision("tf32")
+
+
 def _device():
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     return torch.device("cuda:0")
