@@ -14,6 +14,7 @@ HS_OK, HS_ERR_ARG, HS_ERR_CUDA, HS_ERR_UNSUPPORTED = 0, 1, 2, 3
 SHIFT_NONE, SHIFT_NEST_ROLL, SHIFT_NEST_GRID, SHIFT_RING = 0, 1, 2, 3
 ATTN_COS = 1
 ATTN_NO_TC = 2
+ATTN_NO_TRUNC_COMP = 4
 
 STRATEGY_CODES = {"nest_roll": SHIFT_NEST_ROLL, "nest_grid_shift": SHIFT_NEST_GRID, "ring_shift": SHIFT_RING}
 

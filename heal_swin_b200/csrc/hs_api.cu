@@ -18,6 +18,10 @@ int hs_window_attn_bwd(const float* qkv, const float* dout, const int32_t* src, 
                        const float* mask, const float* bias, const float* logit_scale, float scale,
                        float* dqkv, float* dbias, float* dlogit_scale, int B, int64_t N, int C, int H,
                        int ws, uint32_t flags, void* stream) {
+  if (!(flags & HS_ATTN_NO_TC) && hs::window_attn_tc_supported(qkv, dqkv, mask, B, N, C, H, ws) &&
+      !(reinterpret_cast<uintptr_t>(dout) & 15))
+    return hs::window_attn_bwd_tc(qkv, dout, src, groups, bias, logit_scale, scale, dqkv, dbias, dlogit_scale, B, N,
+                                  C, H, flags, (cudaStream_t)stream);
   return hs::window_attn_bwd_simt(qkv, dout, src, groups, mask, bias, logit_scale, scale, dqkv, dbias,
                                   dlogit_scale, B, N, C, H, ws, flags, (cudaStream_t)stream);
 }

@@ -20,24 +20,17 @@
 #include "hs_common.h"
 #include "hs_kernels.h"
 #include "hs_sm100.cuh"
+#include "hs_tc_common.cuh"
 
 namespace {
 
 using namespace hs::sm100;
+using namespace hs::tc;
 
-constexpr int kWS = 64;
-constexpr int kD = 32;
-constexpr int kTile = kWS * kD * 4;  // 8192 B: one q / k / v / o tile of a unit
 constexpr int kSlots = 3;            // smem ring depth (pairs)
 constexpr int kStageCols = 192;      // TMEM columns per stage: S/P 128 + O 2 x 32
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 384;  // 3 warpgroups: 2 x softmax/epilogue, 1 x {producer, MMA, 2 idle warps}
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLogitScaleMax = 4.605170185988092f;  // log(1/0.01), swin_hp_transformer.py:144-146
-constexpr float kNormEps = 1e-12f;                    // F.normalize eps
-constexpr float kMaskFill = -100.0f;                  // hp_shifting.py:25
-
-constexpr int kFlagContig = 1, kFlagUniform = 2, kFlagValid = 4;
 
 struct SlotMeta {
   int rows[2][kWS];        // global row (b * N + token) of every slot of the two units
@@ -66,15 +59,12 @@ struct TcArgs {
   const float* bias;         // (H, 64, 64) or null
   const float* logit_scale;  // (H) or null
   float scale;
+  float fix1, fix2;  // TF32 truncation compensation (hs_tc_common.cuh), 1.0 when disabled
   int B, nW, C, H, cos;
   long long N;
   int total;  // B * nW units per head
 };
 
-__device__ __forceinline__ uint32_t sw128_off(int r, int c16) { return (uint32_t)(r * 128 + ((c16 ^ (r & 7)) << 4)); }
-__device__ __forceinline__ uint32_t sw128b32_off(int r, int c16) {
-  return (uint32_t)(r * 128 + ((((c16 >> 1) ^ (r & 3)) << 5) | ((c16 & 1) << 4)));
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
@@ -260,7 +250,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
 #pragma unroll
       for (int j = 0; j < kWS; ++j) bias_r[j] = 0.f;
     }
-    const float base_scale = (a.cos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale) * kLog2e;
+    const float base_scale = (a.cos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale) * kLog2e * a.fix2;
     bool store_pending = false;
 
     int n = 0;
@@ -350,7 +340,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
       tc_fence_before();
       mbar_arrive(&S.stage_free[wg]);
 
-      const float inv = 1.0f / sum;
+      const float inv = a.fix1 / sum;
       if (flags & kFlagValid) {
         if (flags & kFlagContig) {
           // stage the tile (128B swizzle) and let one thread write it back with a TMA store
@@ -398,41 +388,6 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-
-// 2-D fp32 tensor (rows x cols, row stride ld floats) with a (32 col x 64 row) box
-int make_map(CUtensorMap* m, const float* base, long long rows, int cols, CUtensorMapSwizzle sw) {
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
-  cuuint32_t box[2] = {kD, kWS};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-  return HS_OK;
-}
-
-int sm_count() {
-  int dev = 0, n = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  return n > 0 ? n : 148;
-}
-
 }  // namespace
 
 namespace hs {
@@ -459,6 +414,8 @@ int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* grou
   a.qkv = qkv; a.out = out; a.src = src; a.groups = groups; a.bias = bias; a.logit_scale = logit_scale;
   a.scale = scale; a.B = B; a.nW = (int)(N / kWS); a.C = C; a.H = H; a.cos = (flags & HS_ATTN_COS) ? 1 : 0;
   a.N = N; a.total = B * a.nW;
+  a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix1;
+  a.fix2 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix2;
   const int npairs = (a.total + 1) / 2;
   const size_t smem = sizeof(Smem) + 1024;
   static bool attr_done = false;  // benign race: the attribute is idempotent

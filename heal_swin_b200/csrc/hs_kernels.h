@@ -20,4 +20,8 @@ int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* grou
                        const float* logit_scale, float scale, float* out, int B, int64_t N, int C, int H,
                        uint32_t flags, cudaStream_t stream);
 
+int window_attn_bwd_tc(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
+                       const float* bias, const float* logit_scale, float scale, float* dqkv, float* dbias,
+                       float* dlogit, int B, int64_t N, int C, int H, uint32_t flags, cudaStream_t stream);
+
 }  // namespace hs

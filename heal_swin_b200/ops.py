@@ -115,7 +115,8 @@ class WindowAttnCore(torch.autograd.Function):
         ls = _f32c(logit_scale.reshape(-1)) if (use_cos and logit_scale is not None) else None
         mask = _f32c(dense_mask) if dense_mask is not None else None
         out = torch.empty((B, N, Cc), device=qkv.device, dtype=torch.float32)
-        flags = (_lib.ATTN_COS if use_cos else 0) | (_lib.ATTN_NO_TC if _ATTN_PRECISION == "fp32" else 0)
+        flags = ((_lib.ATTN_COS if use_cos else 0) | (_lib.ATTN_NO_TC if _ATTN_PRECISION == "fp32" else 0)
+                 | (_lib.ATTN_NO_TRUNC_COMP if os.environ.get("HEALSWIN_NO_TRUNC_COMP") == "1" else 0))
         STATS.launch("window_attn_fwd", lib.hs_window_attn_fwd, ptr(qkv), ptr(src), ptr(groups), ptr(mask), ptr(bias),
                      ptr(ls), C.c_float(scale), ptr(out), B, N, Cc, H, ws, flags, stream, tag=(B, N, Cc, H, ws))
         ctx.save_for_backward(qkv, bias, ls, src, groups, mask, rel_index_i32)

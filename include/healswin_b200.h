@@ -41,6 +41,7 @@ extern "C" {
 /* flags of the attention kernels */
 #define HS_ATTN_COS 1u /* cosine attention, swin_hp_transformer.py:142-147 */
 #define HS_ATTN_NO_TC 2u /* force the exact-fp32 CUDA-core kernels (cross-check of the tcgen05 TF32 path) */
+#define HS_ATTN_NO_TRUNC_COMP 4u /* tcgen05 path: do not compensate the mean TF32 operand-truncation shrink (diagnostics) */
 
 const char* hs_last_error(void);
 int hs_version(void);

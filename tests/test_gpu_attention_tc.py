@@ -10,12 +10,13 @@ import pytest
 import torch
 
 from oracle import hp_oracle as O
-from scripts.tc_check import run_case
+from scripts.tc_check import run_case, run_case_bwd
 from tests.util import rel_err
 
 pytestmark = pytest.mark.gpu
 
 TC_TOL = 2e-3
+BWD_TC_TOL = 3e-3  # gradients: TF32 operands in five chained products (S, dP, dV, dQ, dK)
 
 CASES = [
     (1, 4, 8, 1, "none", False, False),
@@ -33,6 +34,38 @@ CASES = [
 def test_tc_forward_matches_exact_fp32_kernels(case):
     err, _ = run_case(*case, torch.device("cuda:0"))
     assert err < TC_TOL, err
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"B{c[0]}-ns{c[1]}-bp{c[2]}-H{c[3]}-{c[4]}-cos{int(c[5])}-bias{int(c[6])}")
+def test_tc_backward_matches_exact_fp32_kernels(case):
+    """dqkv, d(relative_position_bias_table), d(logit_scale) of the tcgen05 backward vs the fp32 CUDA-core backward."""
+    errs = run_case_bwd(*case, torch.device("cuda:0"))
+    for k, e in errs.items():
+        # d(logit_scale) is one scalar per head: a sum of dS * cos over all windows whose terms largely cancel, so the
+        # TF32 noise of S is amplified relative to the (small) total
+        assert e < (1e-2 if k == "dlogit_scale" else BWD_TC_TOL), (k, e)
+
+
+def test_tc_backward_full_size_linearity_property():
+    """BASELINE configs[1] stage-0 size.  The backward is linear in dO: bwd(a*dO1 + dO2) == a*bwd(dO1) + bwd(dO2)
+    (size-independent property; exercises every window / head of the full-size launch)."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    B, N, C, H, ws = 8, 12 * 128 * 128, 96, 3, 64
+    g = torch.Generator().manual_seed(3)
+    qkv = torch.randn(2, N, 3 * C, generator=g).to(dev).repeat(B // 2, 1, 1).requires_grad_(True)
+    out = ops.window_attention_core(qkv, None, None, None, None, None, None, 32 ** -0.5, H, ws, False)
+    d1 = torch.randn(B, N, C, device=dev)
+    d2 = torch.randn(B, N, C, device=dev)
+    g1, = torch.autograd.grad(out, qkv, d1, retain_graph=True)
+    g2, = torch.autograd.grad(out, qkv, d2, retain_graph=True)
+    g12, = torch.autograd.grad(out, qkv, 0.5 * d1 + d2, retain_graph=True)
+    assert rel_err((0.5 * g1 + g2).cpu(), g12.cpu()) < BWD_TC_TOL
+    # and samples b, b+2 of the repeated batch see identical q, k, v: identical dO must give identical gradients
+    d3 = d1[:2].repeat(B // 2, 1, 1)
+    g3, = torch.autograd.grad(out, qkv, d3)
+    assert torch.equal(g3[0], g3[2]) and torch.equal(g3[1], g3[7])
 
 
 def test_tc_forward_vs_oracle_through_the_block():
