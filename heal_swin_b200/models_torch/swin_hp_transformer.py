@@ -170,20 +170,28 @@ class SwinTransformerBlock(nn.Module):
         assert N == self.input_resolution, f"got {N} tokens, block was built for {self.input_resolution}"
         shortcut = x
         if not self.use_v2_norm_placement:
-            x = self.norm1(x)
+            x = ops.layer_norm(x, self.norm1)
         # shift + partition + W-MSA/SW-MSA + reverse + shift back, one kernel chain   [:319-330]
         x = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups)
-        if self.use_v2_norm_placement:  # :333-338
-            x = shortcut + self.drop_path(self.norm1(x))
-            x = x + self.drop_path(self.norm2(self.mlp(x)))
-        else:
-            x = shortcut + self.drop_path(x)
-            x = x + self.drop_path(self.mlp(self.norm2(x)))
-        return x
+        return _residual_tail(self, shortcut, x)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"
                 f" window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
+
+
+def _residual_tail(blk, shortcut, x):
+    """The two residual branches after the attention   [swin_hp_transformer.py:333-338 / swin_transformer.py:394-401].
+    Without stochastic depth (drop_path == 0 or eval) ``shortcut + norm(x)`` is one fused LayerNorm+add launch."""
+    plain = isinstance(blk.drop_path, nn.Identity) or not blk.training
+    if blk.use_v2_norm_placement:
+        if plain:
+            x = ops.layer_norm(x, blk.norm1, residual=shortcut)
+            return ops.layer_norm(blk.mlp(x), blk.norm2, residual=x)
+        x = shortcut + blk.drop_path(ops.layer_norm(x, blk.norm1))
+        return x + blk.drop_path(ops.layer_norm(blk.mlp(x), blk.norm2))
+    x = shortcut + blk.drop_path(x)
+    return x + blk.drop_path(blk.mlp(ops.layer_norm(x, blk.norm2)))
 
 
 SwinHPTransformerBlock = SwinTransformerBlock  # the name BASELINE.json uses
@@ -203,7 +211,7 @@ class PatchMerging(nn.Module):
         assert N % 4 == 0, f"x size {N} is not divisible by 4 as necessary for patching."
         # cat(x[:,0::4], ..., x[:,3::4]) on the channel axis is a plain view in nested order
         x = x.contiguous().view(B, N // 4, 4 * C)
-        return self.reduction(self.norm(x))
+        return self.reduction(ops.layer_norm(x, self.norm))
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}"
@@ -224,7 +232,7 @@ class PatchExpand(nn.Module):
     def forward(self, x):
         x = self.expand(x)
         B, N, C = x.shape
-        return self.norm(x.contiguous().view(B, 4 * N, C // 4))
+        return ops.layer_norm(x.contiguous().view(B, 4 * N, C // 4), self.norm)
 
 
 PatchExpanding = PatchExpand  # the name BASELINE.json uses
@@ -244,7 +252,7 @@ class FinalPatchExpand_X4(nn.Module):
     def forward(self, x):
         x = self.expand(x)
         B, N, C = x.shape
-        return self.norm(x.contiguous().view(B, N * self.patch_size, C // self.patch_size))
+        return ops.layer_norm(x.contiguous().view(B, N * self.patch_size, C // self.patch_size), self.norm)
 
 
 def _make_blocks(dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size, shift_strategy,
@@ -375,7 +383,7 @@ class UnetDecoder(nn.Module):
                 x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
                 x = self.concat_back_dim[inx](x)
             x = layer_up(x)
-        x = self.up(self.norm_up(x))
+        x = self.up(ops.layer_norm(x, self.norm_up))
         return self.output(x.permute(0, 2, 1))
 
 
@@ -471,7 +479,7 @@ class SwinHPTransformerSys(nn.Module):
         for layer in self.layers:
             x_downsample.append(x)
             x = layer(x)
-        return self.norm(x), x_downsample
+        return ops.layer_norm(x, self.norm), x_downsample
 
     def forward(self, x):  # :948-955
         x, x_downsample = self.forward_features(x)

@@ -22,7 +22,7 @@ import torch.utils.checkpoint as checkpoint
 
 from .. import hp_index, ops
 from ..data_spec import DataSpec
-from .swin_hp_transformer import DropPath, Mlp  # identical in both reference files
+from .swin_hp_transformer import DropPath, Mlp, _residual_tail  # identical in both reference files
 
 
 def _pair(v):
@@ -214,17 +214,11 @@ class SwinTransformerBlock(nn.Module):
         assert L == H * W, "input feature has wrong size"
         shortcut = x
         if not self.use_v2_norm_placement:
-            x = self.norm1(x)
+            x = ops.layer_norm(x, self.norm1)
         x = self.attn.forward_tokens(x, self.window_size[0] * self.window_size[1], self._hs_src, self._hs_groups)
         if self.fixup is not None:
             x = self.fixup(x)
-        if self.use_v2_norm_placement:
-            x = shortcut + self.drop_path(self.norm1(x))
-            x = x + self.drop_path(self.norm2(self.mlp(x)))
-        else:
-            x = shortcut + self.drop_path(x)
-            x = x + self.drop_path(self.mlp(self.norm2(x)))
-        return x
+        return _residual_tail(self, shortcut, x)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"
@@ -254,7 +248,7 @@ class PatchMerging(nn.Module):
         assert L == H * W, "input feature has wrong size"
         assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
         x = self.gather(x).view(B, L // 4, 4 * C)
-        return self.reduction(self.norm(x))
+        return self.reduction(ops.layer_norm(x, self.norm))
 
     def extra_repr(self) -> str:
         return f"input_resolution={self.input_resolution}, dim={self.dim}"
@@ -285,7 +279,7 @@ class PatchExpand(nn.Module):
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
         x = self.shuffle(x.contiguous().view(B, L * 4, C // self.dim_scale))
-        return self.norm(x)
+        return ops.layer_norm(x, self.norm)
 
 
 class FinalPatchExpand_X4(nn.Module):
@@ -309,7 +303,7 @@ class FinalPatchExpand_X4(nn.Module):
         assert L == H * W, "input feature has wrong size"
         pp = self.patch_size[0] * self.patch_size[1]
         x = self.shuffle(x.contiguous().view(B, L * pp, C // pp))
-        return self.norm(x)
+        return ops.layer_norm(x, self.norm)
 
 
 def _make_blocks(dim, input_resolution, depth, num_heads, window_size, shift_size, mlp_ratio, qkv_bias, qk_scale, drop,
@@ -526,7 +520,7 @@ class SwinTransformerSys(nn.Module):
         for layer in self.layers:
             x_downsample.append(x)
             x = layer(x)
-        return self.norm(x), x_downsample
+        return ops.layer_norm(x, self.norm), x_downsample
 
     def forward_up_features(self, x, x_downsample):
         for inx, layer_up in enumerate(self.layers_up):
@@ -534,7 +528,7 @@ class SwinTransformerSys(nn.Module):
                 x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
                 x = self.concat_back_dim[inx](x)
             x = layer_up(x)
-        return self.norm_up(x)
+        return ops.layer_norm(x, self.norm_up)
 
     def up_x4(self, x):
         H, W = self.patches_resolution

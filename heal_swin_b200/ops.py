@@ -155,3 +155,50 @@ def window_attention_core(qkv, bias_table, logit_scale, src, groups, dense_mask,
                           scale, num_heads, window_size, use_cos):
     return WindowAttnCore.apply(qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
                                 float(scale), num_heads, window_size, bool(use_cos))
+
+
+class LayerNormFn(torch.autograd.Function):
+    """y = residual + LayerNorm(x) * weight + bias over the last dim (residual optional), csrc/hs_layernorm.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, eps):
+        require_cuda(x, weight, bias, residual)
+        shape = x.shape
+        Cc = shape[-1]
+        x2 = _f32c(x).reshape(-1, Cc)
+        rows = x2.shape[0]
+        w, b = _f32c(weight), _f32c(bias)
+        res2 = _f32c(residual).reshape(-1, Cc) if residual is not None else None
+        y = torch.empty_like(x2)
+        mean = torch.empty(rows, device=x2.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x2.device, dtype=torch.float32)
+        STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), ptr(res2), ptr(w), ptr(b), ptr(y), ptr(mean),
+                     ptr(rstd), rows, Cc, C.c_float(eps), current_stream(), tag=(rows, Cc))
+        ctx.save_for_backward(x2, w, mean, rstd)
+        ctx.has_res = residual is not None
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mean, rstd = ctx.saved_tensors
+        rows, Cc = x2.shape
+        dy2 = _f32c(dy).reshape(rows, Cc)
+        dx = torch.empty_like(x2)
+        need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dw = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_w else None
+        db = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_b else None
+        STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(x2), ptr(mean), ptr(rstd), ptr(w), ptr(dx),
+                     ptr(dw), ptr(db), rows, Cc, current_stream(), tag=(rows, Cc))
+        dres = dy if ctx.has_res else None
+        return dx.view(ctx.shape), dw, db, dres, None
+
+
+def layer_norm(x, norm, residual=None):
+    """``residual + norm(x)`` for an ``nn.LayerNorm`` module ``norm`` (affine, normalising the last dim) in one
+    launch; any other norm layer is applied as the module it is."""
+    if (isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == x.shape[-1]):
+        return LayerNormFn.apply(x, norm.weight, norm.bias, residual, float(norm.eps))
+    y = norm(x)
+    return y if residual is None else residual + y

@@ -123,6 +123,24 @@ int hs_window_attn_bwd(const float* qkv_dev, const float* dout_dev, const int32_
                        float* dlogit_scale_dev, int B, int64_t N, int C, int H, int ws,
                        uint32_t flags, void* stream);
 
+/*
+ * Row LayerNorm over the last dimension, optionally fused with the residual add of the v2 norm placement:
+ *     y = residual + LayerNorm(x) * gamma + beta            (residual may be NULL)
+ * Replaces nn.LayerNorm at swin_hp_transformer.py:316, 333-338 (norm1 / norm2, with "shortcut + norm(...)" in one
+ * pass), :392 (PatchMerging.norm, 4C), :428 (PatchExpand.norm, C/2), :450 (FinalPatchExpand_X4.norm), :781, :945.
+ * x, residual, y: (rows, C) fp32; mean, rstd: (rows) fp32 saved for the backward (both NULL = do not save).
+ * Statistics as torch: biased variance, rstd = 1/sqrt(var + eps).
+ */
+int hs_layernorm_fwd(const float* x_dev, const float* residual_dev, const float* gamma_dev, const float* beta_dev,
+                     float* y_dev, float* mean_dev, float* rstd_dev, int64_t rows, int C, float eps, void* stream);
+/*
+ * Adjoint: dx (rows, C) is overwritten; dgamma / dbeta (C) are accumulated into (+=), either may be NULL.
+ * (The gradient of the fused residual input is dy itself.)
+ */
+int hs_layernorm_bwd(const float* dy_dev, const float* x_dev, const float* mean_dev, const float* rstd_dev,
+                     const float* gamma_dev, float* dx_dev, float* dgamma_dev, float* dbeta_dev, int64_t rows, int C,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

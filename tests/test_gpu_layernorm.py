@@ -1,0 +1,79 @@
+"""GPU parity of the LayerNorm (+ fused residual) kernels through the C-ABI against torch's fp32 layer_norm
+(floating-point kernel: plain PyTorch fp32 reference) and against the reference-generated op fixtures.
+
+Tolerance: 1e-5 relative L2 forward, 1e-4 backward (fp32 everywhere; only the reduction order differs).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("C", [96, 192, 384, 768, 1536, 48, 24, 64, 16, 8, 2, 100])
+@pytest.mark.parametrize("rows,with_res", [(1001, True), (64, False), (3, True)])
+def test_layernorm_fwd_bwd_vs_torch(C, rows, with_res):
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C * 7 + rows)
+    x = (torch.randn(rows, C, generator=g) * 2 + 0.5).to(dev).requires_grad_(True)
+    res = torch.randn(rows, C, generator=g).to(dev).requires_grad_(True) if with_res else None
+    norm = torch.nn.LayerNorm(C).to(dev)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        norm.bias.copy_(0.2 * torch.randn(C, generator=g))
+    wgt = torch.randn(rows, C, generator=g).to(dev)
+
+    y = ops.layer_norm(x, norm, residual=res)
+    (y * wgt).sum().backward()
+    got = [y.detach(), x.grad.clone(), norm.weight.grad.clone(), norm.bias.grad.clone()]
+    if with_res:
+        got.append(res.grad.clone())
+
+    x2 = x.detach().clone().requires_grad_(True)
+    r2 = res.detach().clone().requires_grad_(True) if with_res else None
+    norm.weight.grad = norm.bias.grad = None
+    y2 = F.layer_norm(x2, (C,), norm.weight, norm.bias, norm.eps)
+    if with_res:
+        y2 = r2 + y2
+    (y2 * wgt).sum().backward()
+    want = [y2.detach(), x2.grad, norm.weight.grad, norm.bias.grad] + ([r2.grad] if with_res else [])
+    tols = [1e-5, 1e-4, 1e-4, 1e-4, 1e-6]
+    for i, (a, b, tol) in enumerate(zip(got, want, tols)):
+        if i == 1 and C == 2:
+            # C = 2: the normalised row is (+1, -1) whatever x is, so dx is pure cancellation (|dx| ~ 1e-4 |dy|);
+            # compare against the scale of the incoming gradient instead of the (vanishing) result
+            assert float((a - b).abs().max()) < 1e-5 * float(wgt.abs().max())
+            continue
+        assert rel_err(a.cpu(), b.cpu()) < tol
+
+
+def test_layernorm_keeps_leading_shape_and_3d_input():
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    x = torch.randn(2, 50, 96, device=dev)
+    norm = torch.nn.LayerNorm(96).to(dev)
+    y = ops.layer_norm(x, norm)
+    assert y.shape == x.shape
+    assert rel_err(y.cpu(), F.layer_norm(x, (96,), norm.weight, norm.bias, norm.eps).detach().cpu()) < 1e-5
+
+
+def test_layernorm_full_size_properties():
+    """BASELINE configs[1] stage-0 size (8 x 196608 rows of 96): rows are normalised independently, so (a) every output
+    row has zero mean / unit variance with the identity affine, (b) permuting rows permutes the output."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    rows, C = 8 * 196608, 96
+    x = torch.randn(rows, C, device=dev) * 3 + 1
+    norm = torch.nn.LayerNorm(C).to(dev)
+    y = ops.layer_norm(x, norm)
+    assert float(y.mean(1).abs().max()) < 1e-5
+    assert float((y.var(1, unbiased=False) - 1).abs().max()) < 1e-3
+    perm = torch.randperm(rows, device=dev)
+    assert torch.equal(ops.layer_norm(x[perm], norm), y[perm])
