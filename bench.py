@@ -182,16 +182,14 @@ def run_ours(a):
     from heal_swin_b200 import _lib, ops
     from tests.util import build_product_model
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from heal_swin_b200 import dist as hsdist
+
+    rank, local, world = hsdist.env_world()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.check(_lib.lib.hs_device_info(None, None, None, None, 0))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    hsdist.init_from_env("nccl", dev)
     # remaining library GEMMs (cuBLAS through torch) run in TF32 like the reference's own container did
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
@@ -205,9 +203,7 @@ def run_ours(a):
             if n.endswith("relative_position_bias_table"):
                 p.copy_((torch.randn(p.shape, generator=gen) * 0.02).to(dev))
     model.train()
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    net = hsdist.wrap_ddp(model, local)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     B, npix = a.batch, kw["dim_in"]
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -225,16 +221,11 @@ def run_ours(a):
         return loss
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        hsdist.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return hsdist.max_over_ranks(ms, dev)
 
     for _ in range(a.warmup):
         step(dev_x, dev_t)
@@ -281,7 +272,8 @@ def run_ours(a):
     value = pix_per_step * a.steps / (ms_dev * 1e-3)
     e2e = pix_per_step * a.steps / (ms_e2e * 1e-3)
 
-    # ---- roofline of the windowed-attention forward kernel at the stage-0 shape
+    # ---- rooflines of the hand-written kernels (all HBM-bound): algorithmic bytes / mean CUDA-event duration of the
+    # launches inside the timed region; the headline `roofline` is the kernel family with the largest share of the step
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -289,20 +281,55 @@ def run_ours(a):
         pass
     hbm_peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json, burst copy)") if "hbm_gbs" in peaks \
         else (6650.0, "fallback (B200_PROFILING.md)")
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+
+    def alg_bytes(name, tag):
+        if name == "window_attn_fwd":  # q, k, v in + o out (4*ws*d*elt per window-head)
+            return tag[0] * tag[1] * 4 * tag[2] * 4
+        if name == "window_attn_bwd":  # q, k, v, dO in + dq, dk, dv out
+            return tag[0] * tag[1] * 7 * tag[2] * 4
+        if name == "layernorm_fwd":    # x (+ residual) in, y out
+            return tag[0] * tag[1] * 4 * (2 + tag[2])
+        if name == "layernorm_bwd":    # dy, x in, dx out
+            return tag[0] * tag[1] * 4 * 3
+        if name == "gather_rows":
+            return tag[0] * tag[1] * tag[2] * 4 * 2
+        return None
+
+    families = {}
+    for (name, tag), times in kernel_ms.items():
+        nb = alg_bytes(name, tag)
+        if nb is None:
+            continue
+        f = families.setdefault(name, {"ms": 0.0, "bytes": 0.0, "launches": 0, "top": None})
+        f["ms"] += sum(times)
+        f["bytes"] += nb * len(times)
+        f["launches"] += len(times)
+        if f["top"] is None or nb > f["top"][1]:
+            f["top"] = (tag, nb, statistics.mean(times), len(times))
+    kernels = {}
+    for name, f in families.items():
+        tag, nb, avg_ms, n = f["top"]
+        ach = nb / (avg_ms * 1e-3) / 1e9
+        kernels[name] = {"share_of_step": f["ms"] / ms_dev, "launches": f["launches"],
+                         "family_achieved_GBps": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
+                         "largest_shape": list(tag), "largest_shape_avg_ms": avg_ms, "largest_shape_launches": n,
+                         "largest_shape_algorithmic_bytes": nb, "largest_shape_achieved_GBps": ach,
+                         "largest_shape_frac": ach / hbm_peak}
     roofline = None
-    fwd = {k[1]: v for k, v in kernel_ms.items() if k[0] == "window_attn_fwd"}
-    if fwd:
-        tag = max(fwd, key=lambda t: t[0] * t[1] * t[2])  # stage 0: most tokens
-        Bq, Nq, Cq, Hq, wsq = tag
-        alg_bytes = Bq * Nq * (3 * Cq + Cq) * 4  # read q,k,v + write o, fp32 (4*ws*d*elt per window-head)
-        avg_ms = statistics.mean(fwd[tag])
-        achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
-        roofline = {"kernel": "hs_window_attn_fwd (attention core, stage-0 shape)", "bound": "hbm",
-                    "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "avg_launch_ms": avg_ms, "launches_timed": len(fwd[tag]),
-                    "shape": {"B": Bq, "N": Nq, "C": Cq, "H": Hq, "ws": wsq}}
-    kernel_share = {f"{k[0]}{list(k[1])}": sum(v) / ms_dev for k, v in kernel_ms.items()}
+    if kernels:
+        dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+        k = kernels[dom]
+        roofline = {"kernel": f"hs_{dom} (largest shape {k['largest_shape']})", "bound": "hbm",
+                    "achieved": k["largest_shape_achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": k["largest_shape_frac"], "traffic": traffic.get(dom), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": k["largest_shape_algorithmic_bytes"],
+                    "avg_launch_ms": k["largest_shape_avg_ms"], "launches_timed": k["largest_shape_launches"],
+                    "share_of_step": k["share_of_step"]}
 
     cpu_base = None
     if world == 1 and not a.no_cpu_baseline:
@@ -320,7 +347,7 @@ def run_ours(a):
                 "h2d_bytes_per_step": host_x.numel() * 4 + host_t.numel() * 8, "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": roofline,
-        "kernel_share_of_step": kernel_share,
+        "kernels": kernels,
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }

@@ -9,12 +9,12 @@
 // The TMEM operand of tcgen05.mma is the A matrix with M on the TMEM lanes, so dQ needs dS with the query index on
 // the lanes while dV and dK need P^T / dS^T with the key index on the lanes.  Both orientations are produced by the
 // tensor cores themselves, stacked into one M = 128 tile (lanes 0-63 "natural", lanes 64-127 "transposed"):
-//      D1[:, 0:64)   = [Q;K] K^T   -> lanes 0-63  : S        D1[:, 64:128) = [Q;K] Q^T   -> lanes 64-127: S^T
-//      D2[:, 0:64)   = [dO;V] V^T  -> lanes 0-63  : dP       D2[:, 64:128) = [dO;V] dO^T -> lanes 64-127: dP^T
+//      D1 = [Q;K] [Q;K]^T    (one N = 128 MMA per K step):   lanes 0-63 x cols 64-127 = S,   lanes 64-127 x cols 0-63 = S^T
+//      D2 = [dO;V] [dO;V]^T                                   lanes 0-63 x cols 64-127 = dP,  lanes 64-127 x cols 0-63 = dP^T
 // (the other half of each product is unused).  Threads 0-63 of a warpgroup own one query row each (softmax statistics,
 // dS row, dbias row), threads 64-127 one key row each (P^T, dS^T from the row statistics published in shared memory).
 // They write dS (over S), P^T (over S^T) and dS^T (over dP^T) back to TMEM as TF32, and three more MMAs with
-// MN-major B tiles (K, dO, Q) produce dQ -> D2[:, 0:32), dV -> D2[:, 32:64), dK -> D1[:, 0:32).
+// MN-major B tiles (K, dO, Q) produce dQ, dV, dK into dead column blocks (see the MMA issuer for the exact map).
 //
 // Every input tile is needed K-major (scores) and, except V, MN-major (outputs): they are fetched twice by TMA with the
 // two swizzles (the second fetch hits L2).  HBM traffic per unit: q, k, v, dO in; dq, dk, dv out = 7 x 8 KB.
@@ -38,6 +38,7 @@ constexpr int kSlots = 3;
 constexpr int kStageCols = 256;  // D1 (128) + D2 (128)
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 384;
+constexpr int kDbtPitch = 65;   // floats; lane j, column i -> bank (j + i) % 32: conflict-free read-modify-write
 constexpr int kBiasPitch = 68;  // floats; 16-byte chunk index advances by 17 per row -> conflict-free LDS.128
 
 struct SlotMeta {
@@ -57,13 +58,16 @@ struct Slot {
 
 struct Smem {
   Slot slot[kSlots];
-  float bias[2][kWS * kBiasPitch];  // [0]: bias[i][j], [1]: bias[j][i]; both pre-multiplied by log2(e)
+  float bias[kWS * kBiasPitch];     // bias[i][j] * log2(e); query rows read it row-wise (LDS.128), key rows column-wise
   SlotMeta meta[kSlots];
   float inv[2][2 * kWS];  // per warpgroup: [0,64) 1/max(|q_i|,eps), [64,128) 1/max(|k_j|,eps)
   float lse[2][kWS];      // per warpgroup: log2-domain row log-sum-exp
   float delta[2][kWS];    // per warpgroup: rowsum(P o dP)
+  float4 lse4[2][kWS];    // the same, replicated 4x per row: what a query-row thread reads along its own columns
+  float4 delta4[2][kWS];
+  float dbt[2][kWS * kDbtPitch];  // per warpgroup: dbt[i][j] = sum over its units of dS[i][j] (query-row thread i owns row i)
   uint64_t full[kSlots], empty[kSlots];
-  uint64_t s_ready[2], ds_ready[2], x_ready[2], o_ready[2], stage_free[2];
+  uint64_t s_ready[2], dsn_ready[2], dst_ready[2], o_ready[2], stage_free[2];
   uint32_t tmem_base;
 };
 
@@ -84,120 +88,178 @@ struct BwdArgs {
   int total;  // B * nW units per head
 };
 
+#ifdef HS_BWD_TRACE
+// Diagnostics build only (tools/trace_bwd.cu): per-phase clock64 stamps of CTA (0, 0), role x unit x point.
+constexpr int kTraceUnits = 48, kTracePoints = 8, kTraceRoles = 6;  // roles: wg0 nat, wg0 tr, wg1 nat, wg1 tr, mma, producer
+__device__ long long g_trace[kTraceRoles * kTraceUnits * kTracePoints];
+#define HS_TRACE(role, n, k)                                                               \
+  do {                                                                                     \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (n) < kTraceUnits)                           \
+      g_trace[((role) * kTraceUnits + (n)) * kTracePoints + (k)] = clock64();              \
+  } while (0)
+#else
+#define HS_TRACE(role, n, k) do {} while (0)
+#endif
+
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
-// Elementwise stage of one unit for one thread.  kNat: thread owns query row r (lanes 0-63); else key row r.
-template <bool kNat>
-__device__ __forceinline__ void unit_elementwise(Smem& S, const BwdArgs& a, const int wg, const int r, const uint32_t D1,
-                                                 const uint32_t D2, const SlotMeta& M, const int flags,
-                                                 const float row_scale, const bool has_bias, float* dB, float& rs_out) {
-  constexpr uint32_t cb = kNat ? 0u : 64u;  // my column block of D1 / D2
-  const float* oinv = S.inv[wg] + (kNat ? kWS : 0);  // normalisation of the *other* index
-  const float* brow = S.bias[kNat ? 0 : 1] + r * kBiasPitch;
-  const int my_group = M.groups[r];
+// ---------------------------------------------------------------------------------------------------------------
+// Elementwise stage of one unit.  Written as ROLLED loops over 8-column chunks with everything recomputed from TMEM
+// (no per-row register arrays): the whole hot path is a few hundred instructions and stays resident in the
+// instruction cache -- the fully unrolled first version (4000 instructions, 64 KB) spent half of its issue slots
+// waiting for instruction fetches (profiles/r1d_attn_bwd_tc_*).  TMEM loads are double-buffered: the next chunk is in
+// flight while the current one is used.
+struct RowCtx {
+  uint32_t s_src, dp_src;  // my 64-column block of D1 (S or S^T) and D2 (dP or dP^T), lane field included
+  uint32_t oinv, brow;     // shared-memory addresses: normalisation of the other index (cos), my bias row / column
+  uint32_t bstep;          // byte step between consecutive bias entries along my columns (4: row, 4 * pitch: column)
+  uint32_t groups;         // shared-memory address of the unit's 64 group ids
+  float row_scale;         // log2(e) * scale (* my 1/|row| for cos) * truncation fix
+  int my_group;
+  bool cos, has_bias, masked;
+};
 
-  float x[kWS];
+// log2-domain logits of columns [c0, c0 + 8) from the raw tensor-core products
+__device__ __forceinline__ void logits8(const RowCtx& R, const uint32_t (&raw)[8], int c0, float (&x)[8], float4& o0,
+                                        float4& o1) {
+  o0 = make_float4(1.f, 1.f, 1.f, 1.f);
+  o1 = o0;
+  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+  if (R.cos) {
+    o0 = lds_f4(R.oinv + 4 * c0);
+    o1 = lds_f4(R.oinv + 4 * c0 + 16);
+  }
+  if (R.has_bias) {
+    if (R.bstep == 4) {
+      b0 = lds_f4(R.brow + 4 * c0);
+      b1 = lds_f4(R.brow + 4 * c0 + 16);
+    } else {  // key rows: bias[c][r] walks down a column; consecutive lanes hit consecutive banks
+      const uint32_t b = R.brow + R.bstep * c0;
+      b0 = make_float4(lds_f1(b), lds_f1(b + R.bstep), lds_f1(b + 2 * R.bstep), lds_f1(b + 3 * R.bstep));
+      b1 = make_float4(lds_f1(b + 4 * R.bstep), lds_f1(b + 5 * R.bstep), lds_f1(b + 6 * R.bstep), lds_f1(b + 7 * R.bstep));
+    }
+  }
+  x[0] = fmaf(__uint_as_float(raw[0]) * R.row_scale, o0.x, b0.x);
+  x[1] = fmaf(__uint_as_float(raw[1]) * R.row_scale, o0.y, b0.y);
+  x[2] = fmaf(__uint_as_float(raw[2]) * R.row_scale, o0.z, b0.z);
+  x[3] = fmaf(__uint_as_float(raw[3]) * R.row_scale, o0.w, b0.w);
+  x[4] = fmaf(__uint_as_float(raw[4]) * R.row_scale, o1.x, b1.x);
+  x[5] = fmaf(__uint_as_float(raw[5]) * R.row_scale, o1.y, b1.y);
+  x[6] = fmaf(__uint_as_float(raw[6]) * R.row_scale, o1.z, b1.z);
+  x[7] = fmaf(__uint_as_float(raw[7]) * R.row_scale, o1.w, b1.w);
+  if (R.masked) {
+    uint32_t g0, g1;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g0), "=r"(g1) : "r"(R.groups + c0) : "memory");
 #pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    uint32_t sr[32];
-    tmem_ld32(D1 + cb + 32 * hf, sr);
+    for (int e = 0; e < 4; ++e) {
+      if ((int)((g0 >> (8 * e)) & 0xff) != R.my_group) x[e] += kMaskFill * kLog2e;
+      if ((int)((g1 >> (8 * e)) & 0xff) != R.my_group) x[4 + e] += kMaskFill * kLog2e;
+    }
+  }
+}
+
+// query-row threads: online softmax statistics of my row -> (log2-domain lse, rowsum(P o dP))
+__device__ __forceinline__ void row_stats(const RowCtx& R, float fix2, float& lse_out, float& delta_out) {
+  float m = -1e30f, l = 0.f, dot = 0.f;
+  auto chunk = [&](const uint32_t (&sraw)[8], const uint32_t (&dpr)[8], int c0) {
+    float x[8];
+    float4 o0, o1;
+    logits8(R, sraw, c0, x, o0, o1);
+    float cm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    const float mn = fmaxf(m, cm);
+    const float sc = ex2_approx(m - mn);
+    l *= sc;
+    dot *= sc;
+    m = mn;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float pv = ex2_approx(x[e] - mn);
+      l += pv;
+      dot = fmaf(pv, __uint_as_float(dpr[e]), dot);
+    }
+  };
+  uint32_t sa[8], da[8], sb[8], db[8];
+  tmem_ld8(R.s_src, sa);
+  tmem_ld8(R.dp_src, da);
+#pragma unroll 1
+  for (int o = 0; o < 8; o += 2) {
     tmem_wait_ld();
-#pragma unroll
-    for (int c4 = 0; c4 < 8; ++c4) {
-      const int c = 32 * hf + 4 * c4;
-      float4 o4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.cos) o4 = *reinterpret_cast<const float4*>(oinv + c);
-      if (has_bias) b4 = *reinterpret_cast<const float4*>(brow + c);
-      x[c + 0] = fmaf(__uint_as_float(sr[4 * c4 + 0]) * row_scale, o4.x, b4.x);
-      x[c + 1] = fmaf(__uint_as_float(sr[4 * c4 + 1]) * row_scale, o4.y, b4.y);
-      x[c + 2] = fmaf(__uint_as_float(sr[4 * c4 + 2]) * row_scale, o4.z, b4.z);
-      x[c + 3] = fmaf(__uint_as_float(sr[4 * c4 + 3]) * row_scale, o4.w, b4.w);
+    tmem_ld8(R.s_src + 8 * (o + 1), sb);
+    tmem_ld8(R.dp_src + 8 * (o + 1), db);
+    chunk(sa, da, 8 * o);
+    tmem_wait_ld();
+    if (o < 6) {
+      tmem_ld8(R.s_src + 8 * (o + 2), sa);
+      tmem_ld8(R.dp_src + 8 * (o + 2), da);
     }
+    chunk(sb, db, 8 * (o + 1));
   }
-  if (!(flags & kFlagUniform)) {
-    const uint32_t* gp = reinterpret_cast<const uint32_t*>(M.groups);
-#pragma unroll
-    for (int c4 = 0; c4 < kWS / 4; ++c4) {
-      const uint32_t g4 = gp[c4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if ((int)((g4 >> (8 * e)) & 0xff) != my_group) x[4 * c4 + e] += kMaskFill * kLog2e;
-    }
-  }
+  lse_out = m + lg2_approx(l);
+  delta_out = dot / l * fix2;  // dP = dO v^T has two truncated operands
+}
 
-  float inv_l = 1.f, delta = 0.f;
-  if (kNat) {
-    // row statistics: x <- exp2(x - max), l = sum, delta = sum(p dP) / l
-    float mx = x[0];
-#pragma unroll
-    for (int c = 1; c < kWS; ++c) mx = fmaxf(mx, x[c]);
-    float l = 0.f;
-#pragma unroll
-    for (int c = 0; c < kWS; ++c) {
-      x[c] = ex2_approx(x[c] - mx);
-      l += x[c];
-    }
-    float dot = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t dr[16];
-      tmem_ld16(D2 + cb + 16 * q, dr);
-      tmem_wait_ld();
-#pragma unroll
-      for (int cc = 0; cc < 16; ++cc) dot = fmaf(x[16 * q + cc], __uint_as_float(dr[cc]), dot);
-    }
-    inv_l = 1.0f / l;
-    delta = dot * inv_l * a.fix2;  // dP = dO v^T has two truncated operands
-    S.lse[wg][r] = mx + lg2_approx(l);
-    S.delta[wg][r] = delta;
-    named_bar_arrive(3 + wg, 128);  // publish (bar.arrive orders the shared-memory writes)
-  } else {
-    named_bar_sync(3 + wg, 128);  // row statistics of all 64 query rows are in shared memory
-  }
-
+// all threads: p = exp2(logit - lse), dS = p (dP - delta); P and dS (scaled by the other index' 1/norm for cos) go back
+// to TMEM as TF32 A operands; query-row threads also accumulate dS into the CTA's dbias tile (they finish first).
+// lse_v / delta_v: shared addresses of the statistics seen along my columns, `vstep` = 1 (vectors over the query index,
+// key-row threads) or 0 (my own row's 4-fold copy, query-row threads).  Returns sum_c dS_c * raw_c (for cos).
+__device__ __forceinline__ float ds_sweep(const RowCtx& R, float fix2, uint32_t lse_v, uint32_t delta_v, uint32_t vstep,
+                                          uint32_t p_dst, uint32_t ds_dst, uint32_t dbt_row /* 0 = none */) {
   float rs = 0.f;
+  auto chunk = [&](const uint32_t (&sraw)[8], const uint32_t (&dpr)[8], int o) {
+    const int c0 = 8 * o;
+    float x[8];
+    float4 o0, o1;
+    logits8(R, sraw, c0, x, o0, o1);
+    const float4 l0 = lds_f4(lse_v + vstep * (4 * c0)), l1 = lds_f4(lse_v + vstep * (4 * c0 + 16));
+    const float4 d0 = lds_f4(delta_v + vstep * (4 * c0)), d1 = lds_f4(delta_v + vstep * (4 * c0 + 16));
+    const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+    const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+    uint32_t pa[8], ua[8];
+    float ds[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t dr[16], s2[16];
-    tmem_ld16(D2 + cb + 16 * q, dr);
-    if (a.cos) tmem_ld16(D1 + cb + 16 * q, s2);
+    for (int e = 0; e < 8; ++e) {
+      const float pv = ex2_approx(x[e] - lv[e]);
+      ds[e] = pv * fmaf(__uint_as_float(dpr[e]), fix2, -dv[e]);
+      const float u = ds[e] * ov[e];
+      rs = fmaf(u, __uint_as_float(sraw[e]), rs);
+      pa[e] = __float_as_uint(tf32_rna(pv));
+      ua[e] = __float_as_uint(tf32_rna(u));
+    }
+    if (dbt_row) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {  // row owned by this thread alone: plain read-modify-write
+        const uint32_t ad = dbt_row + 4 * (c0 + e);
+        const float acc = lds_f1(ad) + ds[e];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(acc) : "memory");
+      }
+    }
+    // the chunk of S / dP at these columns has been consumed: overwrite in place
+    tmem_st8(p_dst + c0, pa);
+    tmem_st8(ds_dst + c0, ua);
+  };
+  uint32_t sa[8], da[8], sb[8], db[8];
+  tmem_ld8(R.s_src, sa);
+  tmem_ld8(R.dp_src, da);
+#pragma unroll 1
+  for (int o = 0; o < 8; o += 2) {
     tmem_wait_ld();
-    uint32_t pa[16];
-#pragma unroll
-    for (int cc = 0; cc < 16; ++cc) {
-      const int c = 16 * q + cc;
-      float p, dl;
-      if (kNat) {
-        p = x[c] * inv_l;
-        dl = delta;
-      } else {
-        p = ex2_approx(x[c] - S.lse[wg][c]);
-        dl = S.delta[wg][c];
-      }
-      const float ds = p * (__uint_as_float(dr[cc]) * a.fix2 - dl);
-      if (kNat) dB[c] += ds;
-      float av = ds;
-      if (a.cos) {
-        const float oi = oinv[c];
-        rs = fmaf(ds, __uint_as_float(s2[cc]) * row_scale * oi, rs);
-        av = ds * oi;
-      }
-      dr[cc] = __float_as_uint(tf32_rna(av));
-      if (!kNat) pa[cc] = __float_as_uint(tf32_rna(p));
+    tmem_ld8(R.s_src + 8 * (o + 1), sb);
+    tmem_ld8(R.dp_src + 8 * (o + 1), db);
+    chunk(sa, da, o);
+    tmem_wait_ld();
+    if (o < 6) {
+      tmem_ld8(R.s_src + 8 * (o + 2), sa);
+      tmem_ld8(R.dp_src + 8 * (o + 2), da);
     }
-    if (kNat) {
-      tmem_st16(D1 + 16 * q, dr);  // dS (scaled by 1/|k_j| for cos) over S
-    } else {
-      tmem_st16(D1 + 64 + 16 * q, pa);  // P^T over S^T
-      tmem_st16(D2 + 64 + 16 * q, dr);  // dS^T (scaled by 1/|q_i| for cos) over dP^T
-    }
+    chunk(sb, db, o + 1);
   }
-  rs_out = rs;
   tmem_wait_st();
+  return rs;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -217,8 +279,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&S.s_ready[i], 1);
-      mbar_init(&S.ds_ready[i], 128);
-      mbar_init(&S.x_ready[i], 1);
+      mbar_init(&S.dsn_ready[i], 64);  // dS of the 64 query rows is in TMEM   -> dQ
+      mbar_init(&S.dst_ready[i], 64);  // P^T, dS^T of the 64 key rows           -> dV, dK
       mbar_init(&S.o_ready[i], 1);
       mbar_init(&S.stage_free[i], 128);
     }
@@ -232,13 +294,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     tma_prefetch_desc(&map_do_mn);
     tma_prefetch_desc(&map_dqkv);
   }
+  for (int idx = threadIdx.x; idx < 2 * kWS * kDbtPitch; idx += kThreads) (&S.dbt[0][0])[idx] = 0.f;
   if (has_bias) {
     const float* bp = a.bias + (long long)h * kWS * kWS;
     for (int idx = threadIdx.x; idx < kWS * kWS; idx += kThreads) {
       const int i = idx >> 6, j = idx & 63;
       const float v = __ldg(bp + idx) * kLog2e;
-      S.bias[0][i * kBiasPitch + j] = v;
-      S.bias[1][j * kBiasPitch + i] = v;
+      S.bias[i * kBiasPitch + j] = v;
     }
   }
   tc_fence_before();
@@ -255,6 +317,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         const int slot = n % kSlots;
         const uint32_t use = (uint32_t)(n / kSlots);
         mbar_wait(&S.empty[slot], (use & 1) ^ 1);
+        if (lane == 0) HS_TRACE(5, n, 0);
         SlotMeta& M = S.meta[slot];
         Slot& T = S.slot[slot];
         const int b = unit / a.nW, w = unit - b * a.nW;
@@ -318,56 +381,56 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.full[slot]);  // arrival 2 of 2 (publishes the metadata too)
+        if (lane == 0) HS_TRACE(5, n, 1);
       }
     } else if (warp == 9 && lane == 0) {
       // ================================================================= MMA issuer (one thread)
       constexpr uint64_t kDescK = umma_smem_desc(16, 1024, kLayoutSw128);       // K-major, 8-row groups 1024 B apart
       constexpr uint64_t kDescMN = umma_smem_desc(1024, 512, kLayoutSw128B32);  // MN-major, 4-row k-atoms 512 B apart
-      constexpr uint32_t kIdescS = umma_idesc_tf32(128, 64, 0, 0);
+      constexpr uint32_t kIdescS = umma_idesc_tf32(128, 128, 0, 0);
       constexpr uint32_t kIdescO = umma_idesc_tf32(128, 32, 0, 1);
       auto issue_outputs = [&](int m) {
         const int t = m & 1, slot = m % kSlots;
         const uint32_t ph = (uint32_t)(m >> 1) & 1;
-        mbar_wait(&S.ds_ready[t], ph);
+        mbar_wait(&S.dsn_ready[t], ph);
+        HS_TRACE(4, m, 2);
         tc_fence_after();
         const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
         const Slot& T = S.slot[slot];
         const uint32_t kb = smem_u32(T.k_mn), db = smem_u32(T.do_mn), qb = smem_u32(T.q_mn);
 #pragma unroll
-        for (int s = 0; s < 8; ++s)  // dQ = dS k
-          umma_tf32_ts(D2, D1 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
-#pragma unroll
-        for (int s = 0; s < 8; ++s)  // dV = P^T dO
-          umma_tf32_ts(D2 + 32, D1 + 64 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
-        umma_commit(&S.x_ready[t]);
-        mbar_wait(&S.x_ready[t], ph);  // dQ has consumed dS before dK overwrites D1[:, 0:32)
+        for (int s = 0; s < 8; ++s)  // dQ = dS k            A: D1[:, 64:128)  ->  D2[:, 64:96)
+          umma_tf32_ts(D2 + 64, D1 + 64 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
+        mbar_wait(&S.dst_ready[t], ph);
         tc_fence_after();
 #pragma unroll
-        for (int s = 0; s < 8; ++s)  // dK = dS^T q
-          umma_tf32_ts(D1, D2 + 64 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
+        for (int s = 0; s < 8; ++s)  // dV = P^T dO          A: D1[:, 0:64)    ->  D2[:, 96:128)
+          umma_tf32_ts(D2 + 96, D1 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
+        HS_TRACE(4, m, 3);
+        // dK overwrites the dS block that dQ has read: tcgen05.mma instructions of one thread execute in issue order
+#pragma unroll
+        for (int s = 0; s < 8; ++s)  // dK = dS^T q          A: D2[:, 0:64)    ->  D1[:, 64:96)
+          umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
         umma_commit(&S.o_ready[t]);
+        HS_TRACE(4, m, 4);
       };
       int n = 0;
       for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
         const int slot = n % kSlots, t = n & 1;
         mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
         mbar_wait(&S.stage_free[t], ((uint32_t)(n >> 1) & 1) ^ 1);
+        HS_TRACE(4, n, 0);
         tc_fence_after();
         const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
         const uint32_t qk = smem_u32(S.slot[slot].qk), dov = smem_u32(S.slot[slot].dov);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)  // [Q;K] K^T
-          umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + kTile + s * 32), kIdescS, s > 0);
+        for (int s = 0; s < 4; ++s)  // [Q;K] [Q;K]^T : lanes 0-63 x cols 64-127 = S, lanes 64-127 x cols 0-63 = S^T
+          umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)  // [Q;K] Q^T
-          umma_tf32_ss(D1 + 64, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)  // [dO;V] V^T
-          umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + kTile + s * 32), kIdescS, s > 0);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)  // [dO;V] dO^T
-          umma_tf32_ss(D2 + 64, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
+        for (int s = 0; s < 4; ++s)  // [dO;V] [dO;V]^T : lanes 0-63 x cols 64-127 = dP, lanes 64-127 x cols 0-63 = dP^T
+          umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
         umma_commit(&S.s_ready[t]);
+        HS_TRACE(4, n, 1);
         if (n > 0) issue_outputs(n - 1);
       }
       if (n > 0) issue_outputs(n - 1);
@@ -383,19 +446,25 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     const uint32_t D1 = tmem + (uint32_t)wg * kStageCols + lane_addr, D2 = D1 + 128;
     const int half_bar = 5 + wg * 2 + (nat ? 0 : 1);  // named barrier of the 64 threads of this half
 
-    float dB[kWS];  // running sum of dS[r][:] over this CTA's units (query-row threads only)
-#pragma unroll
-    for (int c = 0; c < kWS; ++c) dB[c] = 0.f;
     float racc = 0.f;  // running sum of dS o (logits without bias / mask): d logit_scale
     const float eff = a.cos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale;
     bool store_pending = false;
+    int pending_slot = -1;  // store-issuing threads (r == 0): slot whose staging tiles a TMA store may still be reading
 
     int n = 0;
     for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
       if ((n & 1) != wg) continue;
       const int slot = n % kSlots;
       const uint32_t it = (uint32_t)(n >> 1) & 1;
+      if (pending_slot >= 0) {  // the staging tiles of my previous unit live in its slot: free it once they are read
+        tma_store_wait_read<0>();
+        mbar_arrive(&S.empty[pending_slot]);
+        pending_slot = -1;
+      }
       mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
+      const int trole = wg * 2 + (nat ? 0 : 1);
+      if (r == 0) HS_TRACE(trole, n, 0);
+
       const SlotMeta& M = S.meta[slot];
       Slot& T = S.slot[slot];
       const int flags = M.flags;
@@ -416,29 +485,62 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       const float row_scale = eff * kLog2e * my_inv * a.fix2;  // S = q k^T has two truncated operands
 
       mbar_wait(&S.s_ready[wg], it);
+      if (r == 0) HS_TRACE(trole, n, 1);
       tc_fence_after();
-      float rs = 0.f;
-      if (nat)
-        unit_elementwise<true>(S, a, wg, r, D1, D2, M, flags, row_scale, has_bias, dB, rs);
-      else
-        unit_elementwise<false>(S, a, wg, r, D1, D2, M, flags, row_scale, has_bias, dB, rs);
+      RowCtx R;
+      R.s_src = D1 + (nat ? 64u : 0u);   // S (query rows) / S^T (key rows)
+      R.dp_src = D2 + (nat ? 64u : 0u);  // dP / dP^T
+      R.oinv = smem_u32(S.inv[wg] + (nat ? kWS : 0));
+      R.brow = smem_u32(S.bias + (nat ? r * kBiasPitch : r));
+      R.bstep = nat ? 4u : 4u * kBiasPitch;
+      R.groups = smem_u32(M.groups);
+      R.row_scale = row_scale;
+      R.my_group = M.groups[r];
+      R.cos = a.cos != 0;
+      R.has_bias = has_bias;
+      R.masked = !(flags & kFlagUniform);
+      uint32_t lse_v, delta_v, vstep;
+      if (nat) {
+        float lse, delta;
+        row_stats(R, a.fix2, lse, delta);
+        S.lse[wg][r] = lse;
+        S.delta[wg][r] = delta;
+        S.lse4[wg][r] = make_float4(lse, lse, lse, lse);
+        S.delta4[wg][r] = make_float4(delta, delta, delta, delta);
+        named_bar_arrive(3 + wg, 128);  // publish to the key-row threads (bar.arrive orders the shared-memory writes)
+        lse_v = smem_u32(&S.lse4[wg][r]);
+        delta_v = smem_u32(&S.delta4[wg][r]);
+        vstep = 0;
+      } else {
+        named_bar_sync(3 + wg, 128);  // row statistics of all 64 query rows are in shared memory
+        lse_v = smem_u32(S.lse[wg]);
+        delta_v = smem_u32(S.delta[wg]);
+        vstep = 1;
+      }
+      // P^T over S^T for the key rows (the query rows write P into a dead block); dS over S / dS^T over dP^T
+      float rs = ds_sweep(R, a.fix2, lse_v, delta_v, vstep, D1, nat ? D1 + 64 : D2,
+                          (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u);
+      rs *= row_scale;  // sum_c dS[r][c] * log2(e) * (eff * cos(r, c))
       tc_fence_before();
-      mbar_arrive(&S.ds_ready[wg]);
-      rs *= (1.0f / kLog2e);  // sum_c dS[r][c] * (eff * cos(r, c))
+      mbar_arrive(nat ? &S.dsn_ready[wg] : &S.dst_ready[wg]);
+      if (r == 0) HS_TRACE(trole, n, 2);
+      rs *= (1.0f / kLog2e);  // sum_c dS[r][c] * (eff * cos(r, c))   (meaningful for cos attention only)
       if (nat) racc += rs;
 
       mbar_wait(&S.o_ready[wg], it);
+      if (r == 0) HS_TRACE(trole, n, 3);
       tc_fence_after();
       uint32_t acc0[kD], acc1[kD];
       if (nat) {
-        tmem_ld32(D2, acc0);  // dQ
+        tmem_ld32(D2 + 64, acc0);  // dQ
       } else {
-        tmem_ld32(D1, acc0);       // dK
-        tmem_ld32(D2 + 32, acc1);  // dV
+        tmem_ld32(D1 + 64, acc0);  // dK
+        tmem_ld32(D2 + 96, acc1);  // dV
       }
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&S.stage_free[wg]);
+      if (r == 0) HS_TRACE(trole, n, 4);
 
       // through the scaling / F.normalize:  d row = g * acc - row * corr
       const float g = eff * my_inv * a.fix1;  // dS (rounded) x k / q (truncated)
@@ -494,26 +596,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
             tma_store_2d(&map_dqkv, T.do_mn, 2 * a.C + h * kD, row0);
           }
           tma_store_commit();
-          tma_store_wait_read<0>();  // staging lives in the slot: release it only after the TMA engine has read it
           store_pending = true;
+          pending_slot = slot;  // released at the top of this thread's next unit, once the TMA engine has read it
         }
       }
-      mbar_arrive(&S.empty[slot]);
+      if (pending_slot != slot) mbar_arrive(&S.empty[slot]);
+      if (r == 0) HS_TRACE(trole, n, 5);
+    }
+    if (pending_slot >= 0) {
+      tma_store_wait_read<0>();
+      mbar_arrive(&S.empty[pending_slot]);
     }
     if (store_pending) tma_store_wait<0>();
 
-    if (nat) {
-      if (a.dbias) {
-        float* gb = a.dbias + ((long long)h * kWS + r) * kWS;
-#pragma unroll
-        for (int c = 0; c < kWS; ++c) atomicAdd(gb + c, dB[c]);
+    if (a.dbias) {
+      // both warpgroups accumulated into the same tile: wait for all 8 elementwise warps, then one atomic per entry
+      named_bar_sync(9, 256);
+      float* gb = a.dbias + (long long)h * kWS * kWS;
+      for (int idx = threadIdx.x; idx < kWS * kWS; idx += 256) {
+        const int i = idx >> 6, j = idx & 63;
+        atomicAdd(gb + idx, S.dbt[0][i * kDbtPitch + j] + S.dbt[1][i * kDbtPitch + j]);
       }
-      if (a.cos && a.dlogit) {
-        // d logit_scale = sum dS o logits_cos, zero where the clamp is active (torch.clamp backward)
+    }
+    if (nat && a.cos && a.dlogit) {
+      // d logit_scale = sum dS o logits_cos, zero where the clamp is active (torch.clamp backward)
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-        if (lane == 0 && __ldg(a.logit_scale + h) <= kLogitScaleMax) atomicAdd(a.dlogit + h, racc);
-      }
+      for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+      if (lane == 0 && __ldg(a.logit_scale + h) <= kLogitScaleMax) atomicAdd(a.dlogit + h, racc);
     }
   }
 

@@ -21,6 +21,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// explicit shared-space loads for addresses selected at run time (keeps them LDS instead of generic LD)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_add_shared_f32(uint32_t addr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -152,6 +167,20 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+
+// 32 lanes x 8 consecutive columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------- UMMA (tcgen05.mma, kind::tf32)
 // shared-memory matrix descriptor (sm_100 version field = 1); start address added per MMA
 __host__ __device__ constexpr uint64_t umma_smem_desc(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
@@ -190,11 +219,11 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+// Round an fp32 value to the nearest TF32 (ties away from zero, like cvt.rna.tf32.f32) for an operand that the tensor
+// core will TRUNCATE to its top 19 bits: adding half an ulp of the 10-bit mantissa to the bit pattern makes that
+// truncation a correct rounding.  One integer add on the ALU pipe instead of a conversion-unit instruction (the
+// conversion unit is shared with ex2 and was the busiest pipe of the attention kernels).
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

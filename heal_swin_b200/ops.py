@@ -77,7 +77,8 @@ class GatherRows(torch.autograd.Function):
         x = _f32c(x)
         B, N, Cc = x.shape
         out = torch.empty_like(x)
-        STATS.launch("gather_rows", lib.hs_gather_rows, ptr(x), ptr(idx_i32), ptr(out), B, N, Cc, current_stream())
+        STATS.launch("gather_rows", lib.hs_gather_rows, ptr(x), ptr(idx_i32), ptr(out), B, N, Cc, current_stream(),
+                     tag=(B, N, Cc))
         ctx.inv = inv_i32
         return out
 
@@ -173,7 +174,7 @@ class LayerNormFn(torch.autograd.Function):
         mean = torch.empty(rows, device=x2.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x2.device, dtype=torch.float32)
         STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), ptr(res2), ptr(w), ptr(b), ptr(y), ptr(mean),
-                     ptr(rstd), rows, Cc, C.c_float(eps), current_stream(), tag=(rows, Cc))
+                     ptr(rstd), rows, Cc, C.c_float(eps), current_stream(), tag=(rows, Cc, int(res2 is not None)))
         ctx.save_for_backward(x2, w, mean, rstd)
         ctx.has_res = residual is not None
         ctx.shape = shape

@@ -1,0 +1,67 @@
+// Diagnostics: phase timeline of the tcgen05 attention backward (CTA (0,0), first units) at the BASELINE stage-0
+// shape.  Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DHS_BWD_TRACE tools/trace_bwd.cu \
+//        heal_swin_b200/csrc/hs_error.cpp -o tools/trace_bwd      (run on the GPU box)
+#include "../heal_swin_b200/csrc/hs_attn_bwd_tc.cu"
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+int main(int argc, char** argv) {
+  const int B = 8, H = 3, C = 96;
+  const long long N = 196608;
+  const int cos = argc > 1 ? atoi(argv[1]) : 1;
+  const size_t nq = (size_t)B * N * 3 * C, no = (size_t)B * N * C;
+  float *qkv, *dout, *dqkv, *bias, *ls, *dbias, *dls;
+  cudaMalloc(&qkv, nq * 4); cudaMalloc(&dout, no * 4); cudaMalloc(&dqkv, nq * 4);
+  cudaMalloc(&bias, H * 64 * 64 * 4); cudaMalloc(&ls, H * 4); cudaMalloc(&dbias, H * 64 * 64 * 4); cudaMalloc(&dls, H * 4);
+  std::vector<float> h(1 << 22);
+  for (auto& v : h) v = (float)rand() / RAND_MAX - 0.5f;
+  for (size_t off = 0; off < nq; off += h.size()) cudaMemcpy(qkv + off, h.data(), std::min(h.size(), nq - off) * 4, cudaMemcpyHostToDevice);
+  for (size_t off = 0; off < no; off += h.size()) cudaMemcpy(dout + off, h.data(), std::min(h.size(), no - off) * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(bias, h.data(), H * 64 * 64 * 4, cudaMemcpyHostToDevice);
+  float hls[3] = {2.3f, 2.1f, 2.5f};
+  cudaMemcpy(ls, hls, 12, cudaMemcpyHostToDevice);
+  cudaMemset(dbias, 0, H * 64 * 64 * 4); cudaMemset(dls, 0, H * 4);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int it = 0; it < 3; ++it) {
+    cudaEventRecord(e0);
+    int rc = hs::window_attn_bwd_tc(qkv, dout, nullptr, nullptr, bias, cos ? ls : nullptr, 0.1767f, dqkv, dbias, dls, B, N, C, H,
+                                    cos ? HS_ATTN_COS : 0, 0);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("run %d rc=%d err=%s %.3f ms\n", it, rc, cudaGetErrorString(err), ms);
+  }
+  static long long tr[kTraceRoles * kTraceUnits * kTracePoints];
+  cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr));
+  auto at = [&](int role, int n, int k) { return tr[(role * kTraceUnits + n) * kTracePoints + k]; };
+  const long long t0 = at(5, 0, 0);
+  const char* names[6] = {"wg0.nat", "wg0.tr ", "wg1.nat", "wg1.tr ", "mma    ", "prod   "};
+  printf("cycles relative to the producer's first stamp; softmax points: full, s_ready, ds_arrive, o_ready, tmem_ld(stage_free), done\n");
+  printf("mma points: [0] waits done, [1] scores issued, [2] ds_ready(n), [3] x_ready(n), [4] dK issued; prod: [0] slot free, [1] issued\n");
+  for (int n = 16; n < 28; ++n) {
+    for (int role = 0; role < 6; ++role) {
+      if (role < 4 && (n & 1) != (role >> 1)) continue;
+      printf("unit %2d %s:", n, names[role]);
+      const int np = role < 4 ? 6 : (role == 4 ? 5 : 2);
+      for (int k = 0; k < np; ++k) printf(" %8lld", at(role, n, k) - t0);
+      printf("\n");
+    }
+  }
+  // average per-phase durations over units 8..47
+  double d[6][8] = {};
+  int cnt[6] = {};
+  for (int n = 8; n < kTraceUnits; ++n)
+    for (int role = 0; role < 4; ++role) {
+      if ((n & 1) != (role >> 1)) continue;
+      for (int k = 0; k < 5; ++k) d[role][k] += (double)(at(role, n, k + 1) - at(role, n, k));
+      if (n + 2 < kTraceUnits) d[role][5] += (double)(at(role, n + 2, 0) - at(role, n, 5));
+      cnt[role]++;
+    }
+  for (int role = 0; role < 4; ++role)
+    printf("%s avg cycles: wait_s %.0f | elementwise %.0f | wait_o %.0f | tmem_ld %.0f | epilogue %.0f | to next full %.0f\n", names[role],
+           d[role][0] / cnt[role], d[role][1] / cnt[role], d[role][2] / cnt[role], d[role][3] / cnt[role], d[role][4] / cnt[role], d[role][5] / cnt[role]);
+  printf("unit period (cycles): %.0f\n", (double)(at(0, 46, 0) - at(0, 8, 0)) / 38.0);
+  return 0;
+}
