@@ -21,9 +21,9 @@ __device__ __forceinline__ float group_sum(float v, int T) {
 
 template <int V>
 __global__ void __launch_bounds__(kThreads)
-ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, const float4* __restrict__ gamma,
-              const float4* __restrict__ beta, float4* __restrict__ y, float* __restrict__ mean_out,
-              float* __restrict__ rstd_out, long long rows, int T, float eps) {
+ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias, const float4* __restrict__ res,
+              const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ y,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int T, float eps) {
   const int lane = threadIdx.x & 31;
   const int t = lane & (T - 1), sub = lane / T, rpw = 32 / T;
   const int C4 = T * V;
@@ -44,6 +44,10 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, cons
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       a[v] = ok ? __ldcs(x + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pre_bias) {  // the bias of the Linear that produced x (its GEMM ran without bias)
+        const float4 pb = __ldg(pre_bias + t + T * v);
+        a[v].x += pb.x; a[v].y += pb.y; a[v].z += pb.z; a[v].w += pb.w;
+      }
       s += (a[v].x + a[v].y) + (a[v].z + a[v].w);
     }
     const float mu = group_sum(s, T) * invC;
@@ -76,23 +80,28 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res, cons
   }
 }
 
-template <int V>
+template <int V, bool kPreBias>
 __global__ void __launch_bounds__(kThreads)
-ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float* __restrict__ mean,
-              const float* __restrict__ rstd, const float4* __restrict__ gamma, float4* __restrict__ dx,
-              float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int T) {
-  extern __shared__ float red[];  // [2][C]
+ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ pre_bias,
+              const float* __restrict__ mean, const float* __restrict__ rstd, const float4* __restrict__ gamma,
+              float4* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dpre_bias, long long rows, int T) {
+  extern __shared__ float red[];  // [2 or 3][C]
   const int lane = threadIdx.x & 31;
   const int t = lane & (T - 1), sub = lane / T, rpw = 32 / T;
   const int C4 = T * V, C = 4 * C4;
   const float invC = 1.0f / (float)C;
-  for (int i = threadIdx.x; i < 2 * C; i += kThreads) red[i] = 0.f;
-  float4 g[V], dg[V], db[V];
+  for (int i = threadIdx.x; i < (kPreBias ? 3 : 2) * C; i += kThreads) red[i] = 0.f;
+  float4 g[V], dg[V], db[V], pb[kPreBias ? V : 1], dpb[kPreBias ? V : 1];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     g[v] = __ldg(gamma + t + T * v);
     dg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kPreBias) {
+      pb[v] = __ldg(pre_bias + t + T * v);
+      dpb[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
   }
   __syncthreads();
   const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -105,8 +114,11 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const float4 xv = ok ? __ldcs(x + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 xv = ok ? __ldcs(x + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
       const float4 d = ok ? __ldcs(dy + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kPreBias && ok) {
+        xv.x += pb[v].x; xv.y += pb[v].y; xv.z += pb[v].z; xv.w += pb[v].w;
+      }
       xh[v].x = (xv.x - mu) * rs; xh[v].y = (xv.y - mu) * rs; xh[v].z = (xv.z - mu) * rs; xh[v].w = (xv.w - mu) * rs;
       w[v].x = d.x * g[v].x; w[v].y = d.y * g[v].y; w[v].z = d.z * g[v].z; w[v].w = d.w * g[v].w;
       s1 += (w[v].x + w[v].y) + (w[v].z + w[v].w);
@@ -126,6 +138,9 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
         o.z = rs * (w[v].z - s1 - xh[v].z * s2);
         o.w = rs * (w[v].w - s1 - xh[v].w * s2);
         dx[row * C4 + t + T * v] = o;
+        if (kPreBias) {
+          dpb[v].x += o.x; dpb[v].y += o.y; dpb[v].z += o.z; dpb[v].w += o.w;
+        }
       }
     }
   }
@@ -145,11 +160,23 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
       atomicAdd(red + C + c + 0, db[v].x); atomicAdd(red + C + c + 1, db[v].y);
       atomicAdd(red + C + c + 2, db[v].z); atomicAdd(red + C + c + 3, db[v].w);
     }
+    if (kPreBias) {
+      for (int o = T; o < 32; o <<= 1) {
+        dpb[v].x += __shfl_xor_sync(0xffffffffu, dpb[v].x, o); dpb[v].y += __shfl_xor_sync(0xffffffffu, dpb[v].y, o);
+        dpb[v].z += __shfl_xor_sync(0xffffffffu, dpb[v].z, o); dpb[v].w += __shfl_xor_sync(0xffffffffu, dpb[v].w, o);
+      }
+      if (sub == 0) {
+        const int c = 4 * (t + T * v);
+        atomicAdd(red + 2 * C + c + 0, dpb[v].x); atomicAdd(red + 2 * C + c + 1, dpb[v].y);
+        atomicAdd(red + 2 * C + c + 2, dpb[v].z); atomicAdd(red + 2 * C + c + 3, dpb[v].w);
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += kThreads) {
     if (dgamma) atomicAdd(dgamma + i, red[i]);
     if (dbeta) atomicAdd(dbeta + i, red[C + i]);
+    if (kPreBias && dpre_bias) atomicAdd(dpre_bias + i, red[2 * C + i]);
   }
 }
 
@@ -157,7 +184,8 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
 // Generic fallback for channel counts the vector kernels do not cover (C % 4 != 0 or an odd factor > 3, e.g. the
 // reference's own embed_dim = 2 test config): one warp per row, scalar accesses.  Correct, not fast.
 __global__ void __launch_bounds__(kThreads)
-ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ res, const float* __restrict__ gamma,
+ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ pre_bias, const float* __restrict__ res,
+                      const float* __restrict__ gamma,
                       const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean_out,
                       float* __restrict__ rstd_out, long long rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
@@ -165,14 +193,15 @@ ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ res
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long row = warp0; row < rows; row += stride) {
     const float* xr = x + row * C;
+    auto xin = [&](int c) { return xr[c] + (pre_bias ? pre_bias[c] : 0.f); };
     float s = 0.f;
-    for (int c = lane; c < C; c += 32) s += xr[c];
+    for (int c = lane; c < C; c += 32) s += xin(c);
     const float mu = group_sum(s, 32) / (float)C;
     float q = 0.f;
-    for (int c = lane; c < C; c += 32) q += (xr[c] - mu) * (xr[c] - mu);
+    for (int c = lane; c < C; c += 32) q += (xin(c) - mu) * (xin(c) - mu);
     const float rs = rsqrtf(group_sum(q, 32) / (float)C + eps);
     for (int c = lane; c < C; c += 32) {
-      float o = fmaf((xr[c] - mu) * rs, gamma[c], beta[c]);
+      float o = fmaf((xin(c) - mu) * rs, gamma[c], beta[c]);
       if (res) o += res[row * C + c];
       y[row * C + c] = o;
     }
@@ -184,27 +213,31 @@ ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ res
 }
 
 __global__ void __launch_bounds__(kThreads)
-ln_bwd_generic_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
-                      const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ dx,
-                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C) {
+ln_bwd_generic_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ pre_bias,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                      float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                      float* __restrict__ dpre_bias, long long rows, int C) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long row = warp0; row < rows; row += stride) {
     const float mu = mean[row], rs = rstd[row];
+    auto xin = [&](int c) { return x[row * C + c] + (pre_bias ? pre_bias[c] : 0.f); };
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float xh = (x[row * C + c] - mu) * rs, w = dy[row * C + c] * gamma[c];
+      const float xh = (xin(c) - mu) * rs, w = dy[row * C + c] * gamma[c];
       s1 += w;
       s2 += w * xh;
     }
     s1 = group_sum(s1, 32) / (float)C;
     s2 = group_sum(s2, 32) / (float)C;
     for (int c = lane; c < C; c += 32) {
-      const float d = dy[row * C + c], xh = (x[row * C + c] - mu) * rs;
-      dx[row * C + c] = rs * (d * gamma[c] - s1 - xh * s2);
+      const float d = dy[row * C + c], xh = (xin(c) - mu) * rs;
+      const float o = rs * (d * gamma[c] - s1 - xh * s2);
+      dx[row * C + c] = o;
       if (dgamma) atomicAdd(dgamma + c, d * xh);
       if (dbeta) atomicAdd(dbeta + c, d);
+      if (dpre_bias) atomicAdd(dpre_bias + c, o);
     }
   }
 }
@@ -264,56 +297,70 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 extern "C" {
 
-int hs_layernorm_fwd(const float* x, const float* residual, const float* gamma, const float* beta, float* y,
-                     float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+int hs_layernorm_fwd(const float* x, const float* pre_bias, const float* residual, const float* gamma, const float* beta,
+                     float* y, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
   HS_REQUIRE(x && gamma && beta && y, "hs_layernorm_fwd: null pointer");
   HS_REQUIRE((mean == nullptr) == (rstd == nullptr), "hs_layernorm_fwd: mean and rstd go together");
   HS_REQUIRE(rows > 0, "hs_layernorm_fwd: rows must be positive");
   HS_REQUIRE(C > 0, "hs_layernorm_fwd: C must be positive");
   int T, V;
   const bool vec = pick_shape(C, &T, &V) && aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) &&
-                   (!residual || aligned16(residual));
+                   (!residual || aligned16(residual)) && (!pre_bias || aligned16(pre_bias));
   if (!vec) {
     long long blocks = (rows + kThreads / 32 - 1) / (kThreads / 32);
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    ln_fwd_generic_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, residual, gamma, beta, y, mean, rstd,
-                                                                              rows, C, eps);
+    ln_fwd_generic_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, pre_bias, residual, gamma, beta, y,
+                                                                              mean, rstd, rows, C, eps);
     HS_LAUNCH_CHECK();
     return HS_OK;
   }
   HS_LN_DISPATCH(V, {
     const int grid = grid_for(ln_fwd_kernel<VV>, 0, rows, T);
     ln_fwd_kernel<VV><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(residual),
-        reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(y),
-        mean, rstd, rows, T, eps);
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pre_bias),
+        reinterpret_cast<const float4*>(residual), reinterpret_cast<const float4*>(gamma),
+        reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(y), mean, rstd, rows, T, eps);
   });
   HS_LAUNCH_CHECK();
   return HS_OK;
 }
 
-int hs_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                     float* dx, float* dgamma, float* dbeta, int64_t rows, int C, void* stream) {
+int hs_layernorm_bwd(const float* dy, const float* x, const float* pre_bias, const float* mean, const float* rstd,
+                     const float* gamma, float* dx, float* dgamma, float* dbeta, float* dpre_bias, int64_t rows, int C,
+                     void* stream) {
   HS_REQUIRE(dy && x && mean && rstd && gamma && dx, "hs_layernorm_bwd: null pointer");
   HS_REQUIRE(rows > 0, "hs_layernorm_bwd: rows must be positive");
   HS_REQUIRE(C > 0, "hs_layernorm_bwd: C must be positive");
   int T, V;
-  const bool vec = pick_shape(C, &T, &V) && aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma);
+  HS_REQUIRE(pre_bias || !dpre_bias, "hs_layernorm_bwd: dpre_bias without pre_bias");
+  // the pre-bias variant keeps V more float4 accumulators: vector path for V <= 6 (C <= 768), generic beyond
+  const bool vec = pick_shape(C, &T, &V) && aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) &&
+                   (!pre_bias || (aligned16(pre_bias) && V <= 6));
   if (!vec) {
     long long blocks = (rows + kThreads / 32 - 1) / (kThreads / 32);
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
-    ln_bwd_generic_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(dy, x, mean, rstd, gamma, dx, dgamma,
-                                                                              dbeta, rows, C);
+    ln_bwd_generic_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(dy, x, pre_bias, mean, rstd, gamma, dx,
+                                                                              dgamma, dbeta, dpre_bias, rows, C);
     HS_LAUNCH_CHECK();
     return HS_OK;
   }
-  const size_t smem = 2 * (size_t)C * sizeof(float);
-  HS_LN_DISPATCH(V, {
-    const int grid = grid_for(ln_bwd_kernel<VV>, smem, rows, T);
-    ln_bwd_kernel<VV><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), mean, rstd,
-        reinterpret_cast<const float4*>(gamma), reinterpret_cast<float4*>(dx), dgamma, dbeta, rows, T);
-  });
+  const size_t smem = (pre_bias ? 3 : 2) * (size_t)C * sizeof(float);
+  if (pre_bias) {
+    HS_LN_DISPATCH(V, {
+      const int grid = grid_for(ln_bwd_kernel<(VV <= 6 ? VV : 6), true>, smem, rows, T);
+      ln_bwd_kernel<(VV <= 6 ? VV : 6), true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
+          reinterpret_cast<const float4*>(pre_bias), mean, rstd, reinterpret_cast<const float4*>(gamma),
+          reinterpret_cast<float4*>(dx), dgamma, dbeta, dpre_bias, rows, T);
+    });
+  } else {
+    HS_LN_DISPATCH(V, {
+      const int grid = grid_for(ln_bwd_kernel<VV, false>, smem, rows, T);
+      ln_bwd_kernel<VV, false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+          reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), nullptr, mean, rstd,
+          reinterpret_cast<const float4*>(gamma), reinterpret_cast<float4*>(dx), dgamma, dbeta, nullptr, rows, T);
+    });
+  }
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

@@ -12,6 +12,7 @@ from typing import List, Literal, Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import torch.utils.checkpoint as checkpoint
 
 from .. import hp_index, ops
@@ -47,8 +48,22 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features, out_features)
         self.drop = nn.Dropout(drop)
 
+    def _fusable(self):
+        return (isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none"
+                and self.fc1.bias is not None and not (self.training and self.drop.p > 0.0))
+
+    def forward_split(self, x):
+        """(fc2 output WITHOUT its bias, that bias or None): the caller adds the bias (fused into the LayerNorm that
+        follows in the v2 placement).  fc1's bias add, the GELU and (backward) fc1's bias gradient are one kernel."""
+        if not self._fusable():
+            return self.forward(x), None
+        h = ops.bias_gelu(F.linear(x, self.fc1.weight), self.fc1.bias)
+        return F.linear(h, self.fc2.weight), self.fc2.bias
+
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        if not self._fusable():
+            return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        return self.fc2(ops.bias_gelu(F.linear(x, self.fc1.weight), self.fc1.bias))
 
 
 class WindowAttention(nn.Module):
@@ -99,6 +114,14 @@ class WindowAttention(nn.Module):
         (unshifted) order; ``src``/``groups`` are the block's shift tables (None = no shift)."""
         out = self._core(self.qkv(x), window_size, src, groups, None)
         return self.proj_drop(self.proj(out))
+
+    def forward_tokens_split(self, x, window_size, src=None, groups=None):
+        """As forward_tokens, but returns (proj output WITHOUT its bias, that bias or None) so that the caller can fuse
+        the bias add into the LayerNorm that follows (v2 norm placement)."""
+        if self.proj.bias is None or (self.training and self.proj_drop.p > 0.0):
+            return self.forward_tokens(x, window_size, src, groups), None
+        out = self._core(self.qkv(x), window_size, src, groups, None)
+        return F.linear(out, self.proj.weight), self.proj.bias
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:124-174]"""
@@ -172,24 +195,28 @@ class SwinTransformerBlock(nn.Module):
         if not self.use_v2_norm_placement:
             x = ops.layer_norm(x, self.norm1)
         # shift + partition + W-MSA/SW-MSA + reverse + shift back, one kernel chain   [:319-330]
-        x = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups)
-        return _residual_tail(self, shortcut, x)
+        x, pre_bias = self.attn.forward_tokens_split(x, self.window_size, self._hs_src, self._hs_groups)
+        return _residual_tail(self, shortcut, x, pre_bias)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"
                 f" window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
 
 
-def _residual_tail(blk, shortcut, x):
+def _residual_tail(blk, shortcut, x, pre_bias=None):
     """The two residual branches after the attention   [swin_hp_transformer.py:333-338 / swin_transformer.py:394-401].
-    Without stochastic depth (drop_path == 0 or eval) ``shortcut + norm(x)`` is one fused LayerNorm+add launch."""
+    ``x`` is the attention branch, ``pre_bias`` the not-yet-added bias of its output projection (or None).
+    Without stochastic depth (drop_path == 0 or eval) ``shortcut + norm(x + bias)`` is one fused launch."""
     plain = isinstance(blk.drop_path, nn.Identity) or not blk.training
     if blk.use_v2_norm_placement:
         if plain:
-            x = ops.layer_norm(x, blk.norm1, residual=shortcut)
-            return ops.layer_norm(blk.mlp(x), blk.norm2, residual=x)
-        x = shortcut + blk.drop_path(ops.layer_norm(x, blk.norm1))
+            x = ops.layer_norm(x, blk.norm1, residual=shortcut, pre_bias=pre_bias)
+            h, hb = blk.mlp.forward_split(x)
+            return ops.layer_norm(h, blk.norm2, residual=x, pre_bias=hb)
+        x = shortcut + blk.drop_path(ops.layer_norm(x, blk.norm1, pre_bias=pre_bias))
         return x + blk.drop_path(ops.layer_norm(blk.mlp(x), blk.norm2))
+    if pre_bias is not None:
+        x = x + pre_bias
     x = shortcut + blk.drop_path(x)
     return x + blk.drop_path(blk.mlp(ops.layer_norm(x, blk.norm2)))
 
@@ -338,7 +365,11 @@ class PatchEmbed(nn.Module):
     def forward(self, x):
         B, C, N = x.shape
         assert N == self.data_spec.dim_in, f"Input image size ({N}) doesn't match model ({self.data_spec.dim_in})."
-        x = self.proj(x).transpose(1, 2)
+        # Conv1d(k = s = patch) == Linear over the (f_in x patch) values of every patch; written that way the result is
+        # already the contiguous (B, N/patch, C) token tensor (the conv gives (B, C, N/patch) and a strided view)
+        p = self.config.patch_size
+        patches = x.reshape(B, C, N // p, p).permute(0, 2, 1, 3).reshape(B, N // p, C * p)
+        x = F.linear(patches, self.proj.weight.reshape(self.proj.weight.shape[0], C * p), self.proj.bias)
         if self.norm is not None:
             x = self.norm(x)
         return x
@@ -384,7 +415,10 @@ class UnetDecoder(nn.Module):
                 x = self.concat_back_dim[inx](x)
             x = layer_up(x)
         x = self.up(ops.layer_norm(x, self.norm_up))
-        return self.output(x.permute(0, 2, 1))
+        # Conv1d(kernel 1, no bias) over channels == Linear on the token-major tensor: the (B, N_pix, C) activation is
+        # never transposed, only the f_out-channel result is
+        y = F.linear(x, self.output.weight[:, :, 0])
+        return y.permute(0, 2, 1).contiguous()
 
 
 @dataclass

@@ -18,6 +18,7 @@ from typing import List, Literal, Optional, Tuple, Union
 import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 import torch.utils.checkpoint as checkpoint
 
 from .. import hp_index, ops
@@ -141,6 +142,13 @@ class WindowAttention(nn.Module):
         """x: (B, H*W, C) in raster order; ``src`` / ``groups``: the block's window-slot tables."""
         return self.proj_drop(self.proj(self._core(self.qkv(x), n_tokens, src, groups, None)))
 
+    def forward_tokens_split(self, x, n_tokens, src=None, groups=None):
+        """(proj output WITHOUT its bias, that bias or None): the bias add is fused into the following LayerNorm."""
+        if self.proj.bias is None or (self.training and self.proj_drop.p > 0.0):
+            return self.forward_tokens(x, n_tokens, src, groups), None
+        out = self._core(self.qkv(x), n_tokens, src, groups, None)
+        return F.linear(out, self.proj.weight), self.proj.bias
+
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:148-202]"""
         B_, n, C = x.shape
@@ -215,10 +223,11 @@ class SwinTransformerBlock(nn.Module):
         shortcut = x
         if not self.use_v2_norm_placement:
             x = ops.layer_norm(x, self.norm1)
-        x = self.attn.forward_tokens(x, self.window_size[0] * self.window_size[1], self._hs_src, self._hs_groups)
+        x, pre_bias = self.attn.forward_tokens_split(x, self.window_size[0] * self.window_size[1], self._hs_src,
+                                                     self._hs_groups)
         if self.fixup is not None:
             x = self.fixup(x)
-        return _residual_tail(self, shortcut, x)
+        return _residual_tail(self, shortcut, x, pre_bias)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"
@@ -389,7 +398,10 @@ class PatchEmbed(nn.Module):
         B, C, H, W = x.shape
         assert H == self.data_spec.dim_in[0] and W == self.data_spec.dim_in[1], (
             f"Input image size {H}*{W} doesn't match model ({self.data_spec.dim_in[0]}*{self.data_spec.dim_in[1]}).")
-        x = self.proj(x).flatten(2).transpose(1, 2).contiguous()
+        # Conv2d(k = s = patch) == Linear over the (f_in x p1 x p2) values of every patch -> contiguous (B, L, C) tokens
+        p1, p2 = self.config.patch_size[0], self.config.patch_size[1]
+        patches = x.reshape(B, C, H // p1, p1, W // p2, p2).permute(0, 2, 4, 1, 3, 5).reshape(B, -1, C * p1 * p2)
+        x = F.linear(patches, self.proj.weight.reshape(self.proj.weight.shape[0], -1), self.proj.bias)
         if self.norm is not None:
             x = self.norm(x)
         return x
@@ -536,8 +548,9 @@ class SwinTransformerSys(nn.Module):
         assert L == H * W, "input features has wrong size"
         if self.config.final_upsample == "expand_first":
             x = self.up(x)
-            x = x.view(B, self.config.patch_size[0] * H, self.config.patch_size[1] * W, -1)
-            x = self.output(x.permute(0, 3, 1, 2).contiguous())
+            # 1x1 Conv2d (no bias) == Linear over channels on the token-major tensor; only the result is transposed
+            y = F.linear(x, self.output.weight[:, :, 0, 0])
+            x = y.view(B, self.config.patch_size[0] * H, self.config.patch_size[1] * W, -1).permute(0, 3, 1, 2).contiguous()
         return x
 
     def forward(self, x):

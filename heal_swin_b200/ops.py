@@ -159,47 +159,90 @@ def window_attention_core(qkv, bias_table, logit_scale, src, groups, dense_mask,
 
 
 class LayerNormFn(torch.autograd.Function):
-    """y = residual + LayerNorm(x) * weight + bias over the last dim (residual optional), csrc/hs_layernorm.cu."""
+    """y = residual + LayerNorm(x + pre_bias) * weight + bias over the last dim (pre_bias, residual optional),
+    csrc/hs_layernorm.cu."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, eps):
-        require_cuda(x, weight, bias, residual)
+    def forward(ctx, x, weight, bias, residual, pre_bias, eps):
+        require_cuda(x, weight, bias, residual, pre_bias)
         shape = x.shape
         Cc = shape[-1]
         x2 = _f32c(x).reshape(-1, Cc)
         rows = x2.shape[0]
         w, b = _f32c(weight), _f32c(bias)
         res2 = _f32c(residual).reshape(-1, Cc) if residual is not None else None
+        pb = _f32c(pre_bias) if pre_bias is not None else None
         y = torch.empty_like(x2)
         mean = torch.empty(rows, device=x2.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x2.device, dtype=torch.float32)
-        STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), ptr(res2), ptr(w), ptr(b), ptr(y), ptr(mean),
-                     ptr(rstd), rows, Cc, C.c_float(eps), current_stream(), tag=(rows, Cc, int(res2 is not None)))
-        ctx.save_for_backward(x2, w, mean, rstd)
+        STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), ptr(pb), ptr(res2), ptr(w), ptr(b), ptr(y),
+                     ptr(mean), ptr(rstd), rows, Cc, C.c_float(eps), current_stream(),
+                     tag=(rows, Cc, int(res2 is not None)))
+        ctx.save_for_backward(x2, w, mean, rstd, pb)
         ctx.has_res = residual is not None
         ctx.shape = shape
         return y.view(shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w, mean, rstd = ctx.saved_tensors
+        x2, w, mean, rstd, pb = ctx.saved_tensors
         rows, Cc = x2.shape
         dy2 = _f32c(dy).reshape(rows, Cc)
         dx = torch.empty_like(x2)
         need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_pb = pb is not None and ctx.needs_input_grad[4]
         dw = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_w else None
         db = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_b else None
-        STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(x2), ptr(mean), ptr(rstd), ptr(w), ptr(dx),
-                     ptr(dw), ptr(db), rows, Cc, current_stream(), tag=(rows, Cc))
+        dpb = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_pb else None
+        STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(x2), ptr(pb), ptr(mean), ptr(rstd), ptr(w),
+                     ptr(dx), ptr(dw), ptr(db), ptr(dpb), rows, Cc, current_stream(), tag=(rows, Cc))
         dres = dy if ctx.has_res else None
-        return dx.view(ctx.shape), dw, db, dres, None
+        return dx.view(ctx.shape), dw, db, dres, dpb, None
 
 
-def layer_norm(x, norm, residual=None):
-    """``residual + norm(x)`` for an ``nn.LayerNorm`` module ``norm`` (affine, normalising the last dim) in one
-    launch; any other norm layer is applied as the module it is."""
-    if (isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
-            and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == x.shape[-1]):
-        return LayerNormFn.apply(x, norm.weight, norm.bias, residual, float(norm.eps))
-    y = norm(x)
+def _fusable_norm(norm, x):
+    return (isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
+            and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == x.shape[-1])
+
+
+def layer_norm(x, norm, residual=None, pre_bias=None):
+    """``residual + norm(x + pre_bias)`` for an ``nn.LayerNorm`` module ``norm`` (affine, normalising the last dim) in
+    one launch; any other norm layer is applied as the module it is."""
+    if _fusable_norm(norm, x):
+        return LayerNormFn.apply(x, norm.weight, norm.bias, residual, pre_bias, float(norm.eps))
+    y = norm(x if pre_bias is None else x + pre_bias)
     return y if residual is None else residual + y
+
+
+class BiasGeluFn(torch.autograd.Function):
+    """h = GELU(z + bias) (exact erf GELU), csrc/hs_bias_gelu.cu; backward also yields d(bias)."""
+
+    @staticmethod
+    def forward(ctx, z, bias):
+        require_cuda(z, bias)
+        shape = z.shape
+        Cc = shape[-1]
+        z2 = _f32c(z).reshape(-1, Cc)
+        b = _f32c(bias) if bias is not None else None
+        h = torch.empty_like(z2)
+        STATS.launch("bias_gelu_fwd", lib.hs_bias_gelu_fwd, ptr(z2), ptr(b), ptr(h), z2.shape[0], Cc, current_stream(),
+                     tag=(z2.shape[0], Cc))
+        ctx.save_for_backward(z2, b)
+        ctx.shape = shape
+        return h.view(shape)
+
+    @staticmethod
+    def backward(ctx, dh):
+        z2, b = ctx.saved_tensors
+        rows, Cc = z2.shape
+        dh2 = _f32c(dh).reshape(rows, Cc)
+        dz = torch.empty_like(z2)
+        need_b = b is not None and ctx.needs_input_grad[1]
+        db = torch.zeros(Cc, device=z2.device, dtype=torch.float32) if need_b else None
+        STATS.launch("bias_gelu_bwd", lib.hs_bias_gelu_bwd, ptr(dh2), ptr(z2), ptr(b), ptr(dz), ptr(db), rows, Cc,
+                     current_stream(), tag=(rows, Cc))
+        return dz.view(ctx.shape), db
+
+
+def bias_gelu(z, bias):
+    return BiasGeluFn.apply(z, bias)

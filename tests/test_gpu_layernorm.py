@@ -77,3 +77,51 @@ def test_layernorm_full_size_properties():
     assert float((y.var(1, unbiased=False) - 1).abs().max()) < 1e-3
     perm = torch.randperm(rows, device=dev)
     assert torch.equal(ops.layer_norm(x[perm], norm), y[perm])
+
+
+@pytest.mark.parametrize("C", [96, 384, 768, 1536, 16, 100])
+def test_layernorm_with_pre_bias_and_residual(C):
+    """y = res + LN(x + pre_bias): the fused form used after proj / fc2 in the v2 placement; d(pre_bias) = colsum(dx)."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    rows = 777
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(rows, C, generator=g).to(dev).requires_grad_(True)
+    res = torch.randn(rows, C, generator=g).to(dev).requires_grad_(True)
+    pb = torch.randn(C, generator=g).to(dev).requires_grad_(True)
+    norm = torch.nn.LayerNorm(C).to(dev)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        norm.bias.copy_(0.2 * torch.randn(C, generator=g))
+    wgt = torch.randn(rows, C, generator=g).to(dev)
+    y = ops.layer_norm(x, norm, residual=res, pre_bias=pb)
+    (y * wgt).sum().backward()
+    got = [y.detach().clone(), x.grad.clone(), pb.grad.clone(), norm.weight.grad.clone(), norm.bias.grad.clone()]
+    for t in (x, res, pb, norm.weight, norm.bias):
+        t.grad = None
+    y2 = res + F.layer_norm(x + pb, (C,), norm.weight, norm.bias, norm.eps)
+    (y2 * wgt).sum().backward()
+    want = [y2.detach(), x.grad, pb.grad, norm.weight.grad, norm.bias.grad]
+    for a, b, tol in zip(got, want, [1e-5, 1e-4, 1e-4, 1e-4, 1e-4]):
+        assert rel_err(a.cpu(), b.cpu()) < tol
+
+
+@pytest.mark.parametrize("C", [384, 768, 1536, 3072, 64, 8])
+@pytest.mark.parametrize("rows", [1000, 7])
+def test_bias_gelu_fwd_bwd_vs_torch(C, rows):
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(C + rows)
+    z = (torch.randn(rows, C, generator=g) * 2).to(dev).requires_grad_(True)
+    b = torch.randn(C, generator=g).to(dev).requires_grad_(True)
+    wgt = torch.randn(rows, C, generator=g).to(dev)
+    h = ops.bias_gelu(z, b)
+    (h * wgt).sum().backward()
+    got = [h.detach().clone(), z.grad.clone(), b.grad.clone()]
+    z.grad = b.grad = None
+    h2 = F.gelu(z + b)
+    (h2 * wgt).sum().backward()
+    for a, w, tol in zip(got, [h2.detach(), z.grad, b.grad], [1e-5, 1e-5, 1e-4]):
+        assert rel_err(a.cpu(), w.cpu()) < tol
