@@ -20,7 +20,7 @@
 // two swizzles (the second fetch hits L2).  HBM traffic per unit: q, k, v, dO in; dq, dk, dv out = 7 x 8 KB.
 //
 // Warp roles (384 threads): warps 0-3 / 4-7 = two elementwise warpgroups (unit n -> group n & 1, TMEM stage n & 1),
-// warp 8 = load producer, warp 9 = MMA issuer.  3 shared-memory slots of 56 KB; the output tiles are staged in the
+// warp 8 = load producer, warp 9 = score-MMA issuer, warp 10 = output-MMA issuer.  3 shared-memory slots of 56 KB; the output tiles are staged in the
 // slot's (dead) MN-major tiles and written back by TMA.
 #include <cfloat>
 
@@ -38,7 +38,7 @@ constexpr int kSlots = 3;
 constexpr int kStageCols = 256;  // D1 (128) + D2 (128)
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 384;
-constexpr int kDbtPitch = 65;   // floats; lane j, column i -> bank (j + i) % 32: conflict-free read-modify-write
+constexpr int kDbtPitch = 64;   // floats; 16-byte chunk c4 of row r is stored at chunk (c4 ^ (r & 15)): conflict-free float4 RMW
 constexpr int kBiasPitch = 68;  // floats; 16-byte chunk index advances by 17 per row -> conflict-free LDS.128
 
 struct SlotMeta {
@@ -123,143 +123,166 @@ struct RowCtx {
   bool cos, has_bias, masked;
 };
 
-// log2-domain logits of columns [c0, c0 + 8) from the raw tensor-core products
-__device__ __forceinline__ void logits8(const RowCtx& R, const uint32_t (&raw)[8], int c0, float (&x)[8], float4& o0,
-                                        float4& o1) {
-  o0 = make_float4(1.f, 1.f, 1.f, 1.f);
-  o1 = o0;
-  float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-  if (R.cos) {
-    o0 = lds_f4(R.oinv + 4 * c0);
-    o1 = lds_f4(R.oinv + 4 * c0 + 16);
+constexpr int kCW = 8;  // columns per chunk of the elementwise loops (16 was measured slower: 1.44 vs 1.27 ms)
+
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[kCW]) {
+  if constexpr (kCW == 8) tmem_ld8(taddr, r); else tmem_ld16(taddr, r);
+}
+__device__ __forceinline__ void tmem_st_chunk(uint32_t taddr, const uint32_t (&r)[kCW]) {
+  if constexpr (kCW == 8) tmem_st8(taddr, r); else tmem_st16(taddr, r);
+}
+
+// log2-domain logits of columns [c0, c0 + kCW) from the raw tensor-core products; ov = normalisation of the other index
+__device__ __forceinline__ void logits_chunk(const RowCtx& R, const uint32_t (&raw)[kCW], int c0, float (&x)[kCW],
+                                             float (&ov)[kCW]) {
+  float bv[kCW];
+#pragma unroll
+  for (int q = 0; q < kCW / 4; ++q) {
+    float4 o4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (R.cos) o4 = lds_f4(R.oinv + 4 * (c0 + 4 * q));
+    ov[4 * q + 0] = o4.x; ov[4 * q + 1] = o4.y; ov[4 * q + 2] = o4.z; ov[4 * q + 3] = o4.w;
   }
   if (R.has_bias) {
     if (R.bstep == 4) {
-      b0 = lds_f4(R.brow + 4 * c0);
-      b1 = lds_f4(R.brow + 4 * c0 + 16);
-    } else {  // key rows: bias[c][r] walks down a column; consecutive lanes hit consecutive banks
-      const uint32_t b = R.brow + R.bstep * c0;
-      b0 = make_float4(lds_f1(b), lds_f1(b + R.bstep), lds_f1(b + 2 * R.bstep), lds_f1(b + 3 * R.bstep));
-      b1 = make_float4(lds_f1(b + 4 * R.bstep), lds_f1(b + 5 * R.bstep), lds_f1(b + 6 * R.bstep), lds_f1(b + 7 * R.bstep));
-    }
-  }
-  x[0] = fmaf(__uint_as_float(raw[0]) * R.row_scale, o0.x, b0.x);
-  x[1] = fmaf(__uint_as_float(raw[1]) * R.row_scale, o0.y, b0.y);
-  x[2] = fmaf(__uint_as_float(raw[2]) * R.row_scale, o0.z, b0.z);
-  x[3] = fmaf(__uint_as_float(raw[3]) * R.row_scale, o0.w, b0.w);
-  x[4] = fmaf(__uint_as_float(raw[4]) * R.row_scale, o1.x, b1.x);
-  x[5] = fmaf(__uint_as_float(raw[5]) * R.row_scale, o1.y, b1.y);
-  x[6] = fmaf(__uint_as_float(raw[6]) * R.row_scale, o1.z, b1.z);
-  x[7] = fmaf(__uint_as_float(raw[7]) * R.row_scale, o1.w, b1.w);
-  if (R.masked) {
-    uint32_t g0, g1;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g0), "=r"(g1) : "r"(R.groups + c0) : "memory");
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      if ((int)((g0 >> (8 * e)) & 0xff) != R.my_group) x[e] += kMaskFill * kLog2e;
-      if ((int)((g1 >> (8 * e)) & 0xff) != R.my_group) x[4 + e] += kMaskFill * kLog2e;
+      for (int q = 0; q < kCW / 4; ++q) {
+        const float4 b4 = lds_f4(R.brow + 4 * (c0 + 4 * q));
+        bv[4 * q + 0] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
+      }
+    } else {  // key rows: bias[c][r] walks down a column; consecutive lanes hit consecutive banks
+#pragma unroll
+      for (int e = 0; e < kCW; ++e) bv[e] = lds_f1(R.brow + R.bstep * (c0 + e));
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < kCW; ++e) bv[e] = 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < kCW; ++e) x[e] = fmaf(__uint_as_float(raw[e]) * R.row_scale, ov[e], bv[e]);
+  if (R.masked) {
+#pragma unroll
+    for (int q = 0; q < kCW / 4; ++q) {
+      uint32_t g4;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(g4) : "r"(R.groups + c0 + 4 * q) : "memory");
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if ((int)((g4 >> (8 * e)) & 0xff) != R.my_group) x[4 * q + e] += kMaskFill * kLog2e;
     }
   }
 }
 
 // query-row threads: online softmax statistics of my row -> (log2-domain lse, rowsum(P o dP))
 __device__ __forceinline__ void row_stats(const RowCtx& R, float fix2, float& lse_out, float& delta_out) {
-  float m = -1e30f, l = 0.f, dot = 0.f;
-  auto chunk = [&](const uint32_t (&sraw)[8], const uint32_t (&dpr)[8], int c0) {
-    float x[8];
-    float4 o0, o1;
-    logits8(R, sraw, c0, x, o0, o1);
-    float cm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
-    const float mn = fmaxf(m, cm);
+  float m = -1e30f;
+  float l[4] = {0.f, 0.f, 0.f, 0.f}, dot[4] = {0.f, 0.f, 0.f, 0.f};  // 4 partial sums: short dependency chains
+  auto chunk = [&](const uint32_t (&sraw)[kCW], const uint32_t (&dpr)[kCW], int c0) {
+    float x[kCW], ov[kCW];
+    logits_chunk(R, sraw, c0, x, ov);
+    float cm[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cm[q] = x[q];
+#pragma unroll
+    for (int e = 4; e < kCW; ++e) cm[e & 3] = fmaxf(cm[e & 3], x[e]);
+    const float mn = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
     const float sc = ex2_approx(m - mn);
-    l *= sc;
-    dot *= sc;
     m = mn;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int q = 0; q < 4; ++q) {
+      l[q] *= sc;
+      dot[q] *= sc;
+    }
+#pragma unroll
+    for (int e = 0; e < kCW; ++e) {
       const float pv = ex2_approx(x[e] - mn);
-      l += pv;
-      dot = fmaf(pv, __uint_as_float(dpr[e]), dot);
+      l[e & 3] += pv;
+      dot[e & 3] = fmaf(pv, __uint_as_float(dpr[e]), dot[e & 3]);
     }
   };
-  uint32_t sa[8], da[8], sb[8], db[8];
-  tmem_ld8(R.s_src, sa);
-  tmem_ld8(R.dp_src, da);
+  uint32_t sa[kCW], da[kCW], sb[kCW], db[kCW];
+  tmem_ld_chunk(R.s_src, sa);
+  tmem_ld_chunk(R.dp_src, da);
 #pragma unroll 1
-  for (int o = 0; o < 8; o += 2) {
+  for (int c0 = 0; c0 < kWS; c0 += 2 * kCW) {
     tmem_wait_ld();
-    tmem_ld8(R.s_src + 8 * (o + 1), sb);
-    tmem_ld8(R.dp_src + 8 * (o + 1), db);
-    chunk(sa, da, 8 * o);
+    tmem_ld_chunk(R.s_src + c0 + kCW, sb);
+    tmem_ld_chunk(R.dp_src + c0 + kCW, db);
+    chunk(sa, da, c0);
     tmem_wait_ld();
-    if (o < 6) {
-      tmem_ld8(R.s_src + 8 * (o + 2), sa);
-      tmem_ld8(R.dp_src + 8 * (o + 2), da);
+    if (c0 + 2 * kCW < kWS) {
+      tmem_ld_chunk(R.s_src + c0 + 2 * kCW, sa);
+      tmem_ld_chunk(R.dp_src + c0 + 2 * kCW, da);
     }
-    chunk(sb, db, 8 * (o + 1));
+    chunk(sb, db, c0 + kCW);
   }
-  lse_out = m + lg2_approx(l);
-  delta_out = dot / l * fix2;  // dP = dO v^T has two truncated operands
+  const float lt = (l[0] + l[1]) + (l[2] + l[3]), dt = (dot[0] + dot[1]) + (dot[2] + dot[3]);
+  lse_out = m + lg2_approx(lt);
+  delta_out = dt / lt * fix2;  // dP = dO v^T has two truncated operands
 }
 
 // all threads: p = exp2(logit - lse), dS = p (dP - delta); P and dS (scaled by the other index' 1/norm for cos) go back
-// to TMEM as TF32 A operands; query-row threads also accumulate dS into the CTA's dbias tile (they finish first).
+// to TMEM as TF32 A operands; query-row threads also accumulate dS into their warpgroup's dbias tile.
 // lse_v / delta_v: shared addresses of the statistics seen along my columns, `vstep` = 1 (vectors over the query index,
 // key-row threads) or 0 (my own row's 4-fold copy, query-row threads).  Returns sum_c dS_c * raw_c (for cos).
+// dbt_row: shared address of my row of the dbias tile (0 = none); 16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 15)).
 __device__ __forceinline__ float ds_sweep(const RowCtx& R, float fix2, uint32_t lse_v, uint32_t delta_v, uint32_t vstep,
-                                          uint32_t p_dst, uint32_t ds_dst, uint32_t dbt_row /* 0 = none */) {
-  float rs = 0.f;
-  auto chunk = [&](const uint32_t (&sraw)[8], const uint32_t (&dpr)[8], int o) {
-    const int c0 = 8 * o;
-    float x[8];
-    float4 o0, o1;
-    logits8(R, sraw, c0, x, o0, o1);
-    const float4 l0 = lds_f4(lse_v + vstep * (4 * c0)), l1 = lds_f4(lse_v + vstep * (4 * c0 + 16));
-    const float4 d0 = lds_f4(delta_v + vstep * (4 * c0)), d1 = lds_f4(delta_v + vstep * (4 * c0 + 16));
-    const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-    const float dv[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-    const float ov[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-    uint32_t pa[8], ua[8];
-    float ds[8];
+                                          uint32_t p_dst, uint32_t ds_dst, uint32_t dbt_row, int dbt_xor) {
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  auto chunk = [&](const uint32_t (&sraw)[kCW], const uint32_t (&dpr)[kCW], int c0) {
+    float x[kCW], ov[kCW], lv[kCW], dv[kCW], ds[kCW];
+    logits_chunk(R, sraw, c0, x, ov);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int q = 0; q < kCW / 4; ++q) {
+      const float4 l4 = lds_f4(lse_v + vstep * (4 * (c0 + 4 * q)));
+      const float4 d4 = lds_f4(delta_v + vstep * (4 * (c0 + 4 * q)));
+      lv[4 * q + 0] = l4.x; lv[4 * q + 1] = l4.y; lv[4 * q + 2] = l4.z; lv[4 * q + 3] = l4.w;
+      dv[4 * q + 0] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
+    }
+    float4 acc[kCW / 4];
+    if (dbt_row) {  // issue the tile loads early; the row is owned by this thread alone (plain read-modify-write)
+#pragma unroll
+      for (int q = 0; q < kCW / 4; ++q) acc[q] = lds_f4(dbt_row + 16 * (((c0 >> 2) + q) ^ dbt_xor));
+    }
+    uint32_t pa[kCW], ua[kCW];
+#pragma unroll
+    for (int e = 0; e < kCW; ++e) {
       const float pv = ex2_approx(x[e] - lv[e]);
       ds[e] = pv * fmaf(__uint_as_float(dpr[e]), fix2, -dv[e]);
       const float u = ds[e] * ov[e];
-      rs = fmaf(u, __uint_as_float(sraw[e]), rs);
+      rs[e & 3] = fmaf(u, __uint_as_float(sraw[e]), rs[e & 3]);
       pa[e] = __float_as_uint(tf32_rna(pv));
       ua[e] = __float_as_uint(tf32_rna(u));
     }
+    // the chunk of S / dP at these columns has been consumed: overwrite in place
+    tmem_st_chunk(p_dst + c0, pa);
+    tmem_st_chunk(ds_dst + c0, ua);
     if (dbt_row) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {  // row owned by this thread alone: plain read-modify-write
-        const uint32_t ad = dbt_row + 4 * (c0 + e);
-        const float acc = lds_f1(ad) + ds[e];
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(ad), "f"(acc) : "memory");
+      for (int q = 0; q < kCW / 4; ++q) {
+        acc[q].x += ds[4 * q + 0]; acc[q].y += ds[4 * q + 1]; acc[q].z += ds[4 * q + 2]; acc[q].w += ds[4 * q + 3];
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dbt_row + 16 * (((c0 >> 2) + q) ^ dbt_xor)),
+                     "f"(acc[q].x), "f"(acc[q].y), "f"(acc[q].z), "f"(acc[q].w)
+                     : "memory");
       }
     }
-    // the chunk of S / dP at these columns has been consumed: overwrite in place
-    tmem_st8(p_dst + c0, pa);
-    tmem_st8(ds_dst + c0, ua);
   };
-  uint32_t sa[8], da[8], sb[8], db[8];
-  tmem_ld8(R.s_src, sa);
-  tmem_ld8(R.dp_src, da);
+  uint32_t sa[kCW], da[kCW], sb[kCW], db[kCW];
+  tmem_ld_chunk(R.s_src, sa);
+  tmem_ld_chunk(R.dp_src, da);
 #pragma unroll 1
-  for (int o = 0; o < 8; o += 2) {
+  for (int c0 = 0; c0 < kWS; c0 += 2 * kCW) {
     tmem_wait_ld();
-    tmem_ld8(R.s_src + 8 * (o + 1), sb);
-    tmem_ld8(R.dp_src + 8 * (o + 1), db);
-    chunk(sa, da, o);
+    tmem_ld_chunk(R.s_src + c0 + kCW, sb);
+    tmem_ld_chunk(R.dp_src + c0 + kCW, db);
+    chunk(sa, da, c0);
     tmem_wait_ld();
-    if (o < 6) {
-      tmem_ld8(R.s_src + 8 * (o + 2), sa);
-      tmem_ld8(R.dp_src + 8 * (o + 2), da);
+    if (c0 + 2 * kCW < kWS) {
+      tmem_ld_chunk(R.s_src + c0 + 2 * kCW, sa);
+      tmem_ld_chunk(R.dp_src + c0 + 2 * kCW, da);
     }
-    chunk(sb, db, o + 1);
+    chunk(sb, db, c0 + kCW);
   }
   tmem_wait_st();
-  return rs;
+  return (rs[0] + rs[1]) + (rs[2] + rs[3]);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -345,7 +368,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         M.groups[lane + 32] = (uint8_t)g1;
         if (lane == 0) M.flags = kFlagValid | (contig ? kFlagContig : 0) | (un ? kFlagUniform : 0);
         __syncwarp();
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_arrive_expect_tx(&S.full[slot], contig ? 7u * kTile : 0u);
           if (contig) {
             const int row = goff + rbase;
@@ -383,37 +406,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         if (lane == 0) mbar_arrive(&S.full[slot]);  // arrival 2 of 2 (publishes the metadata too)
         if (lane == 0) HS_TRACE(5, n, 1);
       }
-    } else if (warp == 9 && lane == 0) {
-      // ================================================================= MMA issuer (one thread)
-      constexpr uint64_t kDescK = umma_smem_desc(16, 1024, kLayoutSw128);       // K-major, 8-row groups 1024 B apart
-      constexpr uint64_t kDescMN = umma_smem_desc(1024, 512, kLayoutSw128B32);  // MN-major, 4-row k-atoms 512 B apart
+    } else if (warp == 9 && elect_one()) {
+      // ================================================================= score MMA issuer (one elected thread)
+      constexpr uint64_t kDescK = umma_smem_desc(16, 1024, kLayoutSw128);  // K-major, 8-row groups 1024 B apart
       constexpr uint32_t kIdescS = umma_idesc_tf32(128, 128, 0, 0);
-      constexpr uint32_t kIdescO = umma_idesc_tf32(128, 32, 0, 1);
-      auto issue_outputs = [&](int m) {
-        const int t = m & 1, slot = m % kSlots;
-        const uint32_t ph = (uint32_t)(m >> 1) & 1;
-        mbar_wait(&S.dsn_ready[t], ph);
-        HS_TRACE(4, m, 2);
-        tc_fence_after();
-        const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
-        const Slot& T = S.slot[slot];
-        const uint32_t kb = smem_u32(T.k_mn), db = smem_u32(T.do_mn), qb = smem_u32(T.q_mn);
-#pragma unroll
-        for (int s = 0; s < 8; ++s)  // dQ = dS k            A: D1[:, 64:128)  ->  D2[:, 64:96)
-          umma_tf32_ts(D2 + 64, D1 + 64 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
-        mbar_wait(&S.dst_ready[t], ph);
-        tc_fence_after();
-#pragma unroll
-        for (int s = 0; s < 8; ++s)  // dV = P^T dO          A: D1[:, 0:64)    ->  D2[:, 96:128)
-          umma_tf32_ts(D2 + 96, D1 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
-        HS_TRACE(4, m, 3);
-        // dK overwrites the dS block that dQ has read: tcgen05.mma instructions of one thread execute in issue order
-#pragma unroll
-        for (int s = 0; s < 8; ++s)  // dK = dS^T q          A: D2[:, 0:64)    ->  D1[:, 64:96)
-          umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
-        umma_commit(&S.o_ready[t]);
-        HS_TRACE(4, m, 4);
-      };
       int n = 0;
       for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
         const int slot = n % kSlots, t = n & 1;
@@ -431,9 +427,38 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
         umma_commit(&S.s_ready[t]);
         HS_TRACE(4, n, 1);
-        if (n > 0) issue_outputs(n - 1);
       }
-      if (n > 0) issue_outputs(n - 1);
+    } else if (warp == 10 && elect_one()) {
+      // ================================================================= output MMA issuer (one thread; its own warp so
+      // that issuing the 24 output MMAs of one unit never delays the score MMAs of the next)
+      constexpr uint64_t kDescMN = umma_smem_desc(1024, 512, kLayoutSw128B32);  // MN-major, 4-row k-atoms 512 B apart
+      constexpr uint32_t kIdescO = umma_idesc_tf32(128, 32, 0, 1);
+      int m = 0;
+      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++m) {
+        const int t = m & 1, slot = m % kSlots;
+        const uint32_t ph = (uint32_t)(m >> 1) & 1;
+        const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
+        const Slot& T = S.slot[slot];
+        const uint32_t kb = smem_u32(T.k_mn), db = smem_u32(T.do_mn), qb = smem_u32(T.q_mn);
+        mbar_wait(&S.dsn_ready[t], ph);
+        HS_TRACE(4, m, 2);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 8; ++s)  // dQ = dS k            A: D1[:, 64:128)  ->  D2[:, 64:96)
+          umma_tf32_ts(D2 + 64, D1 + 64 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
+        mbar_wait(&S.dst_ready[t], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 8; ++s)  // dV = P^T dO          A: D1[:, 0:64)    ->  D2[:, 96:128)
+          umma_tf32_ts(D2 + 96, D1 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
+        HS_TRACE(4, m, 3);
+        // dK overwrites the dS block that dQ has read: tcgen05.mma instructions of one thread execute in issue order
+#pragma unroll
+        for (int s = 0; s < 8; ++s)  // dK = dS^T q          A: D2[:, 0:64)    ->  D1[:, 64:96)
+          umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
+        umma_commit(&S.o_ready[t]);
+        HS_TRACE(4, m, 4);
+      }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
@@ -519,7 +544,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       }
       // P^T over S^T for the key rows (the query rows write P into a dead block); dS over S / dS^T over dP^T
       float rs = ds_sweep(R, a.fix2, lse_v, delta_v, vstep, D1, nat ? D1 + 64 : D2,
-                          (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u);
+                          (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u, r & 15);
       rs *= row_scale;  // sum_c dS[r][c] * log2(e) * (eff * cos(r, c))
       tc_fence_before();
       mbar_arrive(nat ? &S.dsn_ready[wg] : &S.dst_ready[wg]);
@@ -615,7 +640,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       float* gb = a.dbias + (long long)h * kWS * kWS;
       for (int idx = threadIdx.x; idx < kWS * kWS; idx += 256) {
         const int i = idx >> 6, j = idx & 63;
-        atomicAdd(gb + idx, S.dbt[0][i * kDbtPitch + j] + S.dbt[1][i * kDbtPitch + j]);
+        const int pos = i * kDbtPitch + 4 * ((j >> 2) ^ (i & 15)) + (j & 3);
+        atomicAdd(gb + idx, S.dbt[0][pos] + S.dbt[1][pos]);
       }
     }
     if (nat && a.cos && a.dlogit) {

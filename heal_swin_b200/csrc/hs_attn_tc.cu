@@ -149,7 +149,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
       }
       __syncwarp();
       // TMA part: arrival 1 of 2 carries the transaction bytes
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t tx = (uint32_t)((valid[0] & contig[0]) + (valid[1] & contig[1])) * 3u * kTile;
         mbar_arrive_expect_tx(&S.full[slot], tx);
 #pragma unroll
@@ -187,8 +187,10 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
       if (lane == 0) mbar_arrive(&S.full[slot]);  // arrival 2 of 2 (publishes the metadata too)
     }
   } else if (warp == 9) {
-    // ================================================================= MMA issuer (one thread)
-    if (lane == 0) {
+    // ================================================================= MMA issuer (one elected thread: with elect.sync
+    // the compiler keeps the descriptors in uniform registers and emits back-to-back UTCHMMA instead of a per-MMA
+    // election loop)
+    if (elect_one()) {
       constexpr uint64_t kDescK = umma_smem_desc(16, 1024, kLayoutSw128);        // K-major, 8-row groups 1024 B apart
       constexpr uint64_t kDescV = umma_smem_desc(1024, 512, kLayoutSw128B32);    // MN-major, 4-row k-atoms 512 B apart
       constexpr uint32_t kIdescS = umma_idesc_tf32(128, 128, 0, 0);
