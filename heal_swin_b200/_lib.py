@@ -40,8 +40,8 @@ SIGNATURES = {
     "hs_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _p],
     "hs_bias_gelu_fwd": [_p, _p, _p, _i64, _i, _p],
     "hs_bias_gelu_bwd": [_p, _p, _p, _p, _p, _i64, _i, _p],
-    "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _p, _i, _i64, _i, _i, _i, _u32, _p],
-    "hs_window_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
+    "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
+    "hs_window_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
 }
 _RESTYPES = {"hs_last_error": C.c_char_p}
 

@@ -1,7 +1,8 @@
 // Backward of the windowed attention core on the sm_100a tensor cores (tcgen05 + TMEM + TMA); window = 64
 // tokens, head_dim = 32, fp32 in / fp32 out, TF32 operands with fp32 accumulation.  Adjoint of
 // hs_attn_tc.cu (reference: autograd of swin_hp_transformer.py:136-171 + the shift / partition / reverse at
-// :319-330).  P is recomputed from q, k (no forward state is needed besides qkv itself).
+// :319-330).  S is recomputed from q, k; the softmax row statistics come from the forward pass (its saved
+// log-sum-exp, and rowsum(P o dP) = dO . O from its output), so no statistics sweep over S is needed.
 //
 // One work unit = one (window, head).  Per unit, with S = q k^T, P = softmax(S*scale + bias + mask), dP = dO v^T,
 // dS = P o (dP - rowsum(P o dP)):
@@ -20,7 +21,7 @@
 // two swizzles (the second fetch hits L2).  HBM traffic per unit: q, k, v, dO in; dq, dk, dv out = 7 x 8 KB.
 //
 // Warp roles (384 threads): warps 0-3 / 4-7 = two elementwise warpgroups (unit n -> group n & 1, TMEM stage n & 1),
-// warp 8 = load producer, warp 9 = score-MMA issuer, warp 10 = output-MMA issuer.  3 shared-memory slots of 56 KB; the output tiles are staged in the
+// warp 8 = load producer, warp 9 = MMA issuer, warps 10-11 = row statistics (from the forward's lse and output).  3 shared-memory slots of 56 KB; the output tiles are staged in the
 // slot's (dead) MN-major tiles and written back by TMA.
 #include <cfloat>
 
@@ -39,6 +40,10 @@ constexpr int kStageCols = 256;  // D1 (128) + D2 (128)
 constexpr int kTmemCols = 512;
 constexpr int kThreads = 384;
 constexpr int kDbtPitch = 64;   // floats; 16-byte chunk c4 of row r is stored at chunk (c4 ^ (r & 15)): conflict-free float4 RMW
+// Output path of the epilogue.  true: every thread writes its 128-byte output row(s) straight from registers (full
+// cache lines); the slot is released immediately.  false: stage the tiles in the slot and TMA-store them (the slot then
+// stays occupied until the TMA engine has read the staging tiles).  Measured at stage 0: direct 1.71 ms, TMA store 1.20 ms.
+constexpr bool kDirectStore = false;
 constexpr int kBiasPitch = 68;  // floats; 16-byte chunk index advances by 17 per row -> conflict-free LDS.128
 
 struct SlotMeta {
@@ -61,18 +66,20 @@ struct Smem {
   float bias[kWS * kBiasPitch];     // bias[i][j] * log2(e); query rows read it row-wise (LDS.128), key rows column-wise
   SlotMeta meta[kSlots];
   float inv[2][2 * kWS];  // per warpgroup: [0,64) 1/max(|q_i|,eps), [64,128) 1/max(|k_j|,eps)
-  float lse[2][kWS];      // per warpgroup: log2-domain row log-sum-exp
-  float delta[2][kWS];    // per warpgroup: rowsum(P o dP)
-  float4 lse4[2][kWS];    // the same, replicated 4x per row: what a query-row thread reads along its own columns
+  float lse[kSlots][kWS];    // per slot (written by the statistics warp): log2-domain log-sum-exp of every query row
+  float delta[kSlots][kWS];  // per slot: rowsum(P o dP) = dO_i . O_i
+  float4 lse4[2][kWS];       // per warpgroup: my row's value replicated 4x (what a query-row thread reads along its columns)
   float4 delta4[2][kWS];
   float dbt[2][kWS * kDbtPitch];  // per warpgroup: dbt[i][j] = sum over its units of dS[i][j] (query-row thread i owns row i)
-  uint64_t full[kSlots], empty[kSlots];
+  uint64_t full[kSlots], empty[kSlots], meta_ready[kSlots], stats_ready[kSlots];
   uint64_t s_ready[2], dsn_ready[2], dst_ready[2], o_ready[2], stage_free[2];
   uint32_t tmem_base;
 };
 
 struct BwdArgs {
   const float* qkv;
+  const float* out;  // forward output (B, N, C)
+  const float* lse;  // forward log2-domain log-sum-exp (H, B*N)
   const float* dout;
   float* dqkv;
   const int32_t* src;
@@ -171,54 +178,6 @@ __device__ __forceinline__ void logits_chunk(const RowCtx& R, const uint32_t (&r
   }
 }
 
-// query-row threads: online softmax statistics of my row -> (log2-domain lse, rowsum(P o dP))
-__device__ __forceinline__ void row_stats(const RowCtx& R, float fix2, float& lse_out, float& delta_out) {
-  float m = -1e30f;
-  float l[4] = {0.f, 0.f, 0.f, 0.f}, dot[4] = {0.f, 0.f, 0.f, 0.f};  // 4 partial sums: short dependency chains
-  auto chunk = [&](const uint32_t (&sraw)[kCW], const uint32_t (&dpr)[kCW], int c0) {
-    float x[kCW], ov[kCW];
-    logits_chunk(R, sraw, c0, x, ov);
-    float cm[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cm[q] = x[q];
-#pragma unroll
-    for (int e = 4; e < kCW; ++e) cm[e & 3] = fmaxf(cm[e & 3], x[e]);
-    const float mn = fmaxf(m, fmaxf(fmaxf(cm[0], cm[1]), fmaxf(cm[2], cm[3])));
-    const float sc = ex2_approx(m - mn);
-    m = mn;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      l[q] *= sc;
-      dot[q] *= sc;
-    }
-#pragma unroll
-    for (int e = 0; e < kCW; ++e) {
-      const float pv = ex2_approx(x[e] - mn);
-      l[e & 3] += pv;
-      dot[e & 3] = fmaf(pv, __uint_as_float(dpr[e]), dot[e & 3]);
-    }
-  };
-  uint32_t sa[kCW], da[kCW], sb[kCW], db[kCW];
-  tmem_ld_chunk(R.s_src, sa);
-  tmem_ld_chunk(R.dp_src, da);
-#pragma unroll 1
-  for (int c0 = 0; c0 < kWS; c0 += 2 * kCW) {
-    tmem_wait_ld();
-    tmem_ld_chunk(R.s_src + c0 + kCW, sb);
-    tmem_ld_chunk(R.dp_src + c0 + kCW, db);
-    chunk(sa, da, c0);
-    tmem_wait_ld();
-    if (c0 + 2 * kCW < kWS) {
-      tmem_ld_chunk(R.s_src + c0 + 2 * kCW, sa);
-      tmem_ld_chunk(R.dp_src + c0 + 2 * kCW, da);
-    }
-    chunk(sb, db, c0 + kCW);
-  }
-  const float lt = (l[0] + l[1]) + (l[2] + l[3]), dt = (dot[0] + dot[1]) + (dot[2] + dot[3]);
-  lse_out = m + lg2_approx(lt);
-  delta_out = dt / lt * fix2;  // dP = dO v^T has two truncated operands
-}
-
 // all threads: p = exp2(logit - lse), dS = p (dP - delta); P and dS (scaled by the other index' 1/norm for cos) go back
 // to TMEM as TF32 A operands; query-row threads also accumulate dS into their warpgroup's dbias tile.
 // lse_v / delta_v: shared addresses of the statistics seen along my columns, `vstep` = 1 (vectors over the query index,
@@ -299,6 +258,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     for (int i = 0; i < kSlots; ++i) {
       mbar_init(&S.full[i], 2);
       mbar_init(&S.empty[i], 128);
+      mbar_init(&S.meta_ready[i], 1);
+      mbar_init(&S.stats_ready[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&S.s_ready[i], 1);
@@ -332,7 +293,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
   const uint32_t tmem = S.tmem_base;
 
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
     if (warp == 8) {
       // ================================================================= load producer
       int n = 0;
@@ -368,6 +329,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         M.groups[lane + 32] = (uint8_t)g1;
         if (lane == 0) M.flags = kFlagValid | (contig ? kFlagContig : 0) | (un ? kFlagUniform : 0);
         __syncwarp();
+        if (lane == 0) mbar_arrive(&S.meta_ready[slot]);  // the statistics warps can start (they read rows[] only)
         if (elect_one()) {
           mbar_arrive_expect_tx(&S.full[slot], contig ? 7u * kTile : 0u);
           if (contig) {
@@ -407,34 +369,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         if (lane == 0) HS_TRACE(5, n, 1);
       }
     } else if (warp == 9 && elect_one()) {
-      // ================================================================= score MMA issuer (one elected thread)
-      constexpr uint64_t kDescK = umma_smem_desc(16, 1024, kLayoutSw128);  // K-major, 8-row groups 1024 B apart
-      constexpr uint32_t kIdescS = umma_idesc_tf32(128, 128, 0, 0);
-      int n = 0;
-      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
-        const int slot = n % kSlots, t = n & 1;
-        mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
-        mbar_wait(&S.stage_free[t], ((uint32_t)(n >> 1) & 1) ^ 1);
-        HS_TRACE(4, n, 0);
-        tc_fence_after();
-        const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
-        const uint32_t qk = smem_u32(S.slot[slot].qk), dov = smem_u32(S.slot[slot].dov);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)  // [Q;K] [Q;K]^T : lanes 0-63 x cols 64-127 = S, lanes 64-127 x cols 0-63 = S^T
-          umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
-#pragma unroll
-        for (int s = 0; s < 4; ++s)  // [dO;V] [dO;V]^T : lanes 0-63 x cols 64-127 = dP, lanes 64-127 x cols 0-63 = dP^T
-          umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
-        umma_commit(&S.s_ready[t]);
-        HS_TRACE(4, n, 1);
-      }
-    } else if (warp == 10 && elect_one()) {
-      // ================================================================= output MMA issuer (one thread; its own warp so
-      // that issuing the 24 output MMAs of one unit never delays the score MMAs of the next)
+      // ================================================================= MMA issuer (one elected thread: with elect.sync the
+      // compiler keeps descriptors in uniform registers and emits back-to-back UTCHMMA)
+      constexpr uint64_t kDescK = umma_smem_desc(16, 1024, kLayoutSw128);       // K-major, 8-row groups 1024 B apart
       constexpr uint64_t kDescMN = umma_smem_desc(1024, 512, kLayoutSw128B32);  // MN-major, 4-row k-atoms 512 B apart
+      constexpr uint32_t kIdescS = umma_idesc_tf32(128, 128, 0, 0);
       constexpr uint32_t kIdescO = umma_idesc_tf32(128, 32, 0, 1);
-      int m = 0;
-      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++m) {
+      auto issue_outputs = [&](int m) {
         const int t = m & 1, slot = m % kSlots;
         const uint32_t ph = (uint32_t)(m >> 1) & 1;
         const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
@@ -458,10 +399,67 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
         umma_commit(&S.o_ready[t]);
         HS_TRACE(4, m, 4);
+      };
+      int n = 0;
+      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
+        const int slot = n % kSlots, t = n & 1;
+        mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
+        mbar_wait(&S.stage_free[t], ((uint32_t)(n >> 1) & 1) ^ 1);
+        HS_TRACE(4, n, 0);
+        tc_fence_after();
+        const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
+        const uint32_t qk = smem_u32(S.slot[slot].qk), dov = smem_u32(S.slot[slot].dov);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)  // [Q;K] [Q;K]^T : lanes 0-63 x cols 64-127 = S, lanes 64-127 x cols 0-63 = S^T
+          umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
+#pragma unroll
+        for (int s = 0; s < 4; ++s)  // [dO;V] [dO;V]^T : lanes 0-63 x cols 64-127 = dP, lanes 64-127 x cols 0-63 = dP^T
+          umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
+        umma_commit(&S.s_ready[t]);
+        HS_TRACE(4, n, 1);
+        if (n > 0) issue_outputs(n - 1);
+      }
+      if (n > 0) issue_outputs(n - 1);
+    } else if (warp >= 10) {
+      // ================================================================= statistics warps (10: even units, 11: odd units).
+      // The softmax row statistics come from the forward pass -- lse from its saved vector, delta_i = sum_j P_ij dP_ij
+      // = dO_i . O_i from its output -- so the elementwise warpgroups need no statistics sweep over S.  They start as
+      // soon as the producer has published the unit's row table, i.e. in parallel with the TMA loads of the slot.
+      int n = 0;
+      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
+        if ((n & 1) != (warp & 1)) continue;
+        const int slot = n % kSlots;
+        mbar_wait(&S.meta_ready[slot], (uint32_t)(n / kSlots) & 1);
+        const SlotMeta& M = S.meta[slot];
+        float4 o[2][8], d[2][8];
+        float lse[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const long long row = M.rows[lane + 32 * k];
+          const float4* orow = reinterpret_cast<const float4*>(a.out + row * a.C + h * kD);
+          const float4* drow = reinterpret_cast<const float4*>(a.dout + row * a.C + h * kD);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            o[k][c] = __ldg(orow + c);
+            d[k][c] = __ldg(drow + c);
+          }
+          lse[k] = __ldg(a.lse + (long long)h * ((long long)a.B * a.N) + row);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          float dot = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            dot += (o[k][c].x * d[k][c].x + o[k][c].y * d[k][c].y) + (o[k][c].z * d[k][c].z + o[k][c].w * d[k][c].w);
+          S.lse[slot][lane + 32 * k] = lse[k];
+          S.delta[slot][lane + 32 * k] = dot;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.stats_ready[slot]);
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     // ================================================================= elementwise + epilogue warpgroups
     const int wg = warp >> 2;              // handles units n with (n & 1) == wg, TMEM stage wg
     const int L = (warp & 3) * 32 + lane;  // TMEM lane
@@ -495,6 +493,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       const int flags = M.flags;
       const uint8_t* myrow = T.qk + L * 128;  // row L of [Q;K]: q_r for the query half, k_r for the key half
 
+      const int my_row = M.rows[r];
       float my_inv = 1.0f;
       if (a.cos) {
         float ss = 0.f;
@@ -505,7 +504,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         }
         my_inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
         S.inv[wg][L] = my_inv;
-        named_bar_sync(1 + wg, 128);
+      }
+      if (a.cos) named_bar_sync(1 + wg, 128);  // the norms of this unit are published
+      mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kSlots) & 1);  // lse / delta of this unit (statistics warp)
+      if (nat) {
+        const float lse = S.lse[slot][r], dl = S.delta[slot][r];
+        S.lse4[wg][r] = make_float4(lse, lse, lse, lse);
+        S.delta4[wg][r] = make_float4(dl, dl, dl, dl);
       }
       const float row_scale = eff * kLog2e * my_inv * a.fix2;  // S = q k^T has two truncated operands
 
@@ -524,24 +529,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       R.cos = a.cos != 0;
       R.has_bias = has_bias;
       R.masked = !(flags & kFlagUniform);
-      uint32_t lse_v, delta_v, vstep;
-      if (nat) {
-        float lse, delta;
-        row_stats(R, a.fix2, lse, delta);
-        S.lse[wg][r] = lse;
-        S.delta[wg][r] = delta;
-        S.lse4[wg][r] = make_float4(lse, lse, lse, lse);
-        S.delta4[wg][r] = make_float4(delta, delta, delta, delta);
-        named_bar_arrive(3 + wg, 128);  // publish to the key-row threads (bar.arrive orders the shared-memory writes)
-        lse_v = smem_u32(&S.lse4[wg][r]);
-        delta_v = smem_u32(&S.delta4[wg][r]);
-        vstep = 0;
-      } else {
-        named_bar_sync(3 + wg, 128);  // row statistics of all 64 query rows are in shared memory
-        lse_v = smem_u32(S.lse[wg]);
-        delta_v = smem_u32(S.delta[wg]);
-        vstep = 1;
-      }
+      const uint32_t lse_v = smem_u32(nat ? (const void*)&S.lse4[wg][r] : (const void*)S.lse[slot]);
+      const uint32_t delta_v = smem_u32(nat ? (const void*)&S.delta4[wg][r] : (const void*)S.delta[slot]);
+      const uint32_t vstep = nat ? 0u : 1u;
       // P^T over S^T for the key rows (the query rows write P into a dead block); dS over S / dS^T over dP^T
       float rs = ds_sweep(R, a.fix2, lse_v, delta_v, vstep, D1, nat ? D1 + 64 : D2,
                           (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u, r & 15);
@@ -571,9 +561,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       const float g = eff * my_inv * a.fix1;  // dS (rounded) x k / q (truncated)
       const bool clamped = my_inv >= 1.0f / kNormEps;
       const float corr = (a.cos && !clamped) ? my_inv * my_inv * rs : 0.f;
-      const int my_row = M.rows[r];
       const int row0 = M.rows[0];
-      const bool contig = (flags & kFlagContig) != 0;
+      const bool contig = !kDirectStore && (flags & kFlagContig) != 0;
       uint8_t* st0 = (nat ? T.q_mn : T.k_mn) + r * 128;
       uint8_t* st1 = T.do_mn + r * 128;
       float* g0 = a.dqkv + (long long)my_row * 3 * a.C + (nat ? 0 : a.C) + h * kD;
@@ -661,10 +650,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
 
 namespace hs {
 
-int window_attn_bwd_tc(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
+int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, const float* dout, const int32_t* src,
+                       const uint8_t* groups,
                        const float* bias, const float* logit_scale, float scale, float* dqkv, float* dbias,
                        float* dlogit, int B, int64_t N, int C, int H, uint32_t flags, cudaStream_t stream) {
-  HS_REQUIRE(qkv && dout && dqkv, "hs_window_attn_bwd: null qkv/dout/dqkv");
+  HS_REQUIRE(qkv && dout && dqkv && out && lse, "hs_window_attn_bwd: null qkv/out/lse/dout/dqkv");
   HS_REQUIRE(!(flags & HS_ATTN_COS) || logit_scale, "hs_window_attn_bwd: cos attention needs logit_scale");
   CUtensorMap map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv;
   const long long rows = (long long)B * N;
@@ -675,7 +665,7 @@ int window_attn_bwd_tc(const float* qkv, const float* dout, const int32_t* src, 
   if ((rc = make_map(&map_do_mn, dout, rows, C, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_map(&map_dqkv, dqkv, rows, 3 * C, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   BwdArgs a{};
-  a.qkv = qkv; a.dout = dout; a.dqkv = dqkv; a.src = src; a.groups = groups; a.bias = bias;
+  a.qkv = qkv; a.out = out; a.lse = lse; a.dout = dout; a.dqkv = dqkv; a.src = src; a.groups = groups; a.bias = bias;
   a.logit_scale = logit_scale; a.dbias = dbias; a.dlogit = dlogit; a.scale = scale;
   a.B = B; a.nW = (int)(N / kWS); a.C = C; a.H = H; a.cos = (flags & HS_ATTN_COS) ? 1 : 0; a.N = N;
   a.total = B * a.nW;

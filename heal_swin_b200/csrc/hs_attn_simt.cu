@@ -27,6 +27,7 @@ struct AttnArgs {
   const float* logit_scale;
   float scale;
   float* out;    // fwd
+  float* lse;    // fwd, optional: (H, B*N) log2-domain log-sum-exp per (head, token)
   float* dqkv;   // bwd
   float* dbias;  // bwd
   float* dlogit; // bwd
@@ -121,7 +122,8 @@ __device__ float load_tile(const AttnArgs& a, const Smem& m, long long wb, int h
 }
 
 // S = (q_eff k^T) * mult + bias + mask, then row softmax in place.  4x4 register tiles when ws % 4 == 0.
-__device__ void logits_softmax(const AttnArgs& a, const Smem& m, long long wb, int h, float mult) {
+__device__ void logits_softmax(const AttnArgs& a, const Smem& m, long long wb, int h, float mult,
+                               float* lse_out = nullptr /* base of this (head, sample): indexed by token */) {
   const int ws = a.ws, D = a.D;
   const int w = (int)(wb % a.nW);
   const float* bias = a.bias ? a.bias + (long long)h * ws * ws : nullptr;
@@ -186,6 +188,7 @@ __device__ void logits_softmax(const AttnArgs& a, const Smem& m, long long wb, i
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
     for (int j = lane; j < ws; j += 32) r[j] *= inv;
+    if (lse_out && lane == 0) lse_out[m.row[i]] = (mx + logf(sum)) * 1.4426950408889634f;
   }
   __syncthreads();
 }
@@ -198,8 +201,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(AttnArgs a) {
   const int ws = a.ws, D = a.D;
   for (long long wb = blockIdx.x; wb < total; wb += gridDim.x) {
     load_tile(a, m, wb, h, false);
-    logits_softmax(a, m, wb, h, 1.0f);
     const int b = (int)(wb / a.nW);
+    logits_softmax(a, m, wb, h, 1.0f, a.lse ? a.lse + ((long long)h * a.B + b) * a.N : nullptr);
     float* obase = a.out + (long long)b * a.N * a.C + (long long)h * D;
     for (int idx = threadIdx.x; idx < ws * D; idx += blockDim.x) {
       const int i = idx / D, dd = idx - i * D;
@@ -369,7 +372,7 @@ int sm_count() {
 namespace hs {
 
 int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* groups, const float* mask,
-                         const float* bias, const float* logit_scale, float scale, float* out, int B,
+                         const float* bias, const float* logit_scale, float scale, float* out, float* lse, int B,
                          int64_t N, int C, int H, int ws, uint32_t flags, cudaStream_t stream) {
   int rc = validate("hs_window_attn_fwd", qkv, B, N, C, H, ws);
   if (rc) return rc;
@@ -377,7 +380,7 @@ int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* gr
   HS_REQUIRE(!(flags & HS_ATTN_COS) || logit_scale, "hs_window_attn_fwd: cos attention needs logit_scale");
   AttnArgs a{};
   a.qkv = qkv; a.src = src; a.groups = groups; a.mask = mask; a.bias = bias; a.logit_scale = logit_scale;
-  a.scale = scale; a.out = out; a.B = B; a.N = N; a.C = C; a.H = H; a.ws = ws; a.D = C / H;
+  a.scale = scale; a.out = out; a.lse = lse; a.B = B; a.N = N; a.C = C; a.H = H; a.ws = ws; a.D = C / H;
   a.nW = (int)(N / ws); a.cos = (flags & HS_ATTN_COS) ? 1 : 0;
   const size_t smem = smem_bytes_fwd(ws, a.D);
   if (smem > 200 * 1024)

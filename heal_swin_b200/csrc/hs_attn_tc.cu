@@ -54,6 +54,7 @@ struct Smem {
 struct TcArgs {
   const float* qkv;
   float* out;
+  float* lse;  // (H, B*N) or null
   const int32_t* src;
   const uint8_t* groups;
   const float* bias;         // (H, 64, 64) or null
@@ -343,6 +344,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
       mbar_arrive(&S.stage_free[wg]);
 
       const float inv = a.fix1 / sum;
+      if (a.lse && (flags & kFlagValid)) {  // log2-domain log-sum-exp of my logits row, for the backward
+        float lg;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(sum));
+        a.lse[(long long)h * ((long long)a.B * a.N) + my_row] = mx + lg;
+      }
       if (flags & kFlagValid) {
         if (flags & kFlagContig) {
           // stage the tile (128B swizzle) and let one thread write it back with a TMA store
@@ -403,7 +409,7 @@ bool window_attn_tc_supported(const float* qkv, const float* out, const float* m
 }
 
 int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* groups, const float* bias,
-                       const float* logit_scale, float scale, float* out, int B, int64_t N, int C, int H,
+                       const float* logit_scale, float scale, float* out, float* lse, int B, int64_t N, int C, int H,
                        uint32_t flags, cudaStream_t stream) {
   HS_REQUIRE(qkv && out, "hs_window_attn_fwd: null qkv/out");
   HS_REQUIRE(!(flags & HS_ATTN_COS) || logit_scale, "hs_window_attn_fwd: cos attention needs logit_scale");
@@ -413,7 +419,7 @@ int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* grou
   if ((rc = make_map(&map_v, qkv, (long long)B * N, 3 * C, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_map(&map_o, out, (long long)B * N, C, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   TcArgs a{};
-  a.qkv = qkv; a.out = out; a.src = src; a.groups = groups; a.bias = bias; a.logit_scale = logit_scale;
+  a.qkv = qkv; a.out = out; a.lse = lse; a.src = src; a.groups = groups; a.bias = bias; a.logit_scale = logit_scale;
   a.scale = scale; a.B = B; a.nW = (int)(N / kWS); a.C = C; a.H = H; a.cos = (flags & HS_ATTN_COS) ? 1 : 0;
   a.N = N; a.total = B * a.nW;
   a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix1;

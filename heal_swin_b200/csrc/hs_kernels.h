@@ -6,7 +6,7 @@
 namespace hs {
 
 int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* groups, const float* mask,
-                         const float* bias, const float* logit_scale, float scale, float* out, int B,
+                         const float* bias, const float* logit_scale, float scale, float* out, float* lse, int B,
                          int64_t N, int C, int H, int ws, uint32_t flags, cudaStream_t stream);
 int window_attn_bwd_simt(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
                          const float* mask, const float* bias, const float* logit_scale, float scale,
@@ -17,10 +17,11 @@ int window_attn_bwd_simt(const float* qkv, const float* dout, const int32_t* src
 bool window_attn_tc_supported(const float* qkv, const float* out, const float* mask, int B, int64_t N, int C, int H,
                               int ws);
 int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* groups, const float* bias,
-                       const float* logit_scale, float scale, float* out, int B, int64_t N, int C, int H,
+                       const float* logit_scale, float scale, float* out, float* lse, int B, int64_t N, int C, int H,
                        uint32_t flags, cudaStream_t stream);
 
-int window_attn_bwd_tc(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
+int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, const float* dout, const int32_t* src,
+                       const uint8_t* groups,
                        const float* bias, const float* logit_scale, float scale, float* dqkv, float* dbias,
                        float* dlogit, int B, int64_t N, int C, int H, uint32_t flags, cudaStream_t stream);
 

@@ -116,11 +116,13 @@ class WindowAttnCore(torch.autograd.Function):
         ls = _f32c(logit_scale.reshape(-1)) if (use_cos and logit_scale is not None) else None
         mask = _f32c(dense_mask) if dense_mask is not None else None
         out = torch.empty((B, N, Cc), device=qkv.device, dtype=torch.float32)
+        # log2-domain log-sum-exp per (head, token): lets the backward skip the softmax-statistics pass
+        lse = torch.empty((H, B * N), device=qkv.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         flags = ((_lib.ATTN_COS if use_cos else 0) | (_lib.ATTN_NO_TC if _ATTN_PRECISION == "fp32" else 0)
                  | (_lib.ATTN_NO_TRUNC_COMP if os.environ.get("HEALSWIN_NO_TRUNC_COMP") == "1" else 0))
         STATS.launch("window_attn_fwd", lib.hs_window_attn_fwd, ptr(qkv), ptr(src), ptr(groups), ptr(mask), ptr(bias),
-                     ptr(ls), C.c_float(scale), ptr(out), B, N, Cc, H, ws, flags, stream, tag=(B, N, Cc, H, ws))
-        ctx.save_for_backward(qkv, bias, ls, src, groups, mask, rel_index_i32)
+                     ptr(ls), C.c_float(scale), ptr(out), ptr(lse), B, N, Cc, H, ws, flags, stream, tag=(B, N, Cc, H, ws))
+        ctx.save_for_backward(qkv, bias, ls, src, groups, mask, rel_index_i32, out, lse)
         ctx.meta = (scale, H, ws, flags, bias_table is not None,
                     None if bias_table is None else tuple(bias_table.shape),
                     None if logit_scale is None else tuple(logit_scale.shape))
@@ -128,7 +130,7 @@ class WindowAttnCore(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, bias, ls, src, groups, mask, rel_index = ctx.saved_tensors
+        qkv, bias, ls, src, groups, mask, rel_index, out, lse = ctx.saved_tensors
         scale, H, ws, flags, has_table, table_shape, ls_shape = ctx.meta
         dout = _f32c(dout)
         B, N, C3 = qkv.shape
@@ -139,7 +141,7 @@ class WindowAttnCore(torch.autograd.Function):
         need_ls = (ls is not None) and ctx.needs_input_grad[2]
         dbias = torch.zeros((H, ws, ws), device=qkv.device, dtype=torch.float32) if need_table else None
         dls = torch.zeros((H,), device=qkv.device, dtype=torch.float32) if need_ls else None
-        STATS.launch("window_attn_bwd", lib.hs_window_attn_bwd, ptr(qkv), ptr(dout), ptr(src), ptr(groups), ptr(mask),
+        STATS.launch("window_attn_bwd", lib.hs_window_attn_bwd, ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(src), ptr(groups), ptr(mask),
                      ptr(bias), ptr(ls), C.c_float(scale), ptr(dqkv), ptr(dbias), ptr(dls), B, N, Cc, H, ws,
                      flags, stream, tag=(B, N, Cc, H, ws))
         dtable = None

@@ -108,16 +108,21 @@ int hs_rel_bias_reduce(const float* dbias_dev, const int32_t* index_dev, float* 
  *   logit_scale (H)     raw parameter (cos attention: logits *= exp(min(ls, log 100))); else NULL
  *   scale               q scaling for the non-cos path (head_dim^-0.5 or qk_scale)
  *   out   (B, N, C)     attention output in the UNSHIFTED token order, row layout [H][D]
+ *   lse   (H, B*N)      optional (may be NULL): per (head, token) log2-domain log-sum-exp of the logits row, saved for
+ *                       the backward (which then needs no softmax-statistics pass)
  */
 int hs_window_attn_fwd(const float* qkv_dev, const int32_t* src_dev, const uint8_t* groups_dev,
                        const float* mask_dev, const float* bias_dev, const float* logit_scale_dev,
-                       float scale, float* out_dev, int B, int64_t N, int C, int H, int ws,
+                       float scale, float* out_dev, float* lse_dev, int B, int64_t N, int C, int H, int ws,
                        uint32_t flags, void* stream);
 /*
  * Adjoint of hs_window_attn_fwd.  dqkv (B, N, 3C) is fully overwritten.  dbias (H, ws, ws) and
- * dlogit_scale (H) are accumulated into (+=), either may be NULL.
+ * dlogit_scale (H) are accumulated into (+=), either may be NULL.  out / lse are the forward's outputs (the
+ * tensor-core path uses them: rowsum(dO o O) and exp2(logit - lse) replace the statistics pass); with either NULL
+ * the exact-fp32 kernels, which recompute everything from qkv, are used.
  */
-int hs_window_attn_bwd(const float* qkv_dev, const float* dout_dev, const int32_t* src_dev,
+int hs_window_attn_bwd(const float* qkv_dev, const float* out_dev, const float* lse_dev, const float* dout_dev,
+                       const int32_t* src_dev,
                        const uint8_t* groups_dev, const float* mask_dev, const float* bias_dev,
                        const float* logit_scale_dev, float scale, float* dqkv_dev, float* dbias_dev,
                        float* dlogit_scale_dev, int B, int64_t N, int C, int H, int ws,

@@ -12,13 +12,15 @@ int main(int argc, char** argv) {
   const long long N = 196608;
   const int cos = argc > 1 ? atoi(argv[1]) : 1;
   const size_t nq = (size_t)B * N * 3 * C, no = (size_t)B * N * C;
-  float *qkv, *dout, *dqkv, *bias, *ls, *dbias, *dls;
+  float *qkv, *dout, *dqkv, *bias, *ls, *dbias, *dls, *outp, *lse;
   cudaMalloc(&qkv, nq * 4); cudaMalloc(&dout, no * 4); cudaMalloc(&dqkv, nq * 4);
+  cudaMalloc(&outp, no * 4); cudaMalloc(&lse, (size_t)H * B * N * 4); cudaMemset(lse, 0, (size_t)H * B * N * 4);
   cudaMalloc(&bias, H * 64 * 64 * 4); cudaMalloc(&ls, H * 4); cudaMalloc(&dbias, H * 64 * 64 * 4); cudaMalloc(&dls, H * 4);
   std::vector<float> h(1 << 22);
   for (auto& v : h) v = (float)rand() / RAND_MAX - 0.5f;
   for (size_t off = 0; off < nq; off += h.size()) cudaMemcpy(qkv + off, h.data(), std::min(h.size(), nq - off) * 4, cudaMemcpyHostToDevice);
   for (size_t off = 0; off < no; off += h.size()) cudaMemcpy(dout + off, h.data(), std::min(h.size(), no - off) * 4, cudaMemcpyHostToDevice);
+  for (size_t off = 0; off < no; off += h.size()) cudaMemcpy(outp + off, h.data(), std::min(h.size(), no - off) * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(bias, h.data(), H * 64 * 64 * 4, cudaMemcpyHostToDevice);
   float hls[3] = {2.3f, 2.1f, 2.5f};
   cudaMemcpy(ls, hls, 12, cudaMemcpyHostToDevice);
@@ -26,7 +28,7 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    int rc = hs::window_attn_bwd_tc(qkv, dout, nullptr, nullptr, bias, cos ? ls : nullptr, 0.1767f, dqkv, dbias, dls, B, N, C, H,
+    int rc = hs::window_attn_bwd_tc(qkv, outp, lse, dout, nullptr, nullptr, bias, cos ? ls : nullptr, 0.1767f, dqkv, dbias, dls, B, N, C, H,
                                     cos ? HS_ATTN_COS : 0, 0);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
