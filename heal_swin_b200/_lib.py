@@ -19,7 +19,7 @@ ATTN_NO_TRUNC_COMP = 4
 STRATEGY_CODES = {"nest_roll": SHIFT_NEST_ROLL, "nest_grid_shift": SHIFT_NEST_GRID, "ring_shift": SHIFT_RING}
 
 _p = C.c_void_p
-_i, _i64, _u32, _f = C.c_int, C.c_int64, C.c_uint32, C.c_float
+_i, _i64, _u32, _f, _u64 = C.c_int, C.c_int64, C.c_uint32, C.c_float, C.c_uint64
 
 # name -> argtypes; restype is int (status) unless listed in _RESTYPES.  tests/test_abi.py checks
 # that every function declared in include/healswin_b200.h appears here and is exported.
@@ -40,8 +40,8 @@ SIGNATURES = {
     "hs_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _p],
     "hs_bias_gelu_fwd": [_p, _p, _p, _i64, _i, _p],
     "hs_bias_gelu_bwd": [_p, _p, _p, _p, _p, _i64, _i, _p],
-    "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
-    "hs_window_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _p, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
+    "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _f, _u64, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
+    "hs_window_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _u64, _p, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
 }
 _RESTYPES = {"hs_last_error": C.c_char_p}
 

@@ -90,6 +90,9 @@ struct BwdArgs {
   float* dlogit;             // (H) or null, accumulated
   float scale;
   float fix1, fix2;  // TF32 truncation compensation (hs_tc_common.cuh), 1.0 when disabled
+  uint32_t drop_thresh;  // attention-probability dropout (0 = off), see hs_common.h
+  float drop_scale;
+  uint64_t seed;
   int B, nW, C, H, cos;
   long long N;
   int total;  // B * nW units per head
@@ -128,6 +131,11 @@ struct RowCtx {
   float row_scale;         // log2(e) * scale (* my 1/|row| for cos) * truncation fix
   int my_group;
   bool cos, has_bias, masked;
+  // attention dropout: element (i, j) of the unit; my row is index `drop_r`, columns run over the other index
+  uint32_t drop_key, drop_thresh;  // thresh 0 = off
+  float drop_scale;
+  int drop_r;
+  bool drop_row_is_query;  // query-row thread: (i, j) = (drop_r, c); key-row thread: (i, j) = (c, drop_r); also set without dropout
 };
 
 constexpr int kCW = 8;  // columns per chunk of the elementwise loops (16 was measured slower: 1.44 vs 1.27 ms)
@@ -183,9 +191,13 @@ __device__ __forceinline__ void logits_chunk(const RowCtx& R, const uint32_t (&r
 // lse_v / delta_v: shared addresses of the statistics seen along my columns, `vstep` = 1 (vectors over the query index,
 // key-row threads) or 0 (my own row's 4-fold copy, query-row threads).  Returns sum_c dS_c * raw_c (for cos).
 // dbt_row: shared address of my row of the dbias tile (0 = none); 16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 15)).
+template <bool kDrop>
 __device__ __forceinline__ float ds_sweep(const RowCtx& R, float fix2, uint32_t lse_v, uint32_t delta_v, uint32_t vstep,
                                           uint32_t p_dst, uint32_t ds_dst, uint32_t dbt_row, int dbt_xor) {
-  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+  // rs = sum_c dS_c * w_c with w = raw * (1/norm of the other index) (the cos logit up to my row's scale).  In exact
+  // arithmetic sum_c dS_c = 0 along a query row, so any constant may be subtracted from w: the P-weighted mean of w is
+  // subtracted (sds * pw) so that an error of the row's delta (it now comes from the forward output) is not amplified.
+  float rs[4] = {0.f, 0.f, 0.f, 0.f}, sds[2] = {0.f, 0.f}, pw[2] = {0.f, 0.f};
   auto chunk = [&](const uint32_t (&sraw)[kCW], const uint32_t (&dpr)[kCW], int c0) {
     float x[kCW], ov[kCW], lv[kCW], dv[kCW], ds[kCW];
     logits_chunk(R, sraw, c0, x, ov);
@@ -205,10 +217,23 @@ __device__ __forceinline__ float ds_sweep(const RowCtx& R, float fix2, uint32_t 
 #pragma unroll
     for (int e = 0; e < kCW; ++e) {
       const float pv = ex2_approx(x[e] - lv[e]);
-      ds[e] = pv * fmaf(__uint_as_float(dpr[e]), fix2, -dv[e]);
+      float dpe = __uint_as_float(dpr[e]) * fix2, pd = pv;
+      if (kDrop) {  // O = dropout(P) V:  dP -> dP o m,  the P fed to dV is P o m   (m = 0 or 1 / (1 - p))
+        const int c = c0 + e;
+        const bool keep = R.drop_row_is_query ? hs::drop_keep(R.drop_key, R.drop_r, c, kWS, R.drop_thresh)
+                                              : hs::drop_keep(R.drop_key, c, R.drop_r, kWS, R.drop_thresh);
+        const float mk = keep ? R.drop_scale : 0.f;
+        dpe *= mk;
+        pd *= mk;
+      }
+      ds[e] = pv * (dpe - dv[e]);
       const float u = ds[e] * ov[e];
       rs[e & 3] = fmaf(u, __uint_as_float(sraw[e]), rs[e & 3]);
-      pa[e] = __float_as_uint(tf32_rna(pv));
+      if (R.cos) {
+        sds[e & 1] += ds[e];
+        pw[e & 1] = fmaf(pv * ov[e], __uint_as_float(sraw[e]), pw[e & 1]);
+      }
+      pa[e] = __float_as_uint(tf32_rna(pd));
       ua[e] = __float_as_uint(tf32_rna(u));
     }
     // the chunk of S / dP at these columns has been consumed: overwrite in place
@@ -241,9 +266,12 @@ __device__ __forceinline__ float ds_sweep(const RowCtx& R, float fix2, uint32_t 
     chunk(sb, db, c0 + kCW);
   }
   tmem_wait_st();
-  return (rs[0] + rs[1]) + (rs[2] + rs[3]);
+  // (only along a query row: the column sums of dS seen by the key-row threads do not vanish)
+  const float centre = R.drop_row_is_query ? (sds[0] + sds[1]) * (pw[0] + pw[1]) : 0.f;
+  return (rs[0] + rs[1]) + (rs[2] + rs[3]) - centre;
 }
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_constant__ CUtensorMap map_qkv_mn,
                    const __grid_constant__ CUtensorMap map_do_k, const __grid_constant__ CUtensorMap map_do_mn,
@@ -529,11 +557,16 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       R.cos = a.cos != 0;
       R.has_bias = has_bias;
       R.masked = !(flags & kFlagUniform);
+      R.drop_thresh = a.drop_thresh;
+      R.drop_scale = a.drop_scale;
+      R.drop_key = a.drop_thresh ? hs::drop_unit_key(a.seed, unit, h, a.H) : 0u;
+      R.drop_r = r;
+      R.drop_row_is_query = nat;
       const uint32_t lse_v = smem_u32(nat ? (const void*)&S.lse4[wg][r] : (const void*)S.lse[slot]);
       const uint32_t delta_v = smem_u32(nat ? (const void*)&S.delta4[wg][r] : (const void*)S.delta[slot]);
       const uint32_t vstep = nat ? 0u : 1u;
       // P^T over S^T for the key rows (the query rows write P into a dead block); dS over S / dS^T over dP^T
-      float rs = ds_sweep(R, a.fix2, lse_v, delta_v, vstep, D1, nat ? D1 + 64 : D2,
+      float rs = ds_sweep<kDrop>(R, a.fix2, lse_v, delta_v, vstep, D1, nat ? D1 + 64 : D2,
                           (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u, r & 15);
       rs *= row_scale;  // sum_c dS[r][c] * log2(e) * (eff * cos(r, c))
       tc_fence_before();
@@ -651,9 +684,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
 namespace hs {
 
 int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, const float* dout, const int32_t* src,
-                       const uint8_t* groups,
-                       const float* bias, const float* logit_scale, float scale, float* dqkv, float* dbias,
-                       float* dlogit, int B, int64_t N, int C, int H, uint32_t flags, cudaStream_t stream) {
+                       const uint8_t* groups, const float* bias, const float* logit_scale, float scale, DropCfg drop,
+                       float* dqkv, float* dbias, float* dlogit, int B, int64_t N, int C, int H, uint32_t flags,
+                       cudaStream_t stream) {
   HS_REQUIRE(qkv && dout && dqkv && out && lse, "hs_window_attn_bwd: null qkv/out/lse/dout/dqkv");
   HS_REQUIRE(!(flags & HS_ATTN_COS) || logit_scale, "hs_window_attn_bwd: cos attention needs logit_scale");
   CUtensorMap map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv;
@@ -671,17 +704,24 @@ int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, con
   a.total = B * a.nW;
   a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix1;
   a.fix2 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix2;
+  a.drop_thresh = drop.p > 0.f ? hs::drop_thresh(drop.p) : 0u;
+  a.drop_scale = 1.0f / (1.0f - drop.p);
+  a.seed = drop.seed;
   const size_t smem = sizeof(Smem) + 1024;
   static bool attr_done = false;  // benign race: the attribute is idempotent
   if (!attr_done) {
-    HS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   int gx = sm_count() / H;
   if (gx < 1) gx = 1;
   if (gx > a.total) gx = a.total;
   dim3 grid(gx, H);
-  attn_bwd_tc_kernel<<<grid, kThreads, smem, stream>>>(map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, a);
+  if (a.drop_thresh)
+    attn_bwd_tc_kernel<true><<<grid, kThreads, smem, stream>>>(map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, a);
+  else
+    attn_bwd_tc_kernel<false><<<grid, kThreads, smem, stream>>>(map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, a);
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

@@ -9,6 +9,7 @@
 #include <cfloat>
 
 #include "hs_common.h"
+#include "hs_kernels.h"
 
 namespace {
 
@@ -36,6 +37,9 @@ struct AttnArgs {
   int C, H, ws, D;
   int nW;        // windows per sample
   int cos;
+  uint32_t drop_thresh;  // 0 = no attention dropout
+  float drop_scale;      // 1 / (1 - p)
+  uint64_t seed;
 };
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -123,7 +127,8 @@ __device__ float load_tile(const AttnArgs& a, const Smem& m, long long wb, int h
 
 // S = (q_eff k^T) * mult + bias + mask, then row softmax in place.  4x4 register tiles when ws % 4 == 0.
 __device__ void logits_softmax(const AttnArgs& a, const Smem& m, long long wb, int h, float mult,
-                               float* lse_out = nullptr /* base of this (head, sample): indexed by token */) {
+                               float* lse_out = nullptr /* base of this (head, sample): indexed by token */,
+                               bool drop_in_place = false) {
   const int ws = a.ws, D = a.D;
   const int w = (int)(wb % a.nW);
   const float* bias = a.bias ? a.bias + (long long)h * ws * ws : nullptr;
@@ -189,6 +194,10 @@ __device__ void logits_softmax(const AttnArgs& a, const Smem& m, long long wb, i
     const float inv = 1.0f / sum;
     for (int j = lane; j < ws; j += 32) r[j] *= inv;
     if (lse_out && lane == 0) lse_out[m.row[i]] = (mx + logf(sum)) * 1.4426950408889634f;
+    if (drop_in_place) {  // forward: attn = dropout(softmax(.))   [swin_hp_transformer.py:165-169]
+      const uint32_t key = hs::drop_unit_key(a.seed, wb, h, a.H);
+      for (int j = lane; j < ws; j += 32) r[j] = hs::drop_keep(key, i, j, ws, a.drop_thresh) ? r[j] * a.drop_scale : 0.f;
+    }
   }
   __syncthreads();
 }
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_kernel(AttnArgs a) {
   for (long long wb = blockIdx.x; wb < total; wb += gridDim.x) {
     load_tile(a, m, wb, h, false);
     const int b = (int)(wb / a.nW);
-    logits_softmax(a, m, wb, h, 1.0f, a.lse ? a.lse + ((long long)h * a.B + b) * a.N : nullptr);
+    logits_softmax(a, m, wb, h, 1.0f, a.lse ? a.lse + ((long long)h * a.B + b) * a.N : nullptr, a.drop_thresh != 0);
     float* obase = a.out + (long long)b * a.N * a.C + (long long)h * D;
     for (int idx = threadIdx.x; idx < ws * D; idx += blockDim.x) {
       const int i = idx / D, dd = idx - i * D;
@@ -243,12 +252,16 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
       dO[i * m.ldq + dd] = dob[(long long)m.row[i] * a.C + dd];
     }
     logits_softmax(a, m, wb, h, eff);  // m.s = P  (syncs inside also publish dO)
+    const uint32_t dkey = hs::drop_unit_key(a.seed, wb, h, a.H);
+    auto dmask = [&](int i, int j) -> float {  // dropout multiplier of P[i][j]: 0 or 1 / (1 - p)
+      return (a.drop_thresh == 0) ? 1.0f : (hs::drop_keep(dkey, i, j, ws, a.drop_thresh) ? a.drop_scale : 0.f);
+    };
     float* dqkv_b = a.dqkv + (long long)b * a.N * 3 * a.C + (long long)h * D;
     // dV[j] = sum_i P[i][j] dO[i]
     for (int idx = threadIdx.x; idx < ws * D; idx += blockDim.x) {
       const int j = idx / D, dd = idx - j * D;
       float acc = 0.f;
-      for (int i = 0; i < ws; ++i) acc = fmaf(m.s[i * m.lds + j], dO[i * m.ldq + dd], acc);
+      for (int i = 0; i < ws; ++i) acc = fmaf(m.s[i * m.lds + j] * dmask(i, j), dO[i * m.ldq + dd], acc);
       dqkv_b[(long long)m.row[j] * 3 * a.C + 2 * a.C + dd] = acc;
     }
     __syncthreads();
@@ -259,13 +272,13 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_kernel(AttnArgs a) {
       for (int j = lane; j < ws; j += 32) {
         float dp = 0.f;
         for (int dd = 0; dd < D; ++dd) dp = fmaf(dO[i * m.ldq + dd], m.v[j * m.ldq + dd], dp);
-        dot = fmaf(pr[j], dp, dot);
+        dot = fmaf(pr[j], dp * dmask(i, j), dot);
       }
       dot = warp_sum(dot);
       for (int j = lane; j < ws; j += 32) {
         float dp = 0.f;
         for (int dd = 0; dd < D; ++dd) dp = fmaf(dO[i * m.ldq + dd], m.v[j * m.ldq + dd], dp);
-        const float ds = pr[j] * (dp - dot);
+        const float ds = pr[j] * (dp * dmask(i, j) - dot);
         pr[j] = ds;
         if (dB) dB[i * ws + j] += ds;  // (i, j) owned by exactly one thread of this CTA
       }
@@ -372,8 +385,8 @@ int sm_count() {
 namespace hs {
 
 int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* groups, const float* mask,
-                         const float* bias, const float* logit_scale, float scale, float* out, float* lse, int B,
-                         int64_t N, int C, int H, int ws, uint32_t flags, cudaStream_t stream) {
+                         const float* bias, const float* logit_scale, float scale, DropCfg drop, float* out, float* lse,
+                         int B, int64_t N, int C, int H, int ws, uint32_t flags, cudaStream_t stream) {
   int rc = validate("hs_window_attn_fwd", qkv, B, N, C, H, ws);
   if (rc) return rc;
   HS_REQUIRE(out != nullptr, "hs_window_attn_fwd: null out");
@@ -382,6 +395,7 @@ int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* gr
   a.qkv = qkv; a.src = src; a.groups = groups; a.mask = mask; a.bias = bias; a.logit_scale = logit_scale;
   a.scale = scale; a.out = out; a.lse = lse; a.B = B; a.N = N; a.C = C; a.H = H; a.ws = ws; a.D = C / H;
   a.nW = (int)(N / ws); a.cos = (flags & HS_ATTN_COS) ? 1 : 0;
+  a.drop_thresh = drop.p > 0.f ? hs::drop_thresh(drop.p) : 0u; a.drop_scale = 1.0f / (1.0f - drop.p); a.seed = drop.seed;
   const size_t smem = smem_bytes_fwd(ws, a.D);
   if (smem > 200 * 1024)
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_window_attn_fwd: window %d x head_dim %d needs %zu B of shared memory", ws, a.D, smem);
@@ -397,7 +411,7 @@ int window_attn_fwd_simt(const float* qkv, const int32_t* src, const uint8_t* gr
 }
 
 int window_attn_bwd_simt(const float* qkv, const float* dout, const int32_t* src, const uint8_t* groups,
-                         const float* mask, const float* bias, const float* logit_scale, float scale,
+                         const float* mask, const float* bias, const float* logit_scale, float scale, DropCfg drop,
                          float* dqkv, float* dbias, float* dlogit, int B, int64_t N, int C, int H, int ws,
                          uint32_t flags, cudaStream_t stream) {
   int rc = validate("hs_window_attn_bwd", qkv, B, N, C, H, ws);
@@ -409,6 +423,7 @@ int window_attn_bwd_simt(const float* qkv, const float* dout, const int32_t* src
   a.logit_scale = logit_scale; a.scale = scale; a.dqkv = dqkv; a.dbias = dbias; a.dlogit = dlogit;
   a.B = B; a.N = N; a.C = C; a.H = H; a.ws = ws; a.D = C / H; a.nW = (int)(N / ws);
   a.cos = (flags & HS_ATTN_COS) ? 1 : 0;
+  a.drop_thresh = drop.p > 0.f ? hs::drop_thresh(drop.p) : 0u; a.drop_scale = 1.0f / (1.0f - drop.p); a.seed = drop.seed;
   const size_t smem = smem_bytes_bwd(ws, a.D, dbias != nullptr);
   if (smem > 200 * 1024)
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_window_attn_bwd: window %d x head_dim %d needs %zu B of shared memory", ws, a.D, smem);

@@ -61,12 +61,16 @@ struct TcArgs {
   const float* logit_scale;  // (H) or null
   float scale;
   float fix1, fix2;  // TF32 truncation compensation (hs_tc_common.cuh), 1.0 when disabled
+  uint32_t drop_thresh;  // attention-probability dropout (kDrop instantiation only), see hs_common.h
+  float drop_scale;
+  uint64_t seed;
   int B, nW, C, H, cos;
   long long N;
   int total;  // B * nW units per head
 };
 
 
+template <bool kDrop>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_v,
                    const __grid_constant__ CUtensorMap map_o, const TcArgs a) {
@@ -323,11 +327,16 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
 #pragma unroll
       for (int j = 1; j < kWS; ++j) mx = fmaxf(mx, x[j]);
       float sum = 0.f;
+      uint32_t drop_key = 0;
+      if (kDrop) drop_key = hs::drop_unit_key(a.seed, (long long)pair * 2 + u, h, a.H);
 #pragma unroll
       for (int j = 0; j < kWS; ++j) {
         const float p = tf32_rna(ex2_approx(x[j] - mx));
-        sum += p;
-        sr[j] = __float_as_uint(p);
+        sum += p;  // softmax normalisation is over the undropped probabilities
+        if (kDrop)
+          sr[j] = hs::drop_keep(drop_key, i, j, kWS, a.drop_thresh) ? __float_as_uint(tf32_rna(p * a.drop_scale)) : 0u;
+        else
+          sr[j] = __float_as_uint(p);
       }
       tmem_st32(stage + lane_addr + u * 64, sr);
       tmem_st32(stage + lane_addr + u * 64 + 32, sr + 32);
@@ -409,8 +418,8 @@ bool window_attn_tc_supported(const float* qkv, const float* out, const float* m
 }
 
 int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* groups, const float* bias,
-                       const float* logit_scale, float scale, float* out, float* lse, int B, int64_t N, int C, int H,
-                       uint32_t flags, cudaStream_t stream) {
+                       const float* logit_scale, float scale, DropCfg drop, float* out, float* lse, int B, int64_t N,
+                       int C, int H, uint32_t flags, cudaStream_t stream) {
   HS_REQUIRE(qkv && out, "hs_window_attn_fwd: null qkv/out");
   HS_REQUIRE(!(flags & HS_ATTN_COS) || logit_scale, "hs_window_attn_fwd: cos attention needs logit_scale");
   CUtensorMap map_qk, map_v, map_o;
@@ -424,18 +433,25 @@ int window_attn_fwd_tc(const float* qkv, const int32_t* src, const uint8_t* grou
   a.N = N; a.total = B * a.nW;
   a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix1;
   a.fix2 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : kTruncFix2;
+  a.drop_thresh = drop.p > 0.f ? hs::drop_thresh(drop.p) : 0u;
+  a.drop_scale = 1.0f / (1.0f - drop.p);
+  a.seed = drop.seed;
   const int npairs = (a.total + 1) / 2;
   const size_t smem = sizeof(Smem) + 1024;
   static bool attr_done = false;  // benign race: the attribute is idempotent
   if (!attr_done) {
-    HS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HS_CUDA(cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   int gx = sm_count() / H;
   if (gx < 1) gx = 1;
   if (gx > npairs) gx = npairs;
   dim3 grid(gx, H);
-  attn_fwd_tc_kernel<<<grid, kThreads, smem, stream>>>(map_qk, map_v, map_o, a);
+  if (a.drop_thresh)
+    attn_fwd_tc_kernel<true><<<grid, kThreads, smem, stream>>>(map_qk, map_v, map_o, a);
+  else
+    attn_fwd_tc_kernel<false><<<grid, kThreads, smem, stream>>>(map_qk, map_v, map_o, a);
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

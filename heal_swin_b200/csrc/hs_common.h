@@ -15,6 +15,32 @@ int fail(int code, const char* fmt, ...);
 
 }  // namespace hs
 
+// ---- attention-probability dropout (swin_hp_transformer.py:167, nn.Dropout(attn_drop) on the softmax output) ----
+// Counter-based: whether P[i][j] of (window-in-batch wb, head h) is kept is a pure function of (seed, wb, h, i, j), so
+// the forward, the backward and both orientations of the tensor-core backward regenerate identical masks without
+// storing them.  lowbias32 integer mix; an entry is dropped when its hash is below p * 2^32.
+#if defined(__CUDACC__)
+#define HS_HD __host__ __device__ __forceinline__
+#else
+#define HS_HD inline
+#endif
+namespace hs {
+HS_HD uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+HS_HD uint32_t drop_unit_key(uint64_t seed, long long wb, int h, int H) {
+  return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + (uint32_t)(wb * H + h)));
+}
+HS_HD bool drop_keep(uint32_t unit_key, int i, int j, int ws, uint32_t thresh) {
+  return mix32(unit_key ^ ((uint32_t)(i * ws + j) * 0x9E3779B9u)) >= thresh;
+}
+HS_HD uint32_t drop_thresh(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+}  // namespace hs
+
 #define HS_REQUIRE(cond, ...)                                  \
   do {                                                         \
     if (!(cond)) return hs::fail(HS_ERR_ARG, __VA_ARGS__);     \

@@ -99,15 +99,13 @@ class WindowAttention(nn.Module):
         self.softmax = nn.Softmax(dim=-1)
 
     def _core(self, qkv, window_size, src, groups, dense_mask):
-        if self.training and self.attn_drop.p > 0.0:
-            raise NotImplementedError(
-                "attention-probability dropout (attn_drop > 0 in training mode) is not implemented in the "
-                "fused attention kernel yet; set attn_drop_rate=0.")
+        # nn.Dropout(attn_drop) on the softmax output (:167-169) runs inside the kernel (counter-based mask)
+        drop_p = self.attn_drop.p if self.training else 0.0
         table = self.relative_position_bias_table if self.rel_pos_bias is not None else None
         rel_index = self._hs_rel_index if table is not None else None
         logit_scale = self.logit_scale if self.use_cos_attn else None
         return ops.window_attention_core(qkv, table, logit_scale, src, groups, dense_mask, rel_index,
-                                         self.scale, self.num_heads, window_size, self.use_cos_attn)
+                                         self.scale, self.num_heads, window_size, self.use_cos_attn, attn_drop=drop_p)
 
     def forward_tokens(self, x, window_size, src=None, groups=None):
         """Fused path used by SwinTransformerBlock: x is the (B, N, C) token tensor in its natural

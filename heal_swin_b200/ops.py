@@ -91,13 +91,27 @@ class GatherRows(torch.autograd.Function):
         return out, None, None
 
 
+_DROP_CALLS = 0
+
+
+def _next_dropout_seed() -> int:
+    """64-bit seed of one attention-dropout mask: derived from torch's CPU seed (so torch.manual_seed makes runs
+    reproducible), the rank (different masks on different data shards) and a per-call counter -- no device sync."""
+    global _DROP_CALLS
+    _DROP_CALLS += 1
+    x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + int(os.environ.get("RANK", "0")) * 0xD1B54A32D192ED03
+         + _DROP_CALLS * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF
+    x ^= x >> 31
+    return (x * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+
+
 class WindowAttnCore(torch.autograd.Function):
     """shift -> window_partition -> softmax(q k^T [cos] + bias + mask) v -> window_reverse -> shift_back
     on a packed (B, N, 3C) qkv tensor (swin_hp_transformer.py:136-171, 319-330)."""
 
     @staticmethod
     def forward(ctx, qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
-                scale, num_heads, window_size, use_cos):
+                scale, num_heads, window_size, use_cos, attn_drop=0.0, seed=0):
         require_cuda(qkv)
         qkv = _f32c(qkv)
         B, N, C3 = qkv.shape
@@ -121,8 +135,10 @@ class WindowAttnCore(torch.autograd.Function):
         flags = ((_lib.ATTN_COS if use_cos else 0) | (_lib.ATTN_NO_TC if _ATTN_PRECISION == "fp32" else 0)
                  | (_lib.ATTN_NO_TRUNC_COMP if os.environ.get("HEALSWIN_NO_TRUNC_COMP") == "1" else 0))
         STATS.launch("window_attn_fwd", lib.hs_window_attn_fwd, ptr(qkv), ptr(src), ptr(groups), ptr(mask), ptr(bias),
-                     ptr(ls), C.c_float(scale), ptr(out), ptr(lse), B, N, Cc, H, ws, flags, stream, tag=(B, N, Cc, H, ws))
+                     ptr(ls), C.c_float(scale), C.c_float(attn_drop), C.c_uint64(seed), ptr(out), ptr(lse), B, N, Cc, H, ws,
+                     flags, stream, tag=(B, N, Cc, H, ws))
         ctx.save_for_backward(qkv, bias, ls, src, groups, mask, rel_index_i32, out, lse)
+        ctx.drop = (float(attn_drop), int(seed))
         ctx.meta = (scale, H, ws, flags, bias_table is not None,
                     None if bias_table is None else tuple(bias_table.shape),
                     None if logit_scale is None else tuple(logit_scale.shape))
@@ -142,7 +158,8 @@ class WindowAttnCore(torch.autograd.Function):
         dbias = torch.zeros((H, ws, ws), device=qkv.device, dtype=torch.float32) if need_table else None
         dls = torch.zeros((H,), device=qkv.device, dtype=torch.float32) if need_ls else None
         STATS.launch("window_attn_bwd", lib.hs_window_attn_bwd, ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(src), ptr(groups), ptr(mask),
-                     ptr(bias), ptr(ls), C.c_float(scale), ptr(dqkv), ptr(dbias), ptr(dls), B, N, Cc, H, ws,
+                     ptr(bias), ptr(ls), C.c_float(scale), C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dqkv),
+                     ptr(dbias), ptr(dls), B, N, Cc, H, ws,
                      flags, stream, tag=(B, N, Cc, H, ws))
         dtable = None
         if need_table:
@@ -151,13 +168,18 @@ class WindowAttnCore(torch.autograd.Function):
                          table_shape[0], H, ws, stream)
         if need_ls:
             dls = dls.reshape(ls_shape)
-        return dqkv, dtable, dls, None, None, None, None, None, None, None, None
+        return dqkv, dtable, dls, None, None, None, None, None, None, None, None, None, None
 
 
 def window_attention_core(qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
-                          scale, num_heads, window_size, use_cos):
+                          scale, num_heads, window_size, use_cos, attn_drop=0.0, seed=None):
+    """``attn_drop`` > 0 applies dropout to the attention probabilities inside the kernel (training mode of
+    ``nn.Dropout(attn_drop)``, swin_hp_transformer.py:167-169); ``seed`` fixes the mask (default: a fresh one)."""
+    attn_drop = float(attn_drop)
+    if attn_drop > 0.0 and seed is None:
+        seed = _next_dropout_seed()
     return WindowAttnCore.apply(qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
-                                float(scale), num_heads, window_size, bool(use_cos))
+                                float(scale), num_heads, window_size, bool(use_cos), attn_drop, int(seed or 0))
 
 
 class LayerNormFn(torch.autograd.Function):

@@ -110,11 +110,15 @@ int hs_rel_bias_reduce(const float* dbias_dev, const int32_t* index_dev, float* 
  *   out   (B, N, C)     attention output in the UNSHIFTED token order, row layout [H][D]
  *   lse   (H, B*N)      optional (may be NULL): per (head, token) log2-domain log-sum-exp of the logits row, saved for
  *                       the backward (which then needs no softmax-statistics pass)
+ *   attn_drop, seed     dropout of the attention probabilities (nn.Dropout(attn_drop) at :167-169, training mode): entry
+ *                       (i, j) of a (window, head) is zeroed with probability attn_drop and the rest scaled by
+ *                       1 / (1 - attn_drop); the mask is a pure function of (seed, window, head, i, j), so the backward
+ *                       must be given the same seed.  attn_drop = 0 disables it.
  */
 int hs_window_attn_fwd(const float* qkv_dev, const int32_t* src_dev, const uint8_t* groups_dev,
                        const float* mask_dev, const float* bias_dev, const float* logit_scale_dev,
-                       float scale, float* out_dev, float* lse_dev, int B, int64_t N, int C, int H, int ws,
-                       uint32_t flags, void* stream);
+                       float scale, float attn_drop, uint64_t seed, float* out_dev, float* lse_dev, int B, int64_t N,
+                       int C, int H, int ws, uint32_t flags, void* stream);
 /*
  * Adjoint of hs_window_attn_fwd.  dqkv (B, N, 3C) is fully overwritten.  dbias (H, ws, ws) and
  * dlogit_scale (H) are accumulated into (+=), either may be NULL.  out / lse are the forward's outputs (the
@@ -124,8 +128,8 @@ int hs_window_attn_fwd(const float* qkv_dev, const int32_t* src_dev, const uint8
 int hs_window_attn_bwd(const float* qkv_dev, const float* out_dev, const float* lse_dev, const float* dout_dev,
                        const int32_t* src_dev,
                        const uint8_t* groups_dev, const float* mask_dev, const float* bias_dev,
-                       const float* logit_scale_dev, float scale, float* dqkv_dev, float* dbias_dev,
-                       float* dlogit_scale_dev, int B, int64_t N, int C, int H, int ws,
+                       const float* logit_scale_dev, float scale, float attn_drop, uint64_t seed, float* dqkv_dev,
+                       float* dbias_dev, float* dlogit_scale_dev, int B, int64_t N, int C, int H, int ws,
                        uint32_t flags, void* stream);
 
 /*

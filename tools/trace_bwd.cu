@@ -28,7 +28,7 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) {
     cudaEventRecord(e0);
-    int rc = hs::window_attn_bwd_tc(qkv, outp, lse, dout, nullptr, nullptr, bias, cos ? ls : nullptr, 0.1767f, dqkv, dbias, dls, B, N, C, H,
+    int rc = hs::window_attn_bwd_tc(qkv, outp, lse, dout, nullptr, nullptr, bias, cos ? ls : nullptr, 0.1767f, hs::DropCfg{0.f, 0}, dqkv, dbias, dls, B, N, C, H,
                                     cos ? HS_ATTN_COS : 0, 0);
     cudaEventRecord(e1);
     cudaError_t err = cudaDeviceSynchronize();
