@@ -57,13 +57,14 @@ class Mlp(nn.Module):
         follows in the v2 placement).  fc1's bias add, the GELU and (backward) fc1's bias gradient are one kernel."""
         if not self._fusable():
             return self.forward(x), None
-        h = ops.bias_gelu(F.linear(x, self.fc1.weight), self.fc1.bias)
-        return F.linear(h, self.fc2.weight), self.fc2.bias
+        h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias)
+        return ops.linear(h, self.fc2.weight), self.fc2.bias
 
     def forward(self, x):
         if not self._fusable():
-            return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
-        return self.fc2(ops.bias_gelu(F.linear(x, self.fc1.weight), self.fc1.bias))
+            h = self.drop(self.act(ops.linear(x, self.fc1.weight, self.fc1.bias)))
+            return self.drop(ops.linear(h, self.fc2.weight, self.fc2.bias))
+        return ops.linear(ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias), self.fc2.weight, self.fc2.bias)
 
 
 class WindowAttention(nn.Module):
@@ -110,27 +111,27 @@ class WindowAttention(nn.Module):
     def forward_tokens(self, x, window_size, src=None, groups=None):
         """Fused path used by SwinTransformerBlock: x is the (B, N, C) token tensor in its natural
         (unshifted) order; ``src``/``groups`` are the block's shift tables (None = no shift)."""
-        out = self._core(self.qkv(x), window_size, src, groups, None)
-        return self.proj_drop(self.proj(out))
+        out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), window_size, src, groups, None)
+        return self.proj_drop(ops.linear(out, self.proj.weight, self.proj.bias))
 
     def forward_tokens_split(self, x, window_size, src=None, groups=None):
         """As forward_tokens, but returns (proj output WITHOUT its bias, that bias or None) so that the caller can fuse
         the bias add into the LayerNorm that follows (v2 norm placement)."""
         if self.proj.bias is None or (self.training and self.proj_drop.p > 0.0):
             return self.forward_tokens(x, window_size, src, groups), None
-        out = self._core(self.qkv(x), window_size, src, groups, None)
-        return F.linear(out, self.proj.weight), self.proj.bias
+        out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), window_size, src, groups, None)
+        return ops.linear(out, self.proj.weight), self.proj.bias
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:124-174]"""
         B_, n, C = x.shape
-        qkv = self.qkv(x)
+        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
         if mask is not None:
             nW = mask.shape[0]
             assert B_ % nW == 0
             qkv = qkv.reshape(B_ // nW, nW * n, 3 * C)
         out = self._core(qkv, n, None, None, mask)
-        return self.proj_drop(self.proj(out.reshape(B_, n, C)))
+        return self.proj_drop(ops.linear(out.reshape(B_, n, C), self.proj.weight, self.proj.bias))
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}"
@@ -236,7 +237,7 @@ class PatchMerging(nn.Module):
         assert N % 4 == 0, f"x size {N} is not divisible by 4 as necessary for patching."
         # cat(x[:,0::4], ..., x[:,3::4]) on the channel axis is a plain view in nested order
         x = x.contiguous().view(B, N // 4, 4 * C)
-        return self.reduction(ops.layer_norm(x, self.norm))
+        return ops.linear(ops.layer_norm(x, self.norm), self.reduction.weight, self.reduction.bias)
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}"
@@ -255,7 +256,8 @@ class PatchExpand(nn.Module):
         self.norm = norm_layer(dim * dim_scale // 4)
 
     def forward(self, x):
-        x = self.expand(x)
+        if isinstance(self.expand, nn.Linear):
+            x = ops.linear(x, self.expand.weight, self.expand.bias)
         B, N, C = x.shape
         return ops.layer_norm(x.contiguous().view(B, 4 * N, C // 4), self.norm)
 
@@ -275,7 +277,7 @@ class FinalPatchExpand_X4(nn.Module):
         self.norm = norm_layer(self.output_dim)
 
     def forward(self, x):
-        x = self.expand(x)
+        x = ops.linear(x, self.expand.weight, self.expand.bias)
         B, N, C = x.shape
         return ops.layer_norm(x.contiguous().view(B, N * self.patch_size, C // self.patch_size), self.norm)
 
@@ -367,7 +369,7 @@ class PatchEmbed(nn.Module):
         # already the contiguous (B, N/patch, C) token tensor (the conv gives (B, C, N/patch) and a strided view)
         p = self.config.patch_size
         patches = x.reshape(B, C, N // p, p).permute(0, 2, 1, 3).reshape(B, N // p, C * p)
-        x = F.linear(patches, self.proj.weight.reshape(self.proj.weight.shape[0], C * p), self.proj.bias)
+        x = ops.linear(patches, self.proj.weight.reshape(self.proj.weight.shape[0], C * p), self.proj.bias)
         if self.norm is not None:
             x = self.norm(x)
         return x
@@ -410,12 +412,12 @@ class UnetDecoder(nn.Module):
         for inx, layer_up in enumerate(self.layers_up):
             if inx > 0:
                 x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
-                x = self.concat_back_dim[inx](x)
+                x = ops.linear(x, self.concat_back_dim[inx].weight, self.concat_back_dim[inx].bias)
             x = layer_up(x)
         x = self.up(ops.layer_norm(x, self.norm_up))
         # Conv1d(kernel 1, no bias) over channels == Linear on the token-major tensor: the (B, N_pix, C) activation is
         # never transposed, only the f_out-channel result is
-        y = F.linear(x, self.output.weight[:, :, 0])
+        y = ops.linear(x, self.output.weight[:, :, 0])
         return y.permute(0, 2, 1).contiguous()
 
 

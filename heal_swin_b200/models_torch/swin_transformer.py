@@ -138,25 +138,26 @@ class WindowAttention(nn.Module):
 
     def forward_tokens(self, x, n_tokens, src=None, groups=None):
         """x: (B, H*W, C) in raster order; ``src`` / ``groups``: the block's window-slot tables."""
-        return self.proj_drop(self.proj(self._core(self.qkv(x), n_tokens, src, groups, None)))
+        out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), n_tokens, src, groups, None)
+        return self.proj_drop(ops.linear(out, self.proj.weight, self.proj.bias))
 
     def forward_tokens_split(self, x, n_tokens, src=None, groups=None):
         """(proj output WITHOUT its bias, that bias or None): the bias add is fused into the following LayerNorm."""
         if self.proj.bias is None or (self.training and self.proj_drop.p > 0.0):
             return self.forward_tokens(x, n_tokens, src, groups), None
-        out = self._core(self.qkv(x), n_tokens, src, groups, None)
-        return F.linear(out, self.proj.weight), self.proj.bias
+        out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), n_tokens, src, groups, None)
+        return ops.linear(out, self.proj.weight), self.proj.bias
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:148-202]"""
         B_, n, C = x.shape
-        qkv = self.qkv(x)
+        qkv = ops.linear(x, self.qkv.weight, self.qkv.bias)
         if mask is not None:
             nW = mask.shape[0]
             assert B_ % nW == 0
             qkv = qkv.reshape(B_ // nW, nW * n, 3 * C)
         out = self._core(qkv, n, None, None, mask)
-        return self.proj_drop(self.proj(out.reshape(B_, n, C)))
+        return self.proj_drop(ops.linear(out.reshape(B_, n, C), self.proj.weight, self.proj.bias))
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}, window_size={self.window_size}, num_heads={self.num_heads}"
@@ -255,7 +256,7 @@ class PatchMerging(nn.Module):
         assert L == H * W, "input feature has wrong size"
         assert H % 2 == 0 and W % 2 == 0, f"x size ({H}*{W}) are not even."
         x = self.gather(x).view(B, L // 4, 4 * C)
-        return self.reduction(ops.layer_norm(x, self.norm))
+        return ops.linear(ops.layer_norm(x, self.norm), self.reduction.weight, self.reduction.bias)
 
     def extra_repr(self) -> str:
         return f"input_resolution={self.input_resolution}, dim={self.dim}"
@@ -282,7 +283,8 @@ class PatchExpand(nn.Module):
 
     def forward(self, x):
         H, W = self.input_resolution
-        x = self.expand(x)
+        if isinstance(self.expand, nn.Linear):
+            x = ops.linear(x, self.expand.weight, self.expand.bias)
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
         x = self.shuffle(x.contiguous().view(B, L * 4, C // self.dim_scale))
@@ -305,7 +307,7 @@ class FinalPatchExpand_X4(nn.Module):
 
     def forward(self, x):
         H, W = self.input_resolution
-        x = self.expand(x)
+        x = ops.linear(x, self.expand.weight, self.expand.bias)
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
         pp = self.patch_size[0] * self.patch_size[1]
@@ -399,7 +401,7 @@ class PatchEmbed(nn.Module):
         # Conv2d(k = s = patch) == Linear over the (f_in x p1 x p2) values of every patch -> contiguous (B, L, C) tokens
         p1, p2 = self.config.patch_size[0], self.config.patch_size[1]
         patches = x.reshape(B, C, H // p1, p1, W // p2, p2).permute(0, 2, 4, 1, 3, 5).reshape(B, -1, C * p1 * p2)
-        x = F.linear(patches, self.proj.weight.reshape(self.proj.weight.shape[0], -1), self.proj.bias)
+        x = ops.linear(patches, self.proj.weight.reshape(self.proj.weight.shape[0], -1), self.proj.bias)
         if self.norm is not None:
             x = self.norm(x)
         return x
@@ -536,7 +538,7 @@ class SwinTransformerSys(nn.Module):
         for inx, layer_up in enumerate(self.layers_up):
             if inx > 0:
                 x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
-                x = self.concat_back_dim[inx](x)
+                x = ops.linear(x, self.concat_back_dim[inx].weight, self.concat_back_dim[inx].bias)
             x = layer_up(x)
         return ops.layer_norm(x, self.norm_up)
 
@@ -547,7 +549,7 @@ class SwinTransformerSys(nn.Module):
         if self.config.final_upsample == "expand_first":
             x = self.up(x)
             # 1x1 Conv2d (no bias) == Linear over channels on the token-major tensor; only the result is transposed
-            y = F.linear(x, self.output.weight[:, :, 0, 0])
+            y = ops.linear(x, self.output.weight[:, :, 0, 0])
             x = y.view(B, self.config.patch_size[0] * H, self.config.patch_size[1] * W, -1).permute(0, 3, 1, 2).contiguous()
         return x
 

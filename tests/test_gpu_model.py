@@ -61,3 +61,24 @@ def test_outputs_are_plain_writable_tensors():
         y = model(torch.from_numpy(gold["x"]).to(dev))
     y[:, 0] = y[:, 0].exp()
     assert torch.isfinite(y).all()
+
+
+TF32_GEMM_FWD_TOL = 2e-3
+
+
+def test_forward_error_with_tf32_library_gemms_is_bounded():
+    """bench.py runs the library GEMMs (cuBLAS) in TF32 like the reference's pinned torch 1.8 did by default.  TF32 GEMMs
+    alone put the network output 1.1-1.4e-3 away from the fp32 oracle (measured, scripts/tf32_model_check.py), slightly
+    outside the 1e-3 bound that holds with fp32 GEMMs (tests above); this pins the documented figure at 2e-3."""
+    dev = torch.device("cuda:0")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        for name in ("ring_cos_v2_ws64", "roll_v1_ws64"):
+            kw, cfg, sd, gold = load_model_case(name)
+            model = build_product_model(kw, sd, dev).eval()
+            with torch.no_grad():
+                y = model(torch.from_numpy(gold["x"]).to(dev))
+            assert rel_err(y.cpu(), gold["y"]) < TF32_GEMM_FWD_TOL, name
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
