@@ -301,6 +301,8 @@ def run_ours(a):
             return tag[0] * tag[1] * 4 * 3
         if name == "gather_rows":
             return tag[0] * tag[1] * tag[2] * 4 * 2
+        if name == "linear_wgrad":     # dy (T, N), x (T, K) in; dw negligible
+            return tag[0] * (tag[1] + tag[2]) * 4
         if name == "bias_gelu_fwd":    # z in, h out
             return tag[0] * tag[1] * 4 * 2
         if name == "bias_gelu_bwd":    # dh, z in, dz out

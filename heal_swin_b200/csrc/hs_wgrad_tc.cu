@@ -1,0 +1,177 @@
+// Weight gradient of a Linear on the sm_100a tensor cores: dW[n][k] += sum_t dY[t][n] * X[t][k]  (t = tokens).
+// This is the one dense GEMM of the path where the library falls well short of the HBM roofline (cuBLAS picks a legacy
+// split-K kernel: 1.8-3x the roofline time at the BASELINE stage-0/1 shapes, scripts/wgrad_check.py), because the
+// contraction runs over the 10^5..10^6 tokens and both operands are "MN-major" (tokens are rows in memory).
+//
+// D[p][q] = sum_t P[t][p] * Q[t][q]:  P = the operand with the larger feature count (128-row blocks of D, one per CTA
+// column), Q = the smaller one (<= 256 columns = one tcgen05.mma N).  Both tiles are fetched by TMA exactly as they lie in
+// memory (64 tokens x 32 features per box, SWIZZLE_128B_ATOM_32B) and consumed as MN-major TF32 operands: a 32-feature
+// slab is 64 rows of 128 B; descriptor LBO = slab stride (8192 B), SBO = 512 B, a K = 8 (token) step advances 1024 B
+// (operand form pinned on hardware with tools/probe_mn.cu, profiles/r1j_probe_mn_major.log).  The token range is split
+// over the CTAs (persistent accumulation in TMEM over a CTA's whole token range), partial results are added atomically.
+#include "hs_common.h"
+#include "hs_sm100.cuh"
+#include "hs_tc_common.cuh"
+
+namespace {
+
+using namespace hs::sm100;
+
+constexpr int kTT = 64;                  // tokens per pipeline stage
+constexpr int kSlab = kTT * 128;         // bytes of one 32-feature slab of a stage
+constexpr int kThreads = 192;            // warps 0-3 epilogue, 4 producer, 5 MMA
+constexpr int kMaxStages = 4;
+
+struct WgArgs {
+  float* out;
+  long long ldo_p, ldo_q;  // out[p * ldo_p + q * ldo_q]
+  long long T;             // tokens
+  int NP, NQ;              // feature counts of P (rows of D) and Q (columns of D, <= 256, multiple of 32)
+  int p_blocks, splits, stages;
+  float fix;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant__ CUtensorMap map_q, const WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[kMaxStages], empty[kMaxStages], done;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_slabs = a.NQ / 32;
+  const int stage_bytes = (4 + q_slabs) * kSlab;
+  const int pb = blockIdx.x % a.p_blocks, split = blockIdx.x / a.p_blocks;
+  const int p0 = pb * 128;
+  int p_slabs = (a.NP - p0 + 31) / 32;  // slabs of this block that touch the tensor (the rest stay zero)
+  if (p_slabs > 4) p_slabs = 4;
+  const long long tiles = (a.T + kTT - 1) / kTT;
+  const long long per = (tiles + a.splits - 1) / a.splits;
+  const long long t_lo = split * per, t_hi = (t_lo + per < tiles) ? t_lo + per : tiles;
+
+  // slabs of P that lie entirely outside the tensor are never loaded: zero them once
+  for (int s = 0; s < a.stages; ++s)
+    for (int i = threadIdx.x; i < (4 - p_slabs) * (kSlab / 16); i += kThreads)
+      reinterpret_cast<float4*>(sm + s * stage_bytes + p_slabs * kSlab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(&done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc(&tmem_base, 256);
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_p);
+    tma_prefetch_desc(&map_q);
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      int n = 0;
+      for (long long t = t_lo; t < t_hi; ++t, ++n) {
+        const int s = n % a.stages;
+        mbar_wait(&empty[s], (((uint32_t)(n / a.stages)) & 1) ^ 1);
+        uint8_t* st = sm + s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], (uint32_t)((p_slabs + q_slabs) * kSlab));
+        const int row = (int)(t * kTT);
+        for (int j = 0; j < p_slabs; ++j) tma_load_2d(st + j * kSlab, &map_p, &full[s], p0 + 32 * j, row);
+        for (int j = 0; j < q_slabs; ++j) tma_load_2d(st + (4 + j) * kSlab, &map_q, &full[s], 32 * j, row);
+      }
+    }
+  } else if (warp == 5) {
+    if (elect_one()) {
+      constexpr uint64_t kDesc = umma_smem_desc(kSlab, 512, kLayoutSw128B32);
+      const uint32_t idesc = umma_idesc_tf32(128, a.NQ, 1, 1);
+      int n = 0;
+      for (long long t = t_lo; t < t_hi; ++t, ++n) {
+        const int s = n % a.stages;
+        mbar_wait(&full[s], ((uint32_t)(n / a.stages)) & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sm + s * stage_bytes), qa = pa + 4 * kSlab;
+#pragma unroll
+        for (int ks = 0; ks < kTT / 8; ++ks)
+          umma_tf32_ss(tmem, umma_desc_at(kDesc, pa + ks * 1024), umma_desc_at(kDesc, qa + ks * 1024), idesc,
+                       (n > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(&done);
+    }
+  } else {
+    // ================================================================= epilogue: D tile -> global (atomic add)
+    if (t_hi > t_lo) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+      const int p = p0 + warp * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
+      for (int c0 = 0; c0 < a.NQ; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_addr + c0, r);
+        tmem_wait_ld();
+        if (p < a.NP) {
+          float* dst = a.out + (long long)p * a.ldo_p + (long long)c0 * a.ldo_q;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * a.ldo_q, __uint_as_float(r[c]) * a.fix);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+extern "C" {
+
+// 1 if hs_linear_wgrad handles dW (N, K) from dY (T, N), X (T, K); otherwise the caller keeps the library GEMM
+int hs_linear_wgrad_supported(int64_t T, int N, int K) {
+  if (T < 4096 || N < 32 || K < 32 || (N % 4) || (K % 4)) return 0;
+  const int q = N < K ? N : K;
+  return (q % 32 == 0 && q <= 256) ? 1 : 0;
+}
+
+int hs_linear_wgrad(const float* dy, const float* x, float* dw, int64_t T, int N, int K, uint32_t flags, void* stream) {
+  HS_REQUIRE(dy && x && dw && T > 0 && N > 0 && K > 0, "hs_linear_wgrad: bad arguments");
+  if (!hs_linear_wgrad_supported(T, N, K))
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: shape T=%lld N=%d K=%d is not covered (min(N, K) must be a "
+                    "multiple of 32 and <= 256)", (long long)T, N, K);
+  HS_REQUIRE(!((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15), "hs_linear_wgrad: unaligned input");
+  // P = operand with more features (rows of D), Q = the other (<= 256 columns)
+  const bool p_is_dy = N >= K;
+  const float* P = p_is_dy ? dy : x;
+  const float* Q = p_is_dy ? x : dy;
+  WgArgs a{};
+  a.out = dw; a.T = T;
+  a.NP = p_is_dy ? N : K; a.NQ = p_is_dy ? K : N;
+  a.ldo_p = p_is_dy ? K : 1; a.ldo_q = p_is_dy ? 1 : K;
+  a.p_blocks = (a.NP + 127) / 128;
+  const long long tiles = (T + kTT - 1) / kTT;
+  int splits = hs::tc::sm_count() / a.p_blocks;
+  if (splits < 1) splits = 1;
+  if (splits > tiles) splits = (int)tiles;
+  a.splits = splits;
+  const int stage_bytes = (4 + a.NQ / 32) * kSlab;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: stage does not fit");
+  a.stages = stages;
+  a.fix = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix2;
+  CUtensorMap map_p, map_q;
+  int rc;
+  if ((rc = hs::tc::make_map(&map_p, P, T, a.NP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT))) return rc;
+  if ((rc = hs::tc::make_map(&map_q, Q, T, a.NQ, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT))) return rc;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  HS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  wgrad_tc_kernel<<<a.p_blocks * a.splits, kThreads, smem, (cudaStream_t)stream>>>(map_p, map_q, a);
+  HS_LAUNCH_CHECK();
+  return HS_OK;
+}
+
+}  // extern "C"

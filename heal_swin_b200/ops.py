@@ -281,5 +281,44 @@ def bias_gelu(z, bias):
 # compensate there; keeping only the qkv projection in fp32 gains 6 % error for 28 % time: not worth it).
 
 
+_CUSTOM_WGRAD = os.environ.get("HEALSWIN_CUSTOM_WGRAD", "1") == "1"
+
+
+class _LinearFn(torch.autograd.Function):
+    """F.linear whose weight gradient dW = dY^T X runs on the hand-written token-split tcgen05 kernel
+    (csrc/hs_wgrad_tc.cu); forward and input gradient stay library GEMMs (they already sit on the HBM roofline at the
+    large stages, scripts/wgrad_check.py)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = _f32c(dy).reshape(-1, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = (dy2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            x2 = _f32c(x).reshape(-1, K)
+            T = x2.shape[0]
+            dw = torch.zeros((N, K), device=x.device, dtype=torch.float32)
+            STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), T, N, K, 0, current_stream(),
+                         tag=(T, N, K))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy2.sum(0)
+        return dx, dw, db
+
+
 def linear(x, weight, bias=None):
+    """``F.linear``.  When TF32 matmuls are enabled and the shape is covered, the weight gradient uses the hand-written
+    kernel; everything else is the library GEMM."""
+    if (_CUSTOM_WGRAD and x.is_cuda and x.dtype == torch.float32 and weight.requires_grad and torch.is_grad_enabled()
+            and torch.backends.cuda.matmul.allow_tf32 and weight.dim() == 2 and weight.is_contiguous()
+            and lib.hs_linear_wgrad_supported(x.numel() // x.shape[-1], weight.shape[0], weight.shape[1])):
+        return _LinearFn.apply(x, weight, bias)
     return torch.nn.functional.linear(x, weight, bias)

@@ -1,0 +1,93 @@
+"""GPU parity of the tcgen05 weight-gradient kernel (dW = dY^T X, TF32 operands, fp32 accumulation) through the C-ABI
+against the fp32 torch product.  Tolerance 2e-3 relative L2 (TF32 operands); exactness checks use TF32-representable data."""
+import pytest
+import torch
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3
+
+
+def _wgrad(dy, x):
+    import ctypes as C
+
+    from heal_swin_b200 import _lib
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    T, N = dy.shape
+    K = x.shape[1]
+    assert lib.hs_linear_wgrad_supported(T, N, K)
+    dw = torch.zeros(N, K, device=dy.device)
+    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), T, N, K, 0, current_stream()))
+    return dw
+
+
+@pytest.mark.parametrize("T,N,K", [(8192, 288, 96), (8192, 96, 96), (8192, 384, 96), (8192, 96, 384), (5000, 576, 192),
+                                   (4096 + 37, 192, 768), (8192, 32, 64), (20000, 100, 64), (8192, 1152, 256)])
+def test_wgrad_matches_fp32_product(T, N, K):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T + N + K)
+    dy = torch.randn(T, N, generator=g).to(dev)
+    x = torch.randn(T, K, generator=g).to(dev)
+    got = _wgrad(dy, x)
+    want = (dy.double().t() @ x.double()).float()
+    assert rel_err(got.cpu(), want.cpu()) < TOL
+
+
+def test_wgrad_exact_on_tf32_representable_data_and_accumulates():
+    """Small integers are exact in TF32 and the sums stay below 2^24: the result must be bit-exact once the truncation
+    compensation is switched off; a second call accumulates (+=)."""
+    import ctypes as C
+
+    from heal_swin_b200 import _lib
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    dev = torch.device("cuda:0")
+    T, N, K = 16384, 288, 96
+    g = torch.Generator().manual_seed(1)
+    dy = torch.randint(-4, 5, (T, N), generator=g).float().to(dev)
+    x = torch.randint(-4, 5, (T, K), generator=g).float().to(dev)
+    dw = torch.zeros(N, K, device=dev)
+    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), T, N, K, _lib.ATTN_NO_TRUNC_COMP, current_stream()))
+    want = (dy.double().t() @ x.double()).float()
+    assert torch.equal(dw, want)
+    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), T, N, K, _lib.ATTN_NO_TRUNC_COMP, current_stream()))
+    assert torch.equal(dw, 2 * want)
+
+
+def test_linear_autograd_uses_the_kernel_under_tf32_and_matches():
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(4, 4096, 96, generator=g).to(dev).requires_grad_(True)
+        lin = torch.nn.Linear(96, 288).to(dev)
+        wgt = torch.randn(4, 4096, 288, generator=g).to(dev)
+        ops.STATS.reset()
+        y = ops.linear(x, lin.weight, lin.bias)
+        (y * wgt).sum().backward()
+        assert ops.STATS.launches == 1  # the wgrad kernel
+        got = (lin.weight.grad.clone(), lin.bias.grad.clone(), x.grad.clone())
+        lin.weight.grad = lin.bias.grad = x.grad = None
+        torch.backends.cuda.matmul.allow_tf32 = False
+        y2 = torch.nn.functional.linear(x, lin.weight, lin.bias)
+        (y2 * wgt).sum().backward()
+        for a, b in zip(got, (lin.weight.grad, lin.bias.grad, x.grad)):
+            assert rel_err(a.cpu(), b.cpu()) < TOL
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_wgrad_full_size_linearity():
+    """BASELINE stage-0 token count (8 x 196608): dW is linear in dY (size-independent property)."""
+    dev = torch.device("cuda:0")
+    T, N, K = 8 * 196608, 288, 96
+    x = torch.randn(T, K, device=dev)
+    d1 = torch.randn(T, N, device=dev)
+    d2 = torch.randn(T, N, device=dev)
+    w1, w2, w12 = _wgrad(d1, x), _wgrad(d2, x), _wgrad(d1 + 0.5 * d2, x)
+    assert rel_err((w1 + 0.5 * w2).cpu(), w12.cpu()) < TOL
