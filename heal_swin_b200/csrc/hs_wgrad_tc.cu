@@ -24,11 +24,12 @@ constexpr int kMaxStages = 4;
 
 struct WgArgs {
   float* out;
+  float* colsum;  // optional (NP): colsum[p] += sum_t P[t][p]  -- the bias gradient when P = dY; needs NQ + 32 <= 256
   long long ldo_p, ldo_q;  // out[p * ldo_p + q * ldo_q]
   long long T;             // tokens
   int NP, NQ;              // feature counts of P (rows of D) and Q (columns of D, <= 256, multiple of 32)
   int p_blocks, splits, stages;
-  float fix;
+  float fix, fix1;  // truncation compensation for two / one truncated operand
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -39,7 +40,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_slabs = a.NQ / 32;
-  const int stage_bytes = (4 + q_slabs) * kSlab;
+  const int ones = a.colsum ? 1 : 0;  // one extra Q slab holding the constant column (1, 0, ..., 0)
+  const int stage_bytes = (4 + q_slabs + ones) * kSlab;
   const int pb = blockIdx.x % a.p_blocks, split = blockIdx.x / a.p_blocks;
   const int p0 = pb * 128;
   int p_slabs = (a.NP - p0 + 31) / 32;  // slabs of this block that touch the tensor (the rest stay zero)
@@ -52,6 +54,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
   for (int s = 0; s < a.stages; ++s)
     for (int i = threadIdx.x; i < (4 - p_slabs) * (kSlab / 16); i += kThreads)
       reinterpret_cast<float4*>(sm + s * stage_bytes + p_slabs * kSlab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (ones)
+    for (int s = 0; s < a.stages; ++s) {
+      uint8_t* slab = sm + s * stage_bytes + (4 + q_slabs) * kSlab;
+      for (int i = threadIdx.x; i < kSlab / 16; i += kThreads) reinterpret_cast<float4*>(slab)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  __syncthreads();
+  if (ones && threadIdx.x < kTT)  // feature 0 of every token row = 1 (16-byte chunk 0 of row r sits at (r & 3) << 5)
+    for (int s = 0; s < a.stages; ++s)
+      *reinterpret_cast<float*>(sm + s * stage_bytes + (4 + q_slabs) * kSlab + threadIdx.x * 128 + ((threadIdx.x & 3) << 5)) = 1.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full[s], 1);
@@ -87,7 +98,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
   } else if (warp == 5) {
     if (elect_one()) {
       constexpr uint64_t kDesc = umma_smem_desc(kSlab, 512, kLayoutSw128B32);
-      const uint32_t idesc = umma_idesc_tf32(128, a.NQ, 1, 1);
+      const uint32_t idesc = umma_idesc_tf32(128, a.NQ + 32 * ones, 1, 1);
       int n = 0;
       for (long long t = t_lo; t < t_hi; ++t, ++n) {
         const int s = n % a.stages;
@@ -119,6 +130,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
           for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * a.ldo_q, __uint_as_float(r[c]) * a.fix);
         }
       }
+      if (ones) {  // column NQ of D = sum_t P[t][p] * 1
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_addr + a.NQ, r);
+        tmem_wait_ld();
+        if (p < a.NP) atomicAdd(a.colsum + p, __uint_as_float(r[0]) * a.fix1);
+      }
     }
   }
   tc_fence_before();
@@ -130,14 +147,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
 
 extern "C" {
 
-// 1 if hs_linear_wgrad handles dW (N, K) from dY (T, N), X (T, K); otherwise the caller keeps the library GEMM
+// 0: not covered (the caller keeps the library GEMM); 1: dW covered; 2: dW and the fused bias gradient covered
 int hs_linear_wgrad_supported(int64_t T, int N, int K) {
   if (T < 4096 || N < 32 || K < 32 || (N % 4) || (K % 4)) return 0;
   const int q = N < K ? N : K;
-  return (q % 32 == 0 && q <= 256) ? 1 : 0;
+  if (!(q % 32 == 0 && q <= 256)) return 0;
+  return (N >= K && K + 32 <= 256) ? 2 : 1;
 }
 
-int hs_linear_wgrad(const float* dy, const float* x, float* dw, int64_t T, int N, int K, uint32_t flags, void* stream) {
+int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int64_t T, int N, int K, uint32_t flags,
+                    void* stream) {
   HS_REQUIRE(dy && x && dw && T > 0 && N > 0 && K > 0, "hs_linear_wgrad: bad arguments");
   if (!hs_linear_wgrad_supported(T, N, K))
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: shape T=%lld N=%d K=%d is not covered (min(N, K) must be a "
@@ -150,6 +169,11 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, int64_t T, int N
   WgArgs a{};
   a.out = dw; a.T = T;
   a.NP = p_is_dy ? N : K; a.NQ = p_is_dy ? K : N;
+  if (dbias) {
+    if (!(p_is_dy && a.NQ + 32 <= 256))
+      return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: the fused bias gradient needs N >= K and K <= 224 (N=%d K=%d)", N, K);
+    a.colsum = dbias;
+  }
   a.ldo_p = p_is_dy ? K : 1; a.ldo_q = p_is_dy ? 1 : K;
   a.p_blocks = (a.NP + 127) / 128;
   const long long tiles = (T + kTT - 1) / kTT;
@@ -157,12 +181,13 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, int64_t T, int N
   if (splits < 1) splits = 1;
   if (splits > tiles) splits = (int)tiles;
   a.splits = splits;
-  const int stage_bytes = (4 + a.NQ / 32) * kSlab;
+  const int stage_bytes = (4 + a.NQ / 32 + (dbias ? 1 : 0)) * kSlab;
   int stages = (200 * 1024) / stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: stage does not fit");
   a.stages = stages;
   a.fix = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix2;
+  a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix1;
   CUtensorMap map_p, map_q;
   int rc;
   if ((rc = hs::tc::make_map(&map_p, P, T, a.NP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT))) return rc;

@@ -303,13 +303,16 @@ class _LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = (dy2 @ weight).view(x.shape)
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             x2 = _f32c(x).reshape(-1, K)
             T = x2.shape[0]
             dw = torch.zeros((N, K), device=x.device, dtype=torch.float32)
-            STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), T, N, K, 0, current_stream(),
-                         tag=(T, N, K))
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+            if need_b and lib.hs_linear_wgrad_supported(T, N, K) == 2:  # bias gradient in the same pass over dy
+                db = torch.zeros((N,), device=x.device, dtype=torch.float32)
+            STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, 0,
+                         current_stream(), tag=(T, N, K))
+        if need_b and db is None:
             db = dy2.sum(0)
         return dx, dw, db
 

@@ -166,13 +166,15 @@ int hs_bias_gelu_bwd(const float* dh_dev, const float* z_dev, const float* bias_
 /*
  * Weight gradient of nn.Linear (autograd of F.linear at swin_hp_transformer.py:131, 172, 21-44, 394, 421, 444, 774):
  *     dw[n][k] += sum_t dy[t][n] * x[t][k]         dy: (T, N), x: (T, K), dw: (N, K), all fp32 row-major
- * TF32 tensor-core kernel with the token range split over the SMs; dw is ACCUMULATED into (zero it for a plain
- * gradient).  hs_linear_wgrad_supported tells whether the shape is covered (min(N, K) a multiple of 32 and <= 256,
- * T >= 4096); other shapes stay with the library GEMM.  flags: HS_ATTN_NO_TRUNC_COMP only.
+ * and optionally the bias gradient in the same pass:   dbias[n] += sum_t dy[t][n]   (dbias may be NULL).
+ * TF32 tensor-core kernel with the token range split over the SMs; dw / dbias are ACCUMULATED into (zero them for a
+ * plain gradient).  hs_linear_wgrad_supported returns 0 when the shape is not covered (it then stays with the library
+ * GEMM; covered: min(N, K) a multiple of 32 and <= 256, T >= 4096), 1 when dw is covered, 2 when dbias can be fused too
+ * (N >= K, K <= 224).  flags: HS_ATTN_NO_TRUNC_COMP only.
  */
 int hs_linear_wgrad_supported(int64_t T, int N, int K);
-int hs_linear_wgrad(const float* dy_dev, const float* x_dev, float* dw_dev, int64_t T, int N, int K, uint32_t flags,
-                    void* stream);
+int hs_linear_wgrad(const float* dy_dev, const float* x_dev, float* dw_dev, float* dbias_dev, int64_t T, int N, int K,
+                    uint32_t flags, void* stream);
 
 #ifdef __cplusplus
 }

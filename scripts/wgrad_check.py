@@ -47,6 +47,6 @@ for stage, (M, C) in enumerate([(8 * 196608, 96), (8 * 49152, 192), (8 * 12288, 
         x = torch.randn(M, K, device=dev)
         dy = torch.randn(M, N, device=dev)
         dw = torch.zeros(N, K, device=dev)
-        t = timeit(lambda: check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), M, N, K, 0, current_stream())))
+        t = timeit(lambda: check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), None, M, N, K, 0, current_stream())))
         print(f"stage {stage} {name:4s} M={M} N={N} K={K}: custom wgrad {t:.3f} ms (roof {(M * (N + K)) * 4 / 6.55e12 * 1e3:.3f})", flush=True)
         del x, dy, dw

@@ -19,7 +19,7 @@ def _wgrad(dy, x):
     K = x.shape[1]
     assert lib.hs_linear_wgrad_supported(T, N, K)
     dw = torch.zeros(N, K, device=dy.device)
-    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), T, N, K, 0, current_stream()))
+    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), None, T, N, K, 0, current_stream()))
     return dw
 
 
@@ -49,10 +49,13 @@ def test_wgrad_exact_on_tf32_representable_data_and_accumulates():
     dy = torch.randint(-4, 5, (T, N), generator=g).float().to(dev)
     x = torch.randint(-4, 5, (T, K), generator=g).float().to(dev)
     dw = torch.zeros(N, K, device=dev)
-    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), T, N, K, _lib.ATTN_NO_TRUNC_COMP, current_stream()))
+    db = torch.zeros(N, device=dev)
+    assert lib.hs_linear_wgrad_supported(T, N, K) == 2
+    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), ptr(db), T, N, K, _lib.ATTN_NO_TRUNC_COMP, current_stream()))
     want = (dy.double().t() @ x.double()).float()
     assert torch.equal(dw, want)
-    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), T, N, K, _lib.ATTN_NO_TRUNC_COMP, current_stream()))
+    assert torch.equal(db, dy.double().sum(0).float())  # the fused bias gradient (column sums of dy)
+    check(lib.hs_linear_wgrad(ptr(dy), ptr(x), ptr(dw), ptr(db), T, N, K, _lib.ATTN_NO_TRUNC_COMP, current_stream()))
     assert torch.equal(dw, 2 * want)
 
 
