@@ -403,51 +403,76 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       constexpr uint64_t kDescMN = umma_smem_desc(1024, 512, kLayoutSw128B32);  // MN-major, 4-row k-atoms 512 B apart
       constexpr uint32_t kIdescS = umma_idesc_tf32(128, 128, 0, 0);
       constexpr uint32_t kIdescO = umma_idesc_tf32(128, 32, 0, 1);
-      auto issue_outputs = [&](int m) {
-        const int t = m & 1, slot = m % kSlots;
-        const uint32_t ph = (uint32_t)(m >> 1) & 1;
-        const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
-        const Slot& T = S.slot[slot];
-        const uint32_t kb = smem_u32(T.k_mn), db = smem_u32(T.do_mn), qb = smem_u32(T.q_mn);
-        mbar_wait(&S.dsn_ready[t], ph);
-        HS_TRACE(4, m, 2);
-        tc_fence_after();
+      // One thread schedules the MMAs of both TMEM stages.  It POLLS the barriers (score MMAs of unit ns as soon as its
+      // slot is full and its stage free; dQ of unit no once the query rows are done; dV, dK once the key rows are done),
+      // so that the score MMAs of one warpgroup's next unit never queue behind the other warpgroup's unfinished sweep.
+      int units = 0;
+      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x) ++units;
+      int ns = 0, no = 0, ophase = 0;
+      long long idle0 = 0;
+      while (no < units) {
+        bool progressed = false;
+        if (ns < units) {
+          const int slot = ns % kSlots, t = ns & 1;
+          if (mbar_test_wait(&S.full[slot], (uint32_t)(ns / kSlots) & 1) &&
+              mbar_test_wait(&S.stage_free[t], ((uint32_t)(ns >> 1) & 1) ^ 1)) {
+            HS_TRACE(4, ns, 0);
+            tc_fence_after();
+            const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
+            const uint32_t qk = smem_u32(S.slot[slot].qk), dov = smem_u32(S.slot[slot].dov);
 #pragma unroll
-        for (int s = 0; s < 8; ++s)  // dQ = dS k            A: D1[:, 64:128)  ->  D2[:, 64:96)
-          umma_tf32_ts(D2 + 64, D1 + 64 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
-        mbar_wait(&S.dst_ready[t], ph);
-        tc_fence_after();
+            for (int s = 0; s < 4; ++s)  // [Q;K] [Q;K]^T : lanes 0-63 x cols 64-127 = S, lanes 64-127 x cols 0-63 = S^T
+              umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
 #pragma unroll
-        for (int s = 0; s < 8; ++s)  // dV = P^T dO          A: D1[:, 0:64)    ->  D2[:, 96:128)
-          umma_tf32_ts(D2 + 96, D1 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
-        HS_TRACE(4, m, 3);
-        // dK overwrites the dS block that dQ has read: tcgen05.mma instructions of one thread execute in issue order
+            for (int s = 0; s < 4; ++s)  // [dO;V] [dO;V]^T : lanes 0-63 x cols 64-127 = dP, lanes 64-127 x cols 0-63 = dP^T
+              umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
+            umma_commit(&S.s_ready[t]);
+            HS_TRACE(4, ns, 1);
+            ++ns;
+            progressed = true;
+          }
+        }
+        if (no < ns) {
+          const int t = no & 1, slot = no % kSlots;
+          const uint32_t ph = (uint32_t)(no >> 1) & 1;
+          const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
+          const Slot& T = S.slot[slot];
+          if (ophase == 0 && mbar_test_wait(&S.dsn_ready[t], ph)) {
+            HS_TRACE(4, no, 2);
+            tc_fence_after();
+            const uint32_t kb = smem_u32(T.k_mn);
 #pragma unroll
-        for (int s = 0; s < 8; ++s)  // dK = dS^T q          A: D2[:, 0:64)    ->  D1[:, 64:96)
-          umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
-        umma_commit(&S.o_ready[t]);
-        HS_TRACE(4, m, 4);
-      };
-      int n = 0;
-      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
-        const int slot = n % kSlots, t = n & 1;
-        mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
-        mbar_wait(&S.stage_free[t], ((uint32_t)(n >> 1) & 1) ^ 1);
-        HS_TRACE(4, n, 0);
-        tc_fence_after();
-        const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
-        const uint32_t qk = smem_u32(S.slot[slot].qk), dov = smem_u32(S.slot[slot].dov);
+            for (int s = 0; s < 8; ++s)  // dQ = dS k            A: D1[:, 64:128)  ->  D2[:, 64:96)
+              umma_tf32_ts(D2 + 64, D1 + 64 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
+            ophase = 1;
+            progressed = true;
+          }
+          if (ophase == 1 && mbar_test_wait(&S.dst_ready[t], ph)) {
+            tc_fence_after();
+            const uint32_t db = smem_u32(T.do_mn), qb = smem_u32(T.q_mn);
 #pragma unroll
-        for (int s = 0; s < 4; ++s)  // [Q;K] [Q;K]^T : lanes 0-63 x cols 64-127 = S, lanes 64-127 x cols 0-63 = S^T
-          umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
+            for (int s = 0; s < 8; ++s)  // dV = P^T dO          A: D1[:, 0:64)    ->  D2[:, 96:128)
+              umma_tf32_ts(D2 + 96, D1 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
+            HS_TRACE(4, no, 3);
+            // dK overwrites the dS block that dQ has read: tcgen05.mma instructions of one thread execute in issue order
 #pragma unroll
-        for (int s = 0; s < 4; ++s)  // [dO;V] [dO;V]^T : lanes 0-63 x cols 64-127 = dP, lanes 64-127 x cols 0-63 = dP^T
-          umma_tf32_ss(D2, umma_desc_at(kDescK, dov + s * 32), umma_desc_at(kDescK, dov + s * 32), kIdescS, s > 0);
-        umma_commit(&S.s_ready[t]);
-        HS_TRACE(4, n, 1);
-        if (n > 0) issue_outputs(n - 1);
+            for (int s = 0; s < 8; ++s)  // dK = dS^T q          A: D2[:, 0:64)    ->  D1[:, 64:96)
+              umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
+            umma_commit(&S.o_ready[t]);
+            HS_TRACE(4, no, 4);
+            ophase = 0;
+            ++no;
+            progressed = true;
+          }
+        }
+        if (progressed) {
+          idle0 = 0;
+        } else {  // nothing ready: a protocol bug must not hang the device (same ~2 s bound as mbar_wait)
+          if (idle0 == 0) idle0 = clock64();
+          else if (clock64() - idle0 > 4000000000ll) __trap();
+          __nanosleep(20);
+        }
       }
-      if (n > 0) issue_outputs(n - 1);
     } else if (warp >= 10) {
       // ================================================================= statistics warps (10: even units, 11: odd units).
       // The softmax row statistics come from the forward pass -- lse from its saved vector, delta_i = sum_j P_ij dP_ij
@@ -534,7 +559,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         S.inv[wg][L] = my_inv;
       }
       if (a.cos) named_bar_sync(1 + wg, 128);  // the norms of this unit are published
+      if (r == 0) HS_TRACE(trole, n, 6);
       mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kSlots) & 1);  // lse / delta of this unit (statistics warp)
+      if (r == 0) HS_TRACE(trole, n, 7);
       if (nat) {
         const float lse = S.lse[slot][r], dl = S.delta[slot][r];
         S.lse4[wg][r] = make_float4(lse, lse, lse, lse);

@@ -64,6 +64,15 @@ int main(int argc, char** argv) {
   for (int role = 0; role < 4; ++role)
     printf("%s avg cycles: wait_s %.0f | elementwise %.0f | wait_o %.0f | tmem_ld %.0f | epilogue %.0f | to next full %.0f\n", names[role],
            d[role][0] / cnt[role], d[role][1] / cnt[role], d[role][2] / cnt[role], d[role][3] / cnt[role], d[role][4] / cnt[role], d[role][5] / cnt[role]);
+  {
+    double w6 = 0, w7 = 0, w1 = 0; int c = 0;
+    for (int n = 8; n < kTraceUnits; ++n) {
+      const int role = (n & 1) * 2;  // query-row thread 0 of the unit's warpgroup
+      w6 += (double)(at(role, n, 6) - at(role, n, 0)); w7 += (double)(at(role, n, 7) - at(role, n, 6));
+      w1 += (double)(at(role, n, 1) - at(role, n, 7)); ++c;
+    }
+    printf("wait_s split (query rows): norms+barrier %.0f | stats_ready wait %.0f | s_ready wait %.0f\n", w6 / c, w7 / c, w1 / c);
+  }
   printf("unit period (cycles): %.0f\n", (double)(at(0, 46, 0) - at(0, 8, 0)) / 38.0);
   return 0;
 }
