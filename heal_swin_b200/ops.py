@@ -91,18 +91,12 @@ class GatherRows(torch.autograd.Function):
         return out, None, None
 
 
-_DROP_CALLS = 0
-
-
 def _next_dropout_seed() -> int:
-    """64-bit seed of one attention-dropout mask: derived from torch's CPU seed (so torch.manual_seed makes runs
-    reproducible), the rank (different masks on different data shards) and a per-call counter -- no device sync."""
-    global _DROP_CALLS
-    _DROP_CALLS += 1
-    x = (torch.initial_seed() * 0x9E3779B97F4A7C15 + int(os.environ.get("RANK", "0")) * 0xD1B54A32D192ED03
-         + _DROP_CALLS * 0x2545F4914F6CDD1D) & 0xFFFFFFFFFFFFFFFF
-    x ^= x >> 31
-    return (x * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    """64-bit seed of one attention-dropout mask, drawn from torch's default CPU generator: reproducible under
+    torch.manual_seed, replayed identically when torch.utils.checkpoint re-runs the forward (it restores the RNG state),
+    no device sync.  The rank is mixed in so that data-parallel shards do not share masks."""
+    x = int(torch.randint(0, 2**62, (1,)).item()) ^ (int(os.environ.get("RANK", "0")) * 0xD1B54A32D192ED03)
+    return x & 0xFFFFFFFFFFFFFFFF
 
 
 class WindowAttnCore(torch.autograd.Function):
