@@ -17,8 +17,8 @@ namespace {
 
 using namespace hs::sm100;
 
-constexpr int kTT = 64;                  // tokens per pipeline stage
-constexpr int kSlab = kTT * 128;         // bytes of one 32-feature slab of a stage
+// tokens per pipeline stage: 64 (one slab = 8 KB), or 32 when the smaller feature dimension exceeds 256 (up to 512: two
+// MMAs of N <= 256 per K step into adjacent TMEM columns; 16 + 4 slabs of 4 KB per stage)
 constexpr int kThreads = 192;            // warps 0-3 epilogue, 4 producer, 5 MMA
 constexpr int kMaxStages = 4;
 
@@ -29,6 +29,7 @@ struct WgArgs {
   long long T;             // tokens
   int NP, NQ;              // feature counts of P (rows of D) and Q (columns of D, <= 256, multiple of 32)
   int p_blocks, splits, stages;
+  int tt;                  // tokens per stage (64 or 32)
   float fix, fix1;  // truncation compensation for two / one truncated operand
 };
 
@@ -39,6 +40,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
   __shared__ uint64_t full[kMaxStages], empty[kMaxStages], done;
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kTT = a.tt, kSlab = a.tt * 128;
   const int q_slabs = a.NQ / 32;
   const int ones = a.colsum ? 1 : 0;  // one extra Q slab holding the constant column (1, 0, ..., 0)
   const int stage_bytes = (4 + q_slabs + ones) * kSlab;
@@ -71,7 +73,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
     mbar_init(&done, 1);
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc(&tmem_base, 256);
+  const uint32_t tmem_cols = (a.NQ + 32 * ones > 256) ? 512u : 256u;
+  if (warp == 5) tmem_alloc(&tmem_base, tmem_cols);
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_p);
     tma_prefetch_desc(&map_q);
@@ -97,18 +100,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
     }
   } else if (warp == 5) {
     if (elect_one()) {
-      constexpr uint64_t kDesc = umma_smem_desc(kSlab, 512, kLayoutSw128B32);
-      const uint32_t idesc = umma_idesc_tf32(128, a.NQ + 32 * ones, 1, 1);
+      const uint64_t kDesc = umma_smem_desc((uint32_t)kSlab, 512, kLayoutSw128B32);
+      // D columns: one MMA of N = NQ (+32 for the ones slab) when that is <= 256, else two halves (multiples of 32)
+      const int n_all = a.NQ + 32 * ones;
+      const int n1 = n_all <= 256 ? n_all : ((q_slabs + 1) / 2) * 32;
+      const int n2 = n_all - n1;
+      const uint32_t idesc1 = umma_idesc_tf32(128, n1, 1, 1), idesc2 = umma_idesc_tf32(128, n2 > 0 ? n2 : 32, 1, 1);
       int n = 0;
       for (long long t = t_lo; t < t_hi; ++t, ++n) {
         const int s = n % a.stages;
         mbar_wait(&full[s], ((uint32_t)(n / a.stages)) & 1);
         tc_fence_after();
         const uint32_t pa = smem_u32(sm + s * stage_bytes), qa = pa + 4 * kSlab;
-#pragma unroll
-        for (int ks = 0; ks < kTT / 8; ++ks)
-          umma_tf32_ss(tmem, umma_desc_at(kDesc, pa + ks * 1024), umma_desc_at(kDesc, qa + ks * 1024), idesc,
-                       (n > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < kTT / 8; ++ks) {
+          const uint32_t acc = (n > 0 || ks > 0) ? 1u : 0u;
+          umma_tf32_ss(tmem, umma_desc_at(kDesc, pa + ks * 1024), umma_desc_at(kDesc, qa + ks * 1024), idesc1, acc);
+          if (n2 > 0)
+            umma_tf32_ss(tmem + n1, umma_desc_at(kDesc, pa + ks * 1024),
+                         umma_desc_at(kDesc, qa + (n1 / 32) * kSlab + ks * 1024), idesc2, acc);
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(&done);
@@ -126,8 +136,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
         tmem_wait_ld();
         if (p < a.NP) {
           float* dst = a.out + (long long)p * a.ldo_p + (long long)c0 * a.ldo_q;
+          if (a.ldo_q == 1) {  // my 32 columns are contiguous in memory: 128-bit vector reductions
 #pragma unroll
-          for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * a.ldo_q, __uint_as_float(r[c]) * a.fix);
+            for (int c = 0; c < 32; c += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c),
+                           "f"(__uint_as_float(r[c]) * a.fix), "f"(__uint_as_float(r[c + 1]) * a.fix),
+                           "f"(__uint_as_float(r[c + 2]) * a.fix), "f"(__uint_as_float(r[c + 3]) * a.fix)
+                           : "memory");
+          } else {  // transposed output: consecutive lanes (rows p) are contiguous, one coalesced reduction per column
+#pragma unroll
+            for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * a.ldo_q, __uint_as_float(r[c]) * a.fix);
+          }
         }
       }
       if (ones) {  // column NQ of D = sum_t P[t][p] * 1
@@ -140,7 +159,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem, 256);
+  if (warp == 5) tmem_dealloc(tmem, tmem_cols);
 }
 
 }  // namespace
@@ -151,7 +170,7 @@ extern "C" {
 int hs_linear_wgrad_supported(int64_t T, int N, int K) {
   if (T < 4096 || N < 32 || K < 32 || (N % 4) || (K % 4)) return 0;
   const int q = N < K ? N : K;
-  if (!(q % 32 == 0 && q <= 256)) return 0;
+  if (!(q % 32 == 0 && q <= 512)) return 0;
   return (N >= K && K + 32 <= 256) ? 2 : 1;
 }
 
@@ -160,7 +179,7 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, in
   HS_REQUIRE(dy && x && dw && T > 0 && N > 0 && K > 0, "hs_linear_wgrad: bad arguments");
   if (!hs_linear_wgrad_supported(T, N, K))
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: shape T=%lld N=%d K=%d is not covered (min(N, K) must be a "
-                    "multiple of 32 and <= 256)", (long long)T, N, K);
+                    "multiple of 32 and <= 512)", (long long)T, N, K);
   HS_REQUIRE(!((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15), "hs_linear_wgrad: unaligned input");
   // P = operand with more features (rows of D), Q = the other (<= 256 columns)
   const bool p_is_dy = N >= K;
@@ -176,6 +195,8 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, in
   }
   a.ldo_p = p_is_dy ? K : 1; a.ldo_q = p_is_dy ? 1 : K;
   a.p_blocks = (a.NP + 127) / 128;
+  a.tt = a.NQ <= 256 ? 64 : 32;
+  const int kTT = a.tt, kSlab = a.tt * 128;
   const long long tiles = (T + kTT - 1) / kTT;
   int splits = hs::tc::sm_count() / a.p_blocks;
   if (splits < 1) splits = 1;

@@ -1,2 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_wgrad.py tests/test_gpu_model.py -x -q 2>&1 | tail -5
-timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-250
+timeout 600 python -m pytest tests/test_gpu_wgrad.py -x -q 2>&1 | tail -5
+timeout 600 python scripts/wgrad_check.py 2>&1 | grep -E "custom|not covered|stage 2"

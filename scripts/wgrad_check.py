@@ -39,7 +39,7 @@ import os, sys  # noqa: E402
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from heal_swin_b200._lib import check, current_stream, lib, ptr  # noqa: E402
 
-for stage, (M, C) in enumerate([(8 * 196608, 96), (8 * 49152, 192), (8 * 12288, 384)]):
+for stage, (M, C) in enumerate([(8 * 196608, 96), (8 * 49152, 192), (8 * 12288, 384), (8 * 3072, 768)]):
     for name, N, K in (("qkv", 3 * C, C), ("proj", C, C), ("fc1", 4 * C, C), ("fc2", C, 4 * C)):
         if not lib.hs_linear_wgrad_supported(M, N, K):
             print(f"stage {stage} {name}: not covered")

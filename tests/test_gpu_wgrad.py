@@ -24,7 +24,10 @@ def _wgrad(dy, x):
 
 
 @pytest.mark.parametrize("T,N,K", [(8192, 288, 96), (8192, 96, 96), (8192, 384, 96), (8192, 96, 384), (5000, 576, 192),
-                                   (4096 + 37, 192, 768), (8192, 32, 64), (20000, 100, 64), (8192, 1152, 256)])
+                                   (4096 + 37, 192, 768), (8192, 32, 64), (20000, 100, 64), (8192, 1152, 256),
+                                   # smaller feature dimension in (256, 512]: 32-token stages, two MMAs per K step
+                                   (8192, 1152, 384), (8192, 384, 384), (6000, 384, 1536), (8192, 640, 512),
+                                   (8192, 288, 320)])
 def test_wgrad_matches_fp32_product(T, N, K):
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(T + N + K)
