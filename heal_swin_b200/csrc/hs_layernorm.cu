@@ -20,7 +20,7 @@ __device__ __forceinline__ float group_sum(float v, int T) {
 }
 
 template <int V>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (V <= 3 ? 6 : (V <= 6 ? 3 : 1)))
 ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias, const float4* __restrict__ res,
               const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ y,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int T, float eps) {
@@ -28,12 +28,6 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
   const int t = lane & (T - 1), sub = lane / T, rpw = 32 / T;
   const int C4 = T * V;
   const float invC = 1.0f / (float)(4 * C4);
-  float4 g[V], b[V];
-#pragma unroll
-  for (int v = 0; v < V; ++v) {
-    g[v] = __ldg(gamma + t + T * v);
-    b[v] = __ldg(beta + t + T * v);
-  }
   const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * (kThreads / 32) * rpw;
   for (long long base = warp0 * rpw; base < rows; base += stride) {
@@ -61,11 +55,12 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
     if (ok) {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
+        const float4 g = __ldg(gamma + t + T * v), b = __ldg(beta + t + T * v);  // L1-resident; not kept in registers
         float4 o;
-        o.x = fmaf(a[v].x * rs, g[v].x, b[v].x);
-        o.y = fmaf(a[v].y * rs, g[v].y, b[v].y);
-        o.z = fmaf(a[v].z * rs, g[v].z, b[v].z);
-        o.w = fmaf(a[v].w * rs, g[v].w, b[v].w);
+        o.x = fmaf(a[v].x * rs, g.x, b.x);
+        o.y = fmaf(a[v].y * rs, g.y, b.y);
+        o.z = fmaf(a[v].z * rs, g.z, b.z);
+        o.w = fmaf(a[v].w * rs, g.w, b.w);
         if (res) {
           const float4 r4 = __ldcs(res + row * C4 + t + T * v);
           o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
@@ -81,7 +76,7 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
 }
 
 template <int V, bool kPreBias>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, (V <= 3 ? 3 : (V <= 6 ? 2 : 1)))
 ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ pre_bias,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float4* __restrict__ gamma,
               float4* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
@@ -92,10 +87,9 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
   const int C4 = T * V, C = 4 * C4;
   const float invC = 1.0f / (float)C;
   for (int i = threadIdx.x; i < (kPreBias ? 3 : 2) * C; i += kThreads) red[i] = 0.f;
-  float4 g[V], dg[V], db[V], pb[kPreBias ? V : 1], dpb[kPreBias ? V : 1];
+  float4 dg[V], db[V], pb[kPreBias ? V : 1], dpb[kPreBias ? V : 1];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    g[v] = __ldg(gamma + t + T * v);
     dg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     db[v] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kPreBias) {
@@ -119,8 +113,9 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
       if (kPreBias && ok) {
         xv.x += pb[v].x; xv.y += pb[v].y; xv.z += pb[v].z; xv.w += pb[v].w;
       }
+      const float4 g = __ldg(gamma + t + T * v);  // L1-resident; not kept in registers
       xh[v].x = (xv.x - mu) * rs; xh[v].y = (xv.y - mu) * rs; xh[v].z = (xv.z - mu) * rs; xh[v].w = (xv.w - mu) * rs;
-      w[v].x = d.x * g[v].x; w[v].y = d.y * g[v].y; w[v].z = d.z * g[v].z; w[v].w = d.w * g[v].w;
+      w[v].x = d.x * g.x; w[v].y = d.y * g.y; w[v].z = d.z * g.z; w[v].w = d.w * g.w;
       s1 += (w[v].x + w[v].y) + (w[v].z + w[v].w);
       s2 += (w[v].x * xh[v].x + w[v].y * xh[v].y) + (w[v].z * xh[v].z + w[v].w * xh[v].w);
       dg[v].x = fmaf(d.x, xh[v].x, dg[v].x); dg[v].y = fmaf(d.y, xh[v].y, dg[v].y);
