@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--shift", default=None, help="nest_roll | nest_grid_shift | ring_shift (default by base_pix)")
     ap.add_argument("--embed-dim", type=int, default=96)
     ap.add_argument("--classes", type=int, default=10)
+    ap.add_argument("--drop-rate", type=float, default=0.0,
+                    help="drop_rate = attn_drop_rate = drop_path_rate (every shipped reference config uses 0.1; the "
+                         "headline number uses 0 so that it is comparable with the dropout-free reference arm)")
     ap.add_argument("--no-cos", action="store_true")
     ap.add_argument("--v1-norm", action="store_true")
     ap.add_argument("--gemm-precision", default="tf32", choices=["tf32", "fp32"],
@@ -199,7 +202,8 @@ def run_ours(a):
 
     kw = model_kwargs(a)
     torch.manual_seed(0)
-    model = build_product_model(kw, None, dev)
+    model = build_product_model(dict(kw, drop_rate=a.drop_rate, attn_drop_rate=a.drop_rate, drop_path_rate=a.drop_rate),
+                                None, dev)
     with torch.no_grad():  # the reference zero-initialises the bias tables; give them signal
         gen = torch.Generator(device="cpu").manual_seed(1)
         for n, p in model.named_parameters():
@@ -350,7 +354,7 @@ def run_ours(a):
         "dtype": "tf32", "data": "synthetic",
         "config": {"workload": workload_name(a, kw), "global_batch": world * B, "pixels_per_sample": npix,
                    "parallelism": f"dp{world}", "step": "fwd + CE loss + bwd + (NCCL grad all-reduce) + Adam",
-                   "library_gemm_precision": a.gemm_precision,
+                   "library_gemm_precision": a.gemm_precision, "drop_rates": a.drop_rate,
                    "forward_rel_err_vs_fp32_oracle": "4-6e-4 with fp32 library GEMMs, 1.1-1.4e-3 with TF32 ones "
                                                      "(scripts/tf32_model_check.py, tests/test_gpu_model.py)",
                    "l2_policy": "inputs larger than L2 (activations 0.6-2.4 GB per tensor at stage 0), no flush needed",

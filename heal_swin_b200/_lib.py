@@ -36,12 +36,12 @@ SIGNATURES = {
     "hs_gather_rows": [_p, _p, _p, _i, _i64, _i, _p],
     "hs_rel_bias_expand": [_p, _p, _p, _i, _i, _i, _p],
     "hs_rel_bias_reduce": [_p, _p, _p, _i, _i, _i, _p],
-    "hs_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _f, _p],
-    "hs_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _p],
+    "hs_layernorm_fwd": [_p, _p, _p, _p, _p, _p, _i64, _f, _u64, _p, _p, _p, _i64, _i, _f, _p],
+    "hs_layernorm_bwd": [_p, _p, _p, _p, _p, _p, _p, _i64, _f, _u64, _p, _p, _p, _p, _i64, _i, _p],
     "hs_linear_wgrad_supported": [_i64, _i, _i],
     "hs_linear_wgrad": [_p, _p, _p, _p, _i64, _i, _i, _u32, _p],
-    "hs_bias_gelu_fwd": [_p, _p, _p, _i64, _i, _p],
-    "hs_bias_gelu_bwd": [_p, _p, _p, _p, _p, _i64, _i, _p],
+    "hs_bias_gelu_fwd": [_p, _p, _f, _u64, _p, _i64, _i, _p],
+    "hs_bias_gelu_bwd": [_p, _p, _p, _f, _u64, _p, _p, _i64, _i, _p],
     "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _f, _u64, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
     "hs_window_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _f, _f, _u64, _p, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],
 }

@@ -35,6 +35,14 @@ HS_HD uint32_t drop_unit_key(uint64_t seed, long long wb, int h, int H) {
 HS_HD bool drop_keep(uint32_t unit_key, int i, int j, int ws, uint32_t thresh) {
   return mix32(unit_key ^ ((uint32_t)(i * ws + j) * 0x9E3779B9u)) >= thresh;
 }
+// element-wise dropout of a (rows, C) activation (proj_drop / Mlp.drop, swin_hp_transformer.py:38-43, 173): the mask of
+// element (row, col) is a pure function of (seed, row, col)
+HS_HD uint32_t drop_row_key(uint64_t seed, long long row) {
+  return mix32((uint32_t)seed ^ mix32((uint32_t)(seed >> 32) + (uint32_t)row) ^ (uint32_t)((unsigned long long)row >> 32));
+}
+HS_HD bool drop_keep_elem(uint32_t row_key, int col, uint32_t thresh) {
+  return mix32(row_key ^ ((uint32_t)col * 0x9E3779B9u)) >= thresh;
+}
 HS_HD uint32_t drop_thresh(float p) {
   const double t = (double)p * 4294967296.0;
   return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;

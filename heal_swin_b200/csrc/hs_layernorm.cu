@@ -14,16 +14,34 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// optional extras of the fused LayerNorm: dropout on its input (after the pre-bias) and a per-sample scale on its output
+// (stochastic depth):   y = residual + row_scale[row / rows_per_scale] * (LN(dropout(x + pre_bias)) * gamma + beta)
+struct LnExtra {
+  const float* row_scale;  // null = 1
+  long long rows_per_scale;
+  uint32_t drop_thresh;    // 0 = no dropout
+  float drop_scale;        // 1 / (1 - p)
+  uint64_t seed;
+};
+
+__device__ __forceinline__ void drop4(float4& a, uint32_t key, int col, const LnExtra& e) {
+  a.x = hs::drop_keep_elem(key, col + 0, e.drop_thresh) ? a.x * e.drop_scale : 0.f;
+  a.y = hs::drop_keep_elem(key, col + 1, e.drop_thresh) ? a.y * e.drop_scale : 0.f;
+  a.z = hs::drop_keep_elem(key, col + 2, e.drop_thresh) ? a.z * e.drop_scale : 0.f;
+  a.w = hs::drop_keep_elem(key, col + 3, e.drop_thresh) ? a.w * e.drop_scale : 0.f;
+}
+
 __device__ __forceinline__ float group_sum(float v, int T) {
   for (int o = T >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
-template <int V>
-__global__ void __launch_bounds__(kThreads, (V <= 3 ? 6 : (V <= 6 ? 3 : 1)))
+template <int V, bool kDrop>
+__global__ void __launch_bounds__(kThreads, (V <= 3 ? (kDrop ? 4 : 6) : (V <= 6 ? 3 : 1)))
 ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias, const float4* __restrict__ res,
               const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ y,
-              float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int T, float eps) {
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int T, float eps,
+              const LnExtra ex) {
   const int lane = threadIdx.x & 31;
   const int t = lane & (T - 1), sub = lane / T, rpw = 32 / T;
   const int C4 = T * V;
@@ -35,6 +53,7 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
     const bool ok = row < rows;
     float4 a[V];
     float s = 0.f;
+    const uint32_t dkey = kDrop ? hs::drop_row_key(ex.seed, row) : 0u;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       a[v] = ok ? __ldcs(x + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -42,6 +61,7 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
         const float4 pb = __ldg(pre_bias + t + T * v);
         a[v].x += pb.x; a[v].y += pb.y; a[v].z += pb.z; a[v].w += pb.w;
       }
+      if (kDrop) drop4(a[v], dkey, 4 * (t + T * v), ex);
       s += (a[v].x + a[v].y) + (a[v].z + a[v].w);
     }
     const float mu = group_sum(s, T) * invC;
@@ -53,14 +73,15 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
     }
     const float rs = rsqrtf(group_sum(q, T) * invC + eps);
     if (ok) {
+      const float osc = ex.row_scale ? __ldg(ex.row_scale + row / ex.rows_per_scale) : 1.0f;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const float4 g = __ldg(gamma + t + T * v), b = __ldg(beta + t + T * v);  // L1-resident; not kept in registers
         float4 o;
-        o.x = fmaf(a[v].x * rs, g.x, b.x);
-        o.y = fmaf(a[v].y * rs, g.y, b.y);
-        o.z = fmaf(a[v].z * rs, g.z, b.z);
-        o.w = fmaf(a[v].w * rs, g.w, b.w);
+        o.x = fmaf(a[v].x * rs, g.x, b.x) * osc;
+        o.y = fmaf(a[v].y * rs, g.y, b.y) * osc;
+        o.z = fmaf(a[v].z * rs, g.z, b.z) * osc;
+        o.w = fmaf(a[v].w * rs, g.w, b.w) * osc;
         if (res) {
           const float4 r4 = __ldcs(res + row * C4 + t + T * v);
           o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
@@ -75,12 +96,12 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
   }
 }
 
-template <int V, bool kPreBias>
-__global__ void __launch_bounds__(kThreads, (V <= 3 ? 3 : (V <= 6 ? 2 : 1)))
+template <int V, bool kPreBias, bool kDrop>
+__global__ void __launch_bounds__(kThreads, (V <= 3 ? ((kDrop || kPreBias) ? 2 : 3) : (V <= 6 ? 2 : 1)))
 ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const float4* __restrict__ pre_bias,
               const float* __restrict__ mean, const float* __restrict__ rstd, const float4* __restrict__ gamma,
               float4* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dpre_bias, long long rows, int T) {
+              float* __restrict__ dpre_bias, long long rows, int T, const LnExtra ex) {
   extern __shared__ float red[];  // [2 or 3][C]
   const int lane = threadIdx.x & 31;
   const int t = lane & (T - 1), sub = lane / T, rpw = 32 / T;
@@ -104,15 +125,19 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
     const long long row = base + sub;
     const bool ok = row < rows;
     const float mu = ok ? __ldg(mean + row) : 0.f, rs = ok ? __ldg(rstd + row) : 0.f;
+    const float osc = (ok && ex.row_scale) ? __ldg(ex.row_scale + row / ex.rows_per_scale) : 1.0f;
+    const uint32_t dkey = kDrop ? hs::drop_row_key(ex.seed, row) : 0u;
     float4 xh[V], w[V];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       float4 xv = ok ? __ldcs(x + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 d = ok ? __ldcs(dy + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 d = ok ? __ldcs(dy + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      d.x *= osc; d.y *= osc; d.z *= osc; d.w *= osc;  // gradient w.r.t. the (unscaled) LayerNorm output
       if (kPreBias && ok) {
         xv.x += pb[v].x; xv.y += pb[v].y; xv.z += pb[v].z; xv.w += pb[v].w;
       }
+      if (kDrop) drop4(xv, dkey, 4 * (t + T * v), ex);
       const float4 g = __ldg(gamma + t + T * v);  // L1-resident; not kept in registers
       xh[v].x = (xv.x - mu) * rs; xh[v].y = (xv.y - mu) * rs; xh[v].z = (xv.z - mu) * rs; xh[v].w = (xv.w - mu) * rs;
       w[v].x = d.x * g.x; w[v].y = d.y * g.y; w[v].z = d.z * g.z; w[v].w = d.w * g.w;
@@ -132,6 +157,7 @@ ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x, const
         o.y = rs * (w[v].y - s1 - xh[v].y * s2);
         o.z = rs * (w[v].z - s1 - xh[v].z * s2);
         o.w = rs * (w[v].w - s1 - xh[v].w * s2);
+        if (kDrop) drop4(o, dkey, 4 * (t + T * v), ex);  // back through the input dropout
         dx[row * C4 + t + T * v] = o;
         if (kPreBias) {
           dpb[v].x += o.x; dpb[v].y += o.y; dpb[v].z += o.z; dpb[v].w += o.w;
@@ -182,13 +208,19 @@ __global__ void __launch_bounds__(kThreads)
 ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ pre_bias, const float* __restrict__ res,
                       const float* __restrict__ gamma,
                       const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean_out,
-                      float* __restrict__ rstd_out, long long rows, int C, float eps) {
+                      float* __restrict__ rstd_out, long long rows, int C, float eps, const LnExtra ex) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long row = warp0; row < rows; row += stride) {
     const float* xr = x + row * C;
-    auto xin = [&](int c) { return xr[c] + (pre_bias ? pre_bias[c] : 0.f); };
+    const uint32_t dkey = ex.drop_thresh ? hs::drop_row_key(ex.seed, row) : 0u;
+    const float osc = ex.row_scale ? ex.row_scale[row / ex.rows_per_scale] : 1.0f;
+    auto xin = [&](int c) {
+      const float v = xr[c] + (pre_bias ? pre_bias[c] : 0.f);
+      if (!ex.drop_thresh) return v;
+      return hs::drop_keep_elem(dkey, c, ex.drop_thresh) ? v * ex.drop_scale : 0.f;
+    };
     float s = 0.f;
     for (int c = lane; c < C; c += 32) s += xin(c);
     const float mu = group_sum(s, 32) / (float)C;
@@ -196,7 +228,7 @@ ln_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ pre
     for (int c = lane; c < C; c += 32) q += (xin(c) - mu) * (xin(c) - mu);
     const float rs = rsqrtf(group_sum(q, 32) / (float)C + eps);
     for (int c = lane; c < C; c += 32) {
-      float o = fmaf((xin(c) - mu) * rs, gamma[c], beta[c]);
+      float o = fmaf((xin(c) - mu) * rs, gamma[c], beta[c]) * osc;
       if (res) o += res[row * C + c];
       y[row * C + c] = o;
     }
@@ -211,24 +243,27 @@ __global__ void __launch_bounds__(kThreads)
 ln_bwd_generic_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ pre_bias,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                       float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                      float* __restrict__ dpre_bias, long long rows, int C) {
+                      float* __restrict__ dpre_bias, long long rows, int C, const LnExtra ex) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * (kThreads / 32);
   for (long long row = warp0; row < rows; row += stride) {
     const float mu = mean[row], rs = rstd[row];
-    auto xin = [&](int c) { return x[row * C + c] + (pre_bias ? pre_bias[c] : 0.f); };
+    const uint32_t dkey = ex.drop_thresh ? hs::drop_row_key(ex.seed, row) : 0u;
+    const float osc = ex.row_scale ? ex.row_scale[row / ex.rows_per_scale] : 1.0f;
+    auto keepf = [&](int c) { return !ex.drop_thresh ? 1.0f : (hs::drop_keep_elem(dkey, c, ex.drop_thresh) ? ex.drop_scale : 0.f); };
+    auto xin = [&](int c) { return (x[row * C + c] + (pre_bias ? pre_bias[c] : 0.f)) * keepf(c); };
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float xh = (xin(c) - mu) * rs, w = dy[row * C + c] * gamma[c];
+      const float xh = (xin(c) - mu) * rs, w = dy[row * C + c] * osc * gamma[c];
       s1 += w;
       s2 += w * xh;
     }
     s1 = group_sum(s1, 32) / (float)C;
     s2 = group_sum(s2, 32) / (float)C;
     for (int c = lane; c < C; c += 32) {
-      const float d = dy[row * C + c], xh = (xin(c) - mu) * rs;
-      const float o = rs * (d * gamma[c] - s1 - xh * s2);
+      const float d = dy[row * C + c] * osc, xh = (xin(c) - mu) * rs;
+      const float o = rs * (d * gamma[c] - s1 - xh * s2) * keepf(c);
       dx[row * C + c] = o;
       if (dgamma) atomicAdd(dgamma + c, d * xh);
       if (dbeta) atomicAdd(dbeta + c, d);
@@ -292,8 +327,23 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 
 extern "C" {
 
+static int make_extra(const char* fn, const float* row_scale, int64_t rows_per_scale, float in_drop, uint64_t seed,
+                      LnExtra* ex) {
+  HS_REQUIRE(in_drop >= 0.f && in_drop < 1.f, "%s: in_drop must be in [0, 1), got %f", fn, in_drop);
+  HS_REQUIRE(!row_scale || rows_per_scale > 0, "%s: row_scale needs rows_per_scale > 0", fn);
+  ex->row_scale = row_scale;
+  ex->rows_per_scale = rows_per_scale > 0 ? rows_per_scale : 1;
+  ex->drop_thresh = in_drop > 0.f ? hs::drop_thresh(in_drop) : 0u;
+  ex->drop_scale = 1.0f / (1.0f - in_drop);
+  ex->seed = seed;
+  return HS_OK;
+}
+
 int hs_layernorm_fwd(const float* x, const float* pre_bias, const float* residual, const float* gamma, const float* beta,
-                     float* y, float* mean, float* rstd, int64_t rows, int C, float eps, void* stream) {
+                     const float* row_scale, int64_t rows_per_scale, float in_drop, uint64_t seed, float* y, float* mean,
+                     float* rstd, int64_t rows, int C, float eps, void* stream) {
+  LnExtra ex;
+  if (int rc = make_extra("hs_layernorm_fwd", row_scale, rows_per_scale, in_drop, seed, &ex)) return rc;
   HS_REQUIRE(x && gamma && beta && y, "hs_layernorm_fwd: null pointer");
   HS_REQUIRE((mean == nullptr) == (rstd == nullptr), "hs_layernorm_fwd: mean and rstd go together");
   HS_REQUIRE(rows > 0, "hs_layernorm_fwd: rows must be positive");
@@ -305,24 +355,33 @@ int hs_layernorm_fwd(const float* x, const float* pre_bias, const float* residua
     long long blocks = (rows + kThreads / 32 - 1) / (kThreads / 32);
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
     ln_fwd_generic_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(x, pre_bias, residual, gamma, beta, y,
-                                                                              mean, rstd, rows, C, eps);
+                                                                              mean, rstd, rows, C, eps, ex);
     HS_LAUNCH_CHECK();
     return HS_OK;
   }
-  HS_LN_DISPATCH(V, {
-    const int grid = grid_for(ln_fwd_kernel<VV>, 0, rows, T);
-    ln_fwd_kernel<VV><<<grid, kThreads, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pre_bias),
-        reinterpret_cast<const float4*>(residual), reinterpret_cast<const float4*>(gamma),
-        reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(y), mean, rstd, rows, T, eps);
-  });
+#define HS_LN_FWD_LAUNCH(DROP)                                                                                   \
+  HS_LN_DISPATCH(V, {                                                                                            \
+    const int grid = grid_for(ln_fwd_kernel<VV, DROP>, 0, rows, T);                                              \
+    ln_fwd_kernel<VV, DROP><<<grid, kThreads, 0, (cudaStream_t)stream>>>(                                        \
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(pre_bias),                           \
+        reinterpret_cast<const float4*>(residual), reinterpret_cast<const float4*>(gamma),                       \
+        reinterpret_cast<const float4*>(beta), reinterpret_cast<float4*>(y), mean, rstd, rows, T, eps, ex);      \
+  })
+  if (ex.drop_thresh) {
+    HS_LN_FWD_LAUNCH(true);
+  } else {
+    HS_LN_FWD_LAUNCH(false);
+  }
+#undef HS_LN_FWD_LAUNCH
   HS_LAUNCH_CHECK();
   return HS_OK;
 }
 
 int hs_layernorm_bwd(const float* dy, const float* x, const float* pre_bias, const float* mean, const float* rstd,
-                     const float* gamma, float* dx, float* dgamma, float* dbeta, float* dpre_bias, int64_t rows, int C,
-                     void* stream) {
+                     const float* gamma, const float* row_scale, int64_t rows_per_scale, float in_drop, uint64_t seed,
+                     float* dx, float* dgamma, float* dbeta, float* dpre_bias, int64_t rows, int C, void* stream) {
+  LnExtra ex;
+  if (int rc = make_extra("hs_layernorm_bwd", row_scale, rows_per_scale, in_drop, seed, &ex)) return rc;
   HS_REQUIRE(dy && x && mean && rstd && gamma && dx, "hs_layernorm_bwd: null pointer");
   HS_REQUIRE(rows > 0, "hs_layernorm_bwd: rows must be positive");
   HS_REQUIRE(C > 0, "hs_layernorm_bwd: C must be positive");
@@ -335,27 +394,26 @@ int hs_layernorm_bwd(const float* dy, const float* x, const float* pre_bias, con
     long long blocks = (rows + kThreads / 32 - 1) / (kThreads / 32);
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
     ln_bwd_generic_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>(dy, x, pre_bias, mean, rstd, gamma, dx,
-                                                                              dgamma, dbeta, dpre_bias, rows, C);
+                                                                              dgamma, dbeta, dpre_bias, rows, C, ex);
     HS_LAUNCH_CHECK();
     return HS_OK;
   }
   const size_t smem = (pre_bias ? 3 : 2) * (size_t)C * sizeof(float);
+#define HS_LN_BWD_LAUNCH(PB, DROP)                                                                               \
+  HS_LN_DISPATCH(V, {                                                                                            \
+    constexpr int VB = (PB && VV > 6) ? 6 : VV; /* the pre-bias variant is only dispatched for V <= 6 */         \
+    const int grid = grid_for(ln_bwd_kernel<VB, PB, DROP>, smem, rows, T);                                       \
+    ln_bwd_kernel<VB, PB, DROP><<<grid, kThreads, smem, (cudaStream_t)stream>>>(                                 \
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),                                 \
+        reinterpret_cast<const float4*>(pre_bias), mean, rstd, reinterpret_cast<const float4*>(gamma),           \
+        reinterpret_cast<float4*>(dx), dgamma, dbeta, dpre_bias, rows, T, ex);                                   \
+  })
   if (pre_bias) {
-    HS_LN_DISPATCH(V, {
-      const int grid = grid_for(ln_bwd_kernel<(VV <= 6 ? VV : 6), true>, smem, rows, T);
-      ln_bwd_kernel<(VV <= 6 ? VV : 6), true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-          reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x),
-          reinterpret_cast<const float4*>(pre_bias), mean, rstd, reinterpret_cast<const float4*>(gamma),
-          reinterpret_cast<float4*>(dx), dgamma, dbeta, dpre_bias, rows, T);
-    });
+    if (ex.drop_thresh) { HS_LN_BWD_LAUNCH(true, true); } else { HS_LN_BWD_LAUNCH(true, false); }
   } else {
-    HS_LN_DISPATCH(V, {
-      const int grid = grid_for(ln_bwd_kernel<VV, false>, smem, rows, T);
-      ln_bwd_kernel<VV, false><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-          reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), nullptr, mean, rstd,
-          reinterpret_cast<const float4*>(gamma), reinterpret_cast<float4*>(dx), dgamma, dbeta, nullptr, rows, T);
-    });
+    if (ex.drop_thresh) { HS_LN_BWD_LAUNCH(false, true); } else { HS_LN_BWD_LAUNCH(false, false); }
   }
+#undef HS_LN_BWD_LAUNCH
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

@@ -28,12 +28,16 @@ class DropPath(nn.Module):
         super().__init__()
         self.drop_prob = drop_prob
 
-    def forward(self, x):
+    def sample_scale(self, x):
+        """Per-sample factor (0 or 1 / keep) of one stochastic-depth draw, or None when inactive."""
         if not self.training or not self.drop_prob:
-            return x
+            return None
         keep = 1.0 - self.drop_prob
-        mask = x.new_empty((x.shape[0],) + (1,) * (x.ndim - 1)).bernoulli_(keep)
-        return x * (mask / keep)
+        return x.new_empty((x.shape[0],)).bernoulli_(keep) / keep
+
+    def forward(self, x):
+        scale = self.sample_scale(x)
+        return x if scale is None else x * scale.view((x.shape[0],) + (1,) * (x.ndim - 1))
 
 
 class Mlp(nn.Module):
@@ -50,21 +54,26 @@ class Mlp(nn.Module):
 
     def _fusable(self):
         return (isinstance(self.act, nn.GELU) and getattr(self.act, "approximate", "none") == "none"
-                and self.fc1.bias is not None and not (self.training and self.drop.p > 0.0))
+                and self.fc1.bias is not None)
+
+    def _drop_p(self):
+        return self.drop.p if self.training else 0.0
 
     def forward_split(self, x):
-        """(fc2 output WITHOUT its bias, that bias or None): the caller adds the bias (fused into the LayerNorm that
-        follows in the v2 placement).  fc1's bias add, the GELU and (backward) fc1's bias gradient are one kernel."""
-        if not self._fusable():
-            return self.forward(x), None
-        h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias)
-        return ops.linear(h, self.fc2.weight), self.fc2.bias
+        """(fc2 output WITHOUT its bias and WITHOUT the trailing dropout, that bias or None, that dropout's p): the
+        caller applies both (fused into the LayerNorm that follows in the v2 placement).  fc1's bias add, the GELU, the
+        first dropout and (backward) fc1's bias gradient are one kernel."""
+        if not self._fusable() or self.fc2.bias is None:
+            return self.forward(x), None, 0.0
+        h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias, drop=self._drop_p())
+        return ops.linear(h, self.fc2.weight), self.fc2.bias, self._drop_p()
 
     def forward(self, x):
         if not self._fusable():
             h = self.drop(self.act(ops.linear(x, self.fc1.weight, self.fc1.bias)))
             return self.drop(ops.linear(h, self.fc2.weight, self.fc2.bias))
-        return ops.linear(ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias), self.fc2.weight, self.fc2.bias)
+        h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias, drop=self._drop_p())
+        return self.drop(ops.linear(h, self.fc2.weight, self.fc2.bias))
 
 
 class WindowAttention(nn.Module):
@@ -115,12 +124,13 @@ class WindowAttention(nn.Module):
         return self.proj_drop(ops.linear(out, self.proj.weight, self.proj.bias))
 
     def forward_tokens_split(self, x, window_size, src=None, groups=None):
-        """As forward_tokens, but returns (proj output WITHOUT its bias, that bias or None) so that the caller can fuse
-        the bias add into the LayerNorm that follows (v2 norm placement)."""
-        if self.proj.bias is None or (self.training and self.proj_drop.p > 0.0):
-            return self.forward_tokens(x, window_size, src, groups), None
+        """As forward_tokens, but returns (proj output WITHOUT its bias and WITHOUT proj_drop, that bias or None, the
+        dropout probability still to be applied) so that the caller can fuse both into the LayerNorm that follows (v2
+        norm placement)."""
+        if self.proj.bias is None:
+            return self.forward_tokens(x, window_size, src, groups), None, 0.0
         out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), window_size, src, groups, None)
-        return ops.linear(out, self.proj.weight), self.proj.bias
+        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0)
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:124-174]"""
@@ -194,30 +204,30 @@ class SwinTransformerBlock(nn.Module):
         if not self.use_v2_norm_placement:
             x = ops.layer_norm(x, self.norm1)
         # shift + partition + W-MSA/SW-MSA + reverse + shift back, one kernel chain   [:319-330]
-        x, pre_bias = self.attn.forward_tokens_split(x, self.window_size, self._hs_src, self._hs_groups)
-        return _residual_tail(self, shortcut, x, pre_bias)
+        if self.use_v2_norm_placement:
+            x, pre_bias, pdrop = self.attn.forward_tokens_split(x, self.window_size, self._hs_src, self._hs_groups)
+        else:
+            x, pre_bias, pdrop = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups), None, 0.0
+        return _residual_tail(self, shortcut, x, pre_bias, pdrop)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"
                 f" window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
 
 
-def _residual_tail(blk, shortcut, x, pre_bias=None):
+def _residual_tail(blk, shortcut, x, pre_bias=None, pre_drop=0.0):
     """The two residual branches after the attention   [swin_hp_transformer.py:333-338 / swin_transformer.py:394-401].
-    ``x`` is the attention branch, ``pre_bias`` the not-yet-added bias of its output projection (or None).
-    Without stochastic depth (drop_path == 0 or eval) ``shortcut + norm(x + bias)`` is one fused launch."""
-    plain = isinstance(blk.drop_path, nn.Identity) or not blk.training
+    ``x`` is the attention branch, ``pre_bias`` / ``pre_drop`` the not-yet-applied bias and dropout of its output
+    projection.  In the v2 placement every ``shortcut + drop_path(norm(drop(branch + bias)))`` is ONE fused launch
+    (bias, dropout, LayerNorm, per-sample stochastic-depth scale, residual add)."""
+    dp = blk.drop_path
+    scale_of = (lambda t: dp.sample_scale(t)) if isinstance(dp, DropPath) else (lambda t: None)
     if blk.use_v2_norm_placement:
-        if plain:
-            x = ops.layer_norm(x, blk.norm1, residual=shortcut, pre_bias=pre_bias)
-            h, hb = blk.mlp.forward_split(x)
-            return ops.layer_norm(h, blk.norm2, residual=x, pre_bias=hb)
-        x = shortcut + blk.drop_path(ops.layer_norm(x, blk.norm1, pre_bias=pre_bias))
-        return x + blk.drop_path(ops.layer_norm(blk.mlp(x), blk.norm2))
-    if pre_bias is not None:
-        x = x + pre_bias
-    x = shortcut + blk.drop_path(x)
-    return x + blk.drop_path(blk.mlp(ops.layer_norm(x, blk.norm2)))
+        x = ops.layer_norm(x, blk.norm1, residual=shortcut, pre_bias=pre_bias, row_scale=scale_of(x), in_drop=pre_drop)
+        h, hb, hdrop = blk.mlp.forward_split(x)
+        return ops.layer_norm(h, blk.norm2, residual=x, pre_bias=hb, row_scale=scale_of(x), in_drop=hdrop)
+    x = shortcut + dp(x)
+    return x + dp(blk.mlp(ops.layer_norm(x, blk.norm2)))
 
 
 SwinHPTransformerBlock = SwinTransformerBlock  # the name BASELINE.json uses

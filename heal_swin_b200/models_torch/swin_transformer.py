@@ -142,11 +142,12 @@ class WindowAttention(nn.Module):
         return self.proj_drop(ops.linear(out, self.proj.weight, self.proj.bias))
 
     def forward_tokens_split(self, x, n_tokens, src=None, groups=None):
-        """(proj output WITHOUT its bias, that bias or None): the bias add is fused into the following LayerNorm."""
-        if self.proj.bias is None or (self.training and self.proj_drop.p > 0.0):
-            return self.forward_tokens(x, n_tokens, src, groups), None
+        """(proj output WITHOUT its bias and proj_drop, that bias or None, the dropout p still to apply): both are fused
+        into the following LayerNorm."""
+        if self.proj.bias is None:
+            return self.forward_tokens(x, n_tokens, src, groups), None, 0.0
         out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), n_tokens, src, groups, None)
-        return ops.linear(out, self.proj.weight), self.proj.bias
+        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0)
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:148-202]"""
@@ -222,11 +223,14 @@ class SwinTransformerBlock(nn.Module):
         shortcut = x
         if not self.use_v2_norm_placement:
             x = ops.layer_norm(x, self.norm1)
-        x, pre_bias = self.attn.forward_tokens_split(x, self.window_size[0] * self.window_size[1], self._hs_src,
-                                                     self._hs_groups)
+        n_tok = self.window_size[0] * self.window_size[1]
+        if self.use_v2_norm_placement:
+            x, pre_bias, pdrop = self.attn.forward_tokens_split(x, n_tok, self._hs_src, self._hs_groups)
+        else:
+            x, pre_bias, pdrop = self.attn.forward_tokens(x, n_tok, self._hs_src, self._hs_groups), None, 0.0
         if self.fixup is not None:
             x = self.fixup(x)
-        return _residual_tail(self, shortcut, x, pre_bias)
+        return _residual_tail(self, shortcut, x, pre_bias, pdrop)
 
     def extra_repr(self) -> str:
         return (f"dim={self.dim}, input_resolution={self.input_resolution}, num_heads={self.num_heads},"

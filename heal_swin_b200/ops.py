@@ -177,12 +177,12 @@ def window_attention_core(qkv, bias_table, logit_scale, src, groups, dense_mask,
 
 
 class LayerNormFn(torch.autograd.Function):
-    """y = residual + LayerNorm(x + pre_bias) * weight + bias over the last dim (pre_bias, residual optional),
-    csrc/hs_layernorm.cu."""
+    """y = residual + row_scale * (LayerNorm(dropout(x + pre_bias)) * weight + bias) over the last dim (pre_bias,
+    residual, row_scale and the dropout optional), csrc/hs_layernorm.cu."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, pre_bias, eps):
-        require_cuda(x, weight, bias, residual, pre_bias)
+    def forward(ctx, x, weight, bias, residual, pre_bias, eps, row_scale, in_drop, seed):
+        require_cuda(x, weight, bias, residual, pre_bias, row_scale)
         shape = x.shape
         Cc = shape[-1]
         x2 = _f32c(x).reshape(-1, Cc)
@@ -190,20 +190,25 @@ class LayerNormFn(torch.autograd.Function):
         w, b = _f32c(weight), _f32c(bias)
         res2 = _f32c(residual).reshape(-1, Cc) if residual is not None else None
         pb = _f32c(pre_bias) if pre_bias is not None else None
+        rsc = _f32c(row_scale).reshape(-1) if row_scale is not None else None
+        rps = rows // rsc.numel() if rsc is not None else 0
+        assert rsc is None or rps * rsc.numel() == rows, "row_scale must divide the rows evenly"
         y = torch.empty_like(x2)
         mean = torch.empty(rows, device=x2.device, dtype=torch.float32)
         rstd = torch.empty(rows, device=x2.device, dtype=torch.float32)
-        STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), ptr(pb), ptr(res2), ptr(w), ptr(b), ptr(y),
-                     ptr(mean), ptr(rstd), rows, Cc, C.c_float(eps), current_stream(),
-                     tag=(rows, Cc, int(res2 is not None)))
-        ctx.save_for_backward(x2, w, mean, rstd, pb)
+        STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), ptr(pb), ptr(res2), ptr(w), ptr(b), ptr(rsc), rps,
+                     C.c_float(in_drop), C.c_uint64(seed), ptr(y), ptr(mean), ptr(rstd), rows, Cc, C.c_float(eps),
+                     current_stream(), tag=(rows, Cc, int(res2 is not None)))
+        ctx.save_for_backward(x2, w, mean, rstd, pb, rsc)
         ctx.has_res = residual is not None
         ctx.shape = shape
+        ctx.extra = (rps, float(in_drop), int(seed))
         return y.view(shape)
 
     @staticmethod
     def backward(ctx, dy):
-        x2, w, mean, rstd, pb = ctx.saved_tensors
+        x2, w, mean, rstd, pb, rsc = ctx.saved_tensors
+        rps, in_drop, seed = ctx.extra
         rows, Cc = x2.shape
         dy2 = _f32c(dy).reshape(rows, Cc)
         dx = torch.empty_like(x2)
@@ -213,9 +218,10 @@ class LayerNormFn(torch.autograd.Function):
         db = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_b else None
         dpb = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_pb else None
         STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(x2), ptr(pb), ptr(mean), ptr(rstd), ptr(w),
-                     ptr(dx), ptr(dw), ptr(db), ptr(dpb), rows, Cc, current_stream(), tag=(rows, Cc))
+                     ptr(rsc), rps, C.c_float(in_drop), C.c_uint64(seed), ptr(dx), ptr(dw), ptr(db), ptr(dpb), rows, Cc,
+                     current_stream(), tag=(rows, Cc))
         dres = dy if ctx.has_res else None
-        return dx.view(ctx.shape), dw, db, dres, dpb, None
+        return dx.view(ctx.shape), dw, db, dres, dpb, None, None, None, None
 
 
 def _fusable_norm(norm, x):
@@ -223,30 +229,42 @@ def _fusable_norm(norm, x):
             and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == x.shape[-1])
 
 
-def layer_norm(x, norm, residual=None, pre_bias=None):
-    """``residual + norm(x + pre_bias)`` for an ``nn.LayerNorm`` module ``norm`` (affine, normalising the last dim) in
-    one launch; any other norm layer is applied as the module it is."""
+def layer_norm(x, norm, residual=None, pre_bias=None, row_scale=None, in_drop=0.0, seed=None):
+    """``residual + row_scale * norm(dropout(x + pre_bias))`` for an ``nn.LayerNorm`` module ``norm`` (affine, normalising
+    the last dim) in one launch.  ``row_scale``: one factor per leading-dimension sample (stochastic depth), a constant
+    (no gradient).  ``in_drop``: dropout probability on the LayerNorm input (counter-based mask, fresh seed by default).
+    Any other norm layer is applied as the module it is."""
+    in_drop = float(in_drop)
     if _fusable_norm(norm, x):
-        return LayerNormFn.apply(x, norm.weight, norm.bias, residual, pre_bias, float(norm.eps))
-    y = norm(x if pre_bias is None else x + pre_bias)
+        if in_drop > 0.0 and seed is None:
+            seed = _next_dropout_seed()
+        return LayerNormFn.apply(x, norm.weight, norm.bias, residual, pre_bias, float(norm.eps), row_scale, in_drop,
+                                 int(seed or 0))
+    h = x if pre_bias is None else x + pre_bias
+    if in_drop > 0.0:
+        h = torch.nn.functional.dropout(h, in_drop, True)
+    y = norm(h)
+    if row_scale is not None:
+        y = y * row_scale.view(-1, *([1] * (y.dim() - 1)))
     return y if residual is None else residual + y
 
 
 class BiasGeluFn(torch.autograd.Function):
-    """h = GELU(z + bias) (exact erf GELU), csrc/hs_bias_gelu.cu; backward also yields d(bias)."""
+    """h = dropout(GELU(z + bias)) (exact erf GELU), csrc/hs_bias_gelu.cu; backward also yields d(bias)."""
 
     @staticmethod
-    def forward(ctx, z, bias):
+    def forward(ctx, z, bias, drop, seed):
         require_cuda(z, bias)
         shape = z.shape
         Cc = shape[-1]
         z2 = _f32c(z).reshape(-1, Cc)
         b = _f32c(bias) if bias is not None else None
         h = torch.empty_like(z2)
-        STATS.launch("bias_gelu_fwd", lib.hs_bias_gelu_fwd, ptr(z2), ptr(b), ptr(h), z2.shape[0], Cc, current_stream(),
-                     tag=(z2.shape[0], Cc))
+        STATS.launch("bias_gelu_fwd", lib.hs_bias_gelu_fwd, ptr(z2), ptr(b), C.c_float(drop), C.c_uint64(seed), ptr(h),
+                     z2.shape[0], Cc, current_stream(), tag=(z2.shape[0], Cc))
         ctx.save_for_backward(z2, b)
         ctx.shape = shape
+        ctx.drop = (float(drop), int(seed))
         return h.view(shape)
 
     @staticmethod
@@ -257,13 +275,16 @@ class BiasGeluFn(torch.autograd.Function):
         dz = torch.empty_like(z2)
         need_b = b is not None and ctx.needs_input_grad[1]
         db = torch.zeros(Cc, device=z2.device, dtype=torch.float32) if need_b else None
-        STATS.launch("bias_gelu_bwd", lib.hs_bias_gelu_bwd, ptr(dh2), ptr(z2), ptr(b), ptr(dz), ptr(db), rows, Cc,
-                     current_stream(), tag=(rows, Cc))
-        return dz.view(ctx.shape), db
+        STATS.launch("bias_gelu_bwd", lib.hs_bias_gelu_bwd, ptr(dh2), ptr(z2), ptr(b), C.c_float(ctx.drop[0]),
+                     C.c_uint64(ctx.drop[1]), ptr(dz), ptr(db), rows, Cc, current_stream(), tag=(rows, Cc))
+        return dz.view(ctx.shape), db, None, None
 
 
-def bias_gelu(z, bias):
-    return BiasGeluFn.apply(z, bias)
+def bias_gelu(z, bias, drop=0.0, seed=None):
+    drop = float(drop)
+    if drop > 0.0 and seed is None:
+        seed = _next_dropout_seed()
+    return BiasGeluFn.apply(z, bias, drop, int(seed or 0))
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -133,35 +133,40 @@ int hs_window_attn_bwd(const float* qkv_dev, const float* out_dev, const float* 
                        uint32_t flags, void* stream);
 
 /*
- * Row LayerNorm over the last dimension, optionally fused with the bias of the Linear that produced its input and
- * with the residual add of the v2 norm placement:
- *     y = residual + LayerNorm(x + pre_bias) * gamma + beta          (pre_bias, residual may be NULL)
- * Replaces nn.LayerNorm at swin_hp_transformer.py:316, 333-338 (norm1 / norm2; "shortcut + norm(proj(.))" and
- * "x + norm(fc2(.))" are one pass, the proj / fc2 GEMMs run without bias), :392 (PatchMerging.norm, 4C), :428
- * (PatchExpand.norm, C/2), :450 (FinalPatchExpand_X4.norm), :781, :945.
- * x, residual, y: (rows, C) fp32; pre_bias, gamma, beta: (C); mean, rstd: (rows) fp32 saved for the backward (both
- * NULL = do not save).  Statistics as torch: biased variance, rstd = 1/sqrt(var + eps).
+ * Row LayerNorm over the last dimension, optionally fused with the bias of the Linear that produced its input, the
+ * dropout that follows that Linear, the per-sample stochastic-depth scale and the residual add of the v2 norm placement:
+ *     y = residual + row_scale[row / rows_per_scale] * (LayerNorm(dropout(x + pre_bias)) * gamma + beta)
+ * (pre_bias, residual, row_scale may be NULL; in_drop = 0 disables the dropout).
+ * Replaces nn.LayerNorm at swin_hp_transformer.py:316, 333-338 (norm1 / norm2; "shortcut + drop_path(norm(proj_drop(
+ * proj(.))))" and "x + drop_path(norm(mlp(.)))" are one pass, the proj / fc2 GEMMs run without bias), :392
+ * (PatchMerging.norm, 4C), :428 (PatchExpand.norm, C/2), :450 (FinalPatchExpand_X4.norm), :781, :945.
+ * x, residual, y: (rows, C) fp32; pre_bias, gamma, beta: (C); row_scale: (rows / rows_per_scale); mean, rstd: (rows) fp32
+ * saved for the backward (both NULL = do not save).  Statistics as torch: biased variance, rstd = 1/sqrt(var + eps).
+ * The dropout mask of element (row, col) is a pure function of (seed, row, col): pass the same seed to the backward.
  */
 int hs_layernorm_fwd(const float* x_dev, const float* pre_bias_dev, const float* residual_dev, const float* gamma_dev,
-                     const float* beta_dev, float* y_dev, float* mean_dev, float* rstd_dev, int64_t rows, int C,
-                     float eps, void* stream);
+                     const float* beta_dev, const float* row_scale_dev, int64_t rows_per_scale, float in_drop,
+                     uint64_t seed, float* y_dev, float* mean_dev, float* rstd_dev, int64_t rows, int C, float eps,
+                     void* stream);
 /*
  * Adjoint: dx (rows, C) is overwritten; dgamma / dbeta / dpre_bias (C) are accumulated into (+=), each may be NULL
  * (dpre_bias = column sums of dx = the bias gradient of the producing Linear).  The gradient of the fused residual
  * input is dy itself.
  */
 int hs_layernorm_bwd(const float* dy_dev, const float* x_dev, const float* pre_bias_dev, const float* mean_dev,
-                     const float* rstd_dev, const float* gamma_dev, float* dx_dev, float* dgamma_dev, float* dbeta_dev,
+                     const float* rstd_dev, const float* gamma_dev, const float* row_scale_dev, int64_t rows_per_scale,
+                     float in_drop, uint64_t seed, float* dx_dev, float* dgamma_dev, float* dbeta_dev,
                      float* dpre_bias_dev, int64_t rows, int C, void* stream);
 
 /*
- * h = GELU(z + bias) with the exact erf GELU of nn.GELU (swin_hp_transformer.py:21-44, Mlp: fc1 -> act), z: (rows, C)
- * the bias-free fc1 GEMM output, bias: (C) or NULL; and its adjoint dz = dh * GELU'(z + bias), dbias (C) += column
- * sums of dz (may be NULL).
+ * h = dropout(GELU(z + bias)) with the exact erf GELU of nn.GELU (swin_hp_transformer.py:21-44, Mlp: fc1 -> act -> drop),
+ * z: (rows, C) the bias-free fc1 GEMM output, bias: (C) or NULL, drop = 0 disables the dropout (mask: a pure function of
+ * (seed, row, col)); and its adjoint dz = dh * mask * GELU'(z + bias), dbias (C) += column sums of dz (may be NULL).
  */
-int hs_bias_gelu_fwd(const float* z_dev, const float* bias_dev, float* h_dev, int64_t rows, int C, void* stream);
-int hs_bias_gelu_bwd(const float* dh_dev, const float* z_dev, const float* bias_dev, float* dz_dev, float* dbias_dev,
-                     int64_t rows, int C, void* stream);
+int hs_bias_gelu_fwd(const float* z_dev, const float* bias_dev, float drop, uint64_t seed, float* h_dev, int64_t rows,
+                     int C, void* stream);
+int hs_bias_gelu_bwd(const float* dh_dev, const float* z_dev, const float* bias_dev, float drop, uint64_t seed,
+                     float* dz_dev, float* dbias_dev, int64_t rows, int C, void* stream);
 
 /*
  * Weight gradient of nn.Linear (autograd of F.linear at swin_hp_transformer.py:131, 172, 21-44, 394, 421, 444, 774):

@@ -36,6 +36,14 @@ def main():
         t_b = timeit(lambda: torch.autograd.grad(y, [x, norm.weight, norm.bias], dy, retain_graph=True))
         yt = F.layer_norm(x, (C,), norm.weight, norm.bias, norm.eps)
         t_bt = timeit(lambda: torch.autograd.grad(yt, [x, norm.weight, norm.bias], dy, retain_graph=True))
+        pb = torch.randn(C, device=dev, requires_grad=True)
+        y2 = ops.layer_norm(x, norm, residual=res, pre_bias=pb)
+        t_b2 = timeit(lambda: torch.autograd.grad(y2, [x, norm.weight, norm.bias, pb], dy, retain_graph=True))
+        y3 = ops.layer_norm(x, norm, residual=res, pre_bias=pb, in_drop=0.1, seed=5)
+        t_f3 = timeit(lambda: ops.layer_norm(x, norm, residual=res, pre_bias=pb, in_drop=0.1, seed=5))
+        t_b3 = timeit(lambda: torch.autograd.grad(y3, [x, norm.weight, norm.bias, pb], dy, retain_graph=True))
+        print(f"   with pre-bias: bwd {t_b2:.3f} ms; with pre-bias + dropout 0.1: fwd {t_f3:.3f} ms bwd {t_b3:.3f} ms")
+        del y2, y3
         print(f"rows={rows} C={C}: fused fwd {t_f:.3f} ms ({3 * gb / t_f * 1e3:.0f} GB/s; torch LN+add {t_ft:.3f} ms)  "
               f"bwd {t_b:.3f} ms ({3 * gb / t_b * 1e3:.0f} GB/s; torch {t_bt:.3f} ms)", flush=True)
         del x, res, dy, y, yt

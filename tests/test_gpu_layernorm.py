@@ -125,3 +125,81 @@ def test_bias_gelu_fwd_bwd_vs_torch(C, rows):
     (h2 * wgt).sum().backward()
     for a, w, tol in zip(got, [h2.detach(), z.grad, b.grad], [1e-5, 1e-5, 1e-4]):
         assert rel_err(a.cpu(), w.cpu()) < tol
+
+
+# ---------------------------------------------------------------------------------------------- fused dropout / drop-path
+M32 = 0xFFFFFFFF
+
+
+def _mix32(x):
+    x = x.astype(np.uint64)
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & M32
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & M32
+    x ^= x >> 16
+    return x
+
+
+def host_elem_mask(seed, rows, C, p):
+    """(rows, C) float32 multiplier of the element-wise dropout the kernels apply (csrc/hs_common.h: drop_row_key /
+    drop_keep_elem): 0 where dropped, 1/(1-p) where kept."""
+    thresh = min(int(float(np.float32(p)) * 4294967296.0), M32)
+    r = np.arange(rows, dtype=np.uint64)
+    key = _mix32((np.uint64(seed & M32) ^ _mix32(((seed >> 32) + r) & M32) ^ (r >> 32)) & M32)
+    e = (np.arange(C, dtype=np.uint64) * 0x9E3779B9) & M32
+    keep = _mix32((key[:, None] ^ e[None, :]) & M32) >= thresh
+    return torch.from_numpy(keep.astype(np.float32) * (np.float32(1.0) / (np.float32(1.0) - np.float32(p))))
+
+
+@pytest.mark.parametrize("C", [96, 384, 100])
+def test_layernorm_fused_dropout_droppath_matches_torch_with_the_same_mask(C):
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    B, n, p, seed = 4, 150, 0.2, 0xABCDEF0123456789
+    rows = B * n
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(B, n, C, generator=g).to(dev).requires_grad_(True)
+    res = torch.randn(B, n, C, generator=g).to(dev).requires_grad_(True)
+    pb = torch.randn(C, generator=g).to(dev).requires_grad_(True)
+    scale = torch.tensor([0.0, 1.25, 1.25, 0.0]).to(dev)  # a stochastic-depth draw with keep = 0.8
+    norm = torch.nn.LayerNorm(C).to(dev)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.3 * torch.randn(C, generator=g))
+        norm.bias.copy_(0.2 * torch.randn(C, generator=g))
+    wgt = torch.randn(B, n, C, generator=g).to(dev)
+    y = ops.layer_norm(x, norm, residual=res, pre_bias=pb, row_scale=scale, in_drop=p, seed=seed)
+    (y * wgt).sum().backward()
+    got = [y.detach().clone(), x.grad.clone(), pb.grad.clone(), norm.weight.grad.clone(), norm.bias.grad.clone(), res.grad.clone()]
+    for t in (x, res, pb, norm.weight, norm.bias):
+        t.grad = None
+    mult = host_elem_mask(seed, rows, C, p).view(B, n, C).to(dev)
+    y2 = res + scale.view(B, 1, 1) * F.layer_norm((x + pb) * mult, (C,), norm.weight, norm.bias, norm.eps)
+    (y2 * wgt).sum().backward()
+    want = [y2.detach(), x.grad, pb.grad, norm.weight.grad, norm.bias.grad, res.grad]
+    for a, b, tol in zip(got, want, [1e-5, 1e-4, 1e-4, 1e-4, 1e-4, 1e-6]):
+        assert rel_err(a.cpu(), b.cpu()) < tol
+
+
+@pytest.mark.parametrize("C", [384, 64])
+def test_bias_gelu_fused_dropout_matches_torch_with_the_same_mask(C):
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    rows, p, seed = 999, 0.1, 77
+    g = torch.Generator().manual_seed(C)
+    z = (torch.randn(rows, C, generator=g) * 2).to(dev).requires_grad_(True)
+    b = torch.randn(C, generator=g).to(dev).requires_grad_(True)
+    wgt = torch.randn(rows, C, generator=g).to(dev)
+    h = ops.bias_gelu(z, b, drop=p, seed=seed)
+    (h * wgt).sum().backward()
+    got = [h.detach().clone(), z.grad.clone(), b.grad.clone()]
+    z.grad = b.grad = None
+    mult = host_elem_mask(seed, rows, C, p).to(dev)
+    h2 = F.gelu(z + b) * mult
+    (h2 * wgt).sum().backward()
+    kept = float((mult > 0).float().mean())
+    assert abs(kept - (1 - p)) < 0.01
+    for a, w, tol in zip(got, [h2.detach(), z.grad, b.grad], [1e-5, 1e-5, 1e-4]):
+        assert rel_err(a.cpu(), w.cpu()) < tol

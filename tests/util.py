@@ -31,7 +31,8 @@ def build_product_model(kw, sd=None, device="cpu"):
     from heal_swin_b200.models_torch import swin_hp_transformer as M
 
     cfgkw = {k: v for k, v in kw.items() if k not in ("dim_in", "f_in", "f_out", "base_pix")}
-    cfg = M.SwinHPTransformerConfig(**cfgkw, drop_path_rate=0.0)
+    cfgkw.setdefault("drop_path_rate", 0.0)
+    cfg = M.SwinHPTransformerConfig(**cfgkw)
     spec = DataSpec(dim_in=kw["dim_in"], f_in=kw["f_in"], f_out=kw["f_out"], base_pix=kw["base_pix"])
     model = M.SwinHPTransformerSys(cfg, data_spec=spec)
     if sd is not None:
