@@ -82,3 +82,30 @@ def test_forward_error_with_tf32_library_gemms_is_bounded():
             assert rel_err(y.cpu(), gold["y"]) < TF32_GEMM_FWD_TOL, name
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def test_reference_own_test_config_vs_oracle():
+    """The model of the reference's own pytest config (heal_swin/testing/swin_hp_test_run_config.py:29-55: N_side=32,
+    base_pix=8, window_size=4, patch_size=4, depths=(2, 1), num_heads=(1, 1), embed_dim=2 -> head_dim 2, C=2): every kernel
+    takes its generic path (CUDA-core attention, scalar LayerNorm).  Forward and a gradient vs the CPU oracle."""
+    dev = torch.device("cuda:0")
+    kw = dict(patch_size=4, window_size=4, shift_size=2, shift_strategy="nest_roll", rel_pos_bias=None, embed_dim=2,
+              depths=[2, 1], num_heads=[1, 1], dim_in=8 * 32 * 32, f_in=3, f_out=10, base_pix=8)
+    cfg = O.HPConfig(**kw)
+    sd = O.synth_state_dict(cfg, seed=21)
+    x = torch.randn(2, 3, kw["dim_in"], generator=torch.Generator().manual_seed(4))
+    sd_g = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    want = O.hp_unet_forward(x, sd_g, cfg)
+    wgt = torch.randn(want.shape, generator=torch.Generator().manual_seed(5))
+    (want * wgt).sum().backward()
+    model = build_product_model(kw, sd, dev).train()
+    got = model(x.to(dev))
+    assert rel_err(got.detach().cpu(), want.detach()) < FWD_TOL
+    (got * wgt.to(dev)).sum().backward()
+    params = dict(model.named_parameters())
+    # With C = 2 a LayerNorm output is (+1, -1) whatever its input, so every gradient that has to pass BACK through a
+    # LayerNorm is pure cancellation (1e-7 of the upstream gradient, see test_gpu_layernorm.py) and not comparable;
+    # the parameters after the last normalisation are.
+    for k in ("decoder.output.weight", "decoder.up.norm.weight", "decoder.up.norm.bias"):
+        assert rel_err(params[k].grad.cpu(), sd_g[k].grad) < GRAD_TOL, k
+    assert all(torch.isfinite(p.grad).all() for p in params.values() if p.grad is not None)
