@@ -65,7 +65,7 @@ struct Smem {
   Slot slot[kSlots];
   float bias[kWS * kBiasPitch];     // bias[i][j] * log2(e); query rows read it row-wise (LDS.128), key rows column-wise
   SlotMeta meta[kSlots];
-  float inv[2][2 * kWS];  // per warpgroup: [0,64) 1/max(|q_i|,eps), [64,128) 1/max(|k_j|,eps)
+  float inv[kSlots][2 * kWS];  // per slot (statistics warps, from the forward): [0,64) 1/max(|q_i|,eps), [64,128) 1/max(|k_j|,eps)
   float lse[kSlots][kWS];    // per slot (written by the statistics warp): log2-domain log-sum-exp of every query row
   float delta[kSlots][kWS];  // per slot: rowsum(P o dP) = dO_i . O_i
   float4 lse4[2][kWS];       // per warpgroup: my row's value replicated 4x (what a query-row thread reads along its columns)
@@ -79,7 +79,7 @@ struct Smem {
 struct BwdArgs {
   const float* qkv;
   const float* out;  // forward output (B, N, C)
-  const float* lse;  // forward log2-domain log-sum-exp (H, B*N)
+  const float* lse;  // forward statistics (P, H, B*N): plane 0 log2-domain log-sum-exp; planes 1, 2 (cos) 1/|q|, 1/|k|
   const float* dout;
   float* dqkv;
   const int32_t* src;
@@ -485,7 +485,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         mbar_wait(&S.meta_ready[slot], (uint32_t)(n / kSlots) & 1);
         const SlotMeta& M = S.meta[slot];
         float4 o[2][8], d[2][8];
-        float lse[2];
+        float lse[2], qi[2] = {1.f, 1.f}, ki[2] = {1.f, 1.f};
+        const long long plane = (long long)a.H * ((long long)a.B * a.N);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const long long row = M.rows[lane + 32 * k];
@@ -497,6 +498,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
             d[k][c] = __ldg(drow + c);
           }
           lse[k] = __ldg(a.lse + (long long)h * ((long long)a.B * a.N) + row);
+          if (a.cos) {
+            qi[k] = __ldg(a.lse + plane + (long long)h * ((long long)a.B * a.N) + row);
+            ki[k] = __ldg(a.lse + 2 * plane + (long long)h * ((long long)a.B * a.N) + row);
+          }
         }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
@@ -506,6 +511,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
             dot += (o[k][c].x * d[k][c].x + o[k][c].y * d[k][c].y) + (o[k][c].z * d[k][c].z + o[k][c].w * d[k][c].w);
           S.lse[slot][lane + 32 * k] = lse[k];
           S.delta[slot][lane + 32 * k] = dot;
+          S.inv[slot][lane + 32 * k] = qi[k];
+          S.inv[slot][kWS + lane + 32 * k] = ki[k];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.stats_ready[slot]);
@@ -547,21 +554,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       const uint8_t* myrow = T.qk + L * 128;  // row L of [Q;K]: q_r for the query half, k_r for the key half
 
       const int my_row = M.rows[r];
-      float my_inv = 1.0f;
-      if (a.cos) {
-        float ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 v = *reinterpret_cast<const float4*>(myrow + (((c + lane) & 7) << 4));
-          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
-        my_inv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
-        S.inv[wg][L] = my_inv;
-      }
-      if (a.cos) named_bar_sync(1 + wg, 128);  // the norms of this unit are published
       if (r == 0) HS_TRACE(trole, n, 6);
-      mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kSlots) & 1);  // lse / delta of this unit (statistics warp)
+      mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kSlots) & 1);  // lse / delta / norms of this unit (statistics warps)
       if (r == 0) HS_TRACE(trole, n, 7);
+      const float my_inv = S.inv[slot][L];  // 1/|q_r| (query rows) or 1/|k_r| (key rows); 1 without cos attention
       if (nat) {
         const float lse = S.lse[slot][r], dl = S.delta[slot][r];
         S.lse4[wg][r] = make_float4(lse, lse, lse, lse);
@@ -575,7 +571,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       RowCtx R;
       R.s_src = D1 + (nat ? 64u : 0u);   // S (query rows) / S^T (key rows)
       R.dp_src = D2 + (nat ? 64u : 0u);  // dP / dP^T
-      R.oinv = smem_u32(S.inv[wg] + (nat ? kWS : 0));
+      R.oinv = smem_u32(S.inv[slot] + (nat ? kWS : 0));
       R.brow = smem_u32(S.bias + (nat ? r * kBiasPitch : r));
       R.bstep = nat ? 4u : 4u * kBiasPitch;
       R.groups = smem_u32(M.groups);

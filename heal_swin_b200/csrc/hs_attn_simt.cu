@@ -107,7 +107,15 @@ __device__ float load_tile(const AttnArgs& a, const Smem& m, long long wb, int h
       float ss = 0.f;
       for (int dd = lane; dd < D; dd += 32) ss += p[dd] * p[dd];
       ss = warp_sum(ss);
-      if (lane == 0) m.inv[r] = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+      if (lane == 0) {
+        const float iv = 1.0f / fmaxf(sqrtf(ss), kNormEps);
+        m.inv[r] = iv;
+        if (a.lse) {  // planes 1 (1/|q|) and 2 (1/|k|) of the statistics buffer (cos attention)
+          const long long plane = (long long)a.H * a.B * a.N;
+          const int j = r < ws ? r : r - ws;
+          a.lse[(r < ws ? 1 : 2) * plane + ((long long)h * a.B + b) * a.N + m.row[j]] = iv;
+        }
+      }
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < ws * D; idx += blockDim.x) {

@@ -54,7 +54,7 @@ struct Smem {
 struct TcArgs {
   const float* qkv;
   float* out;
-  float* lse;  // (H, B*N) or null
+  float* lse;  // (P, H, B*N) or null: plane 0 log-sum-exp, planes 1, 2 (cos attention only) 1/|q|, 1/|k|
   const int32_t* src;
   const uint8_t* groups;
   const float* bias;         // (H, 64, 64) or null
@@ -286,8 +286,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
           sq += qv.x * qv.x + qv.y * qv.y + qv.z * qv.z + qv.w * qv.w;
           sk += kv.x * kv.x + kv.y * kv.y + kv.z * kv.z + kv.w * kv.w;
         }
-        row_scale *= 1.0f / fmaxf(sqrtf(sq), kNormEps);
-        S.kinv[wg][L] = 1.0f / fmaxf(sqrtf(sk), kNormEps);
+        const float qinv = 1.0f / fmaxf(sqrtf(sq), kNormEps), kinv = 1.0f / fmaxf(sqrtf(sk), kNormEps);
+        row_scale *= qinv;
+        S.kinv[wg][L] = kinv;
+        if (a.lse && (flags & kFlagValid)) {  // planes 1, 2 of the statistics buffer: the backward reuses the norms
+          const long long plane = (long long)a.H * ((long long)a.B * a.N);
+          a.lse[plane + (long long)h * ((long long)a.B * a.N) + my_row] = qinv;
+          a.lse[2 * plane + (long long)h * ((long long)a.B * a.N) + my_row] = kinv;
+        }
         named_bar_sync(unit_bar, 64);
       }
 

@@ -125,7 +125,9 @@ class WindowAttnCore(torch.autograd.Function):
         mask = _f32c(dense_mask) if dense_mask is not None else None
         out = torch.empty((B, N, Cc), device=qkv.device, dtype=torch.float32)
         # log2-domain log-sum-exp per (head, token): lets the backward skip the softmax-statistics pass
-        lse = torch.empty((H, B * N), device=qkv.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        # planes: 0 = log-sum-exp; 1, 2 = 1/|q|, 1/|k| (cos attention), reused by the backward
+        lse = (torch.empty((3 if use_cos else 1, H, B * N), device=qkv.device, dtype=torch.float32)
+               if ctx.needs_input_grad[0] else None)
         flags = ((_lib.ATTN_COS if use_cos else 0) | (_lib.ATTN_NO_TC if _ATTN_PRECISION == "fp32" else 0)
                  | (_lib.ATTN_NO_TRUNC_COMP if os.environ.get("HEALSWIN_NO_TRUNC_COMP") == "1" else 0))
         STATS.launch("window_attn_fwd", lib.hs_window_attn_fwd, ptr(qkv), ptr(src), ptr(groups), ptr(mask), ptr(bias),

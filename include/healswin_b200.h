@@ -108,8 +108,9 @@ int hs_rel_bias_reduce(const float* dbias_dev, const int32_t* index_dev, float* 
  *   logit_scale (H)     raw parameter (cos attention: logits *= exp(min(ls, log 100))); else NULL
  *   scale               q scaling for the non-cos path (head_dim^-0.5 or qk_scale)
  *   out   (B, N, C)     attention output in the UNSHIFTED token order, row layout [H][D]
- *   lse   (H, B*N)      optional (may be NULL): per (head, token) log2-domain log-sum-exp of the logits row, saved for
- *                       the backward (which then needs no softmax-statistics pass)
+ *   lse   (P, H, B*N)   optional (may be NULL): forward statistics saved for the backward (which then needs no
+ *                       statistics pass): plane 0 = per (head, token) log2-domain log-sum-exp of the logits row; with
+ *                       HS_ATTN_COS P = 3 and planes 1, 2 = 1 / max(|q|, eps), 1 / max(|k|, eps); otherwise P = 1
  *   attn_drop, seed     dropout of the attention probabilities (nn.Dropout(attn_drop) at :167-169, training mode): entry
  *                       (i, j) of a (window, head) is zeroed with probability attn_drop and the rest scaled by
  *                       1 / (1 - attn_drop); the mask is a pure function of (seed, window, head, i, j), so the backward

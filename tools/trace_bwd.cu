@@ -14,7 +14,7 @@ int main(int argc, char** argv) {
   const size_t nq = (size_t)B * N * 3 * C, no = (size_t)B * N * C;
   float *qkv, *dout, *dqkv, *bias, *ls, *dbias, *dls, *outp, *lse;
   cudaMalloc(&qkv, nq * 4); cudaMalloc(&dout, no * 4); cudaMalloc(&dqkv, nq * 4);
-  cudaMalloc(&outp, no * 4); cudaMalloc(&lse, (size_t)H * B * N * 4); cudaMemset(lse, 0, (size_t)H * B * N * 4);
+  cudaMalloc(&outp, no * 4); cudaMalloc(&lse, (size_t)3 * H * B * N * 4); cudaMemset(lse, 0, (size_t)3 * H * B * N * 4);
   cudaMalloc(&bias, H * 64 * 64 * 4); cudaMalloc(&ls, H * 4); cudaMalloc(&dbias, H * 64 * 64 * 4); cudaMalloc(&dls, H * 4);
   std::vector<float> h(1 << 22);
   for (auto& v : h) v = (float)rand() / RAND_MAX - 0.5f;
