@@ -111,11 +111,6 @@ __device__ long long g_trace[kTraceRoles * kTraceUnits * kTracePoints];
 #define HS_TRACE(role, n, k) do {} while (0)
 #endif
 
-__device__ __forceinline__ float lg2_approx(float x) {
-  float y;
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Elementwise stage of one unit.  Written as ROLLED loops over 8-column chunks with everything recomputed from TMEM
@@ -545,7 +540,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         pending_slot = -1;
       }
       mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
-      const int trole = wg * 2 + (nat ? 0 : 1);
+      [[maybe_unused]] const int trole = wg * 2 + (nat ? 0 : 1);  // trace role (diagnostics build only)
       if (r == 0) HS_TRACE(trole, n, 0);
 
       const SlotMeta& M = S.meta[slot];
