@@ -18,4 +18,4 @@ int fail(int code, const char* fmt, ...) {
 }  // namespace hs
 
 extern "C" const char* hs_last_error(void) { return hs::error_buffer(); }
-extern "C" int hs_version(void) { return 110; }
+extern "C" int hs_version(void) { return 111; }

@@ -65,15 +65,21 @@ class Mlp(nn.Module):
         first dropout and (backward) fc1's bias gradient are one kernel."""
         if not self._fusable() or self.fc2.bias is None:
             return self.forward(x), None, 0.0
+        return self._core(x), self.fc2.bias, self._drop_p()
+
+    def _core(self, x):
+        """fc2(drop(GELU(fc1(x)))) without fc2's bias: one fused autograd node when the shapes allow it."""
+        if ops.mlp_supported(x, self.fc1, self.fc2):
+            return ops.mlp_core(x, self.fc1, self.fc2, drop=self._drop_p())
         h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias, drop=self._drop_p())
-        return ops.linear(h, self.fc2.weight), self.fc2.bias, self._drop_p()
+        return ops.linear(h, self.fc2.weight)
 
     def forward(self, x):
         if not self._fusable():
             h = self.drop(self.act(ops.linear(x, self.fc1.weight, self.fc1.bias)))
             return self.drop(ops.linear(h, self.fc2.weight, self.fc2.bias))
-        h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias, drop=self._drop_p())
-        return self.drop(ops.linear(h, self.fc2.weight, self.fc2.bias))
+        y = self._core(x)
+        return self.drop(y if self.fc2.bias is None else y + self.fc2.bias)
 
 
 class WindowAttention(nn.Module):

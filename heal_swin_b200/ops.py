@@ -334,6 +334,73 @@ class _LinearFn(torch.autograd.Function):
         return dx, dw, db
 
 
+_FUSED_MLP = os.environ.get("HEALSWIN_FUSED_MLP", "1") == "1"
+
+
+class _MlpFn(torch.autograd.Function):
+    """``fc2(dropout(GELU(fc1(x) + b1)))`` WITHOUT fc2's bias, as one autograd node, so that the backward never
+    materialises the (T, 4C) hidden gradient: d(fc1 output) comes from the fused dgrad + GELU' kernel
+    (csrc/hs_mlp_dgrad_tc.cu), both weight gradients (and fc1's bias gradient) from the token-split wgrad kernel; the two
+    forward GEMMs and the final input gradient are library GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, drop, seed):
+        K = x.shape[-1]
+        x2 = _f32c(x).reshape(-1, K)
+        T, J = x2.shape[0], w1.shape[0]
+        z = x2 @ w1.t()
+        h = torch.empty_like(z)
+        STATS.launch("bias_gelu_fwd", lib.hs_bias_gelu_fwd, ptr(z), ptr(b1), C.c_float(drop), C.c_uint64(seed), ptr(h),
+                     T, J, current_stream(), tag=(T, J))
+        y = h @ w2.t()
+        ctx.save_for_backward(x2, w1, b1, w2, z, h)
+        ctx.drop = (float(drop), int(seed))
+        ctx.xshape = x.shape
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, b1, w2, z, h = ctx.saved_tensors
+        T, K = x2.shape
+        J, Cout = w1.shape[0], w2.shape[0]
+        dy2 = _f32c(dy).reshape(T, Cout)
+        stream = current_stream()
+        dw2 = torch.zeros((Cout, J), device=x2.device, dtype=torch.float32)
+        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(h), ptr(dw2), None, T, Cout, J, 0, stream,
+                     tag=(T, Cout, J))
+        dz = torch.empty_like(z)
+        STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1), C.c_float(ctx.drop[0]),
+                     C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, 0, stream, tag=(T, Cout, J))
+        dw1 = torch.zeros((J, K), device=x2.device, dtype=torch.float32)
+        db1 = torch.zeros((J,), device=x2.device, dtype=torch.float32)
+        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dz), ptr(x2), ptr(dw1), ptr(db1), T, J, K, 0, stream,
+                     tag=(T, J, K))
+        dx = (dz @ w1).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        return dx, dw1, db1, dw2, None, None
+
+
+def mlp_supported(x, fc1, fc2):
+    """Whether ``mlp_core`` covers this MLP: TF32 GEMMs enabled, training, and every shape inside the fused kernels."""
+    if not (_FUSED_MLP and _CUSTOM_WGRAD and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
+            and torch.backends.cuda.matmul.allow_tf32 and fc1.bias is not None):
+        return False
+    w1, w2 = fc1.weight, fc2.weight
+    if not (w1.requires_grad and w2.requires_grad and fc1.bias.requires_grad and w1.is_contiguous() and w2.is_contiguous()):
+        return False
+    T, K = x.numel() // x.shape[-1], x.shape[-1]
+    J, Cout = w1.shape[0], w2.shape[0]
+    return bool(lib.hs_mlp_dgrad_gelu_supported(T, Cout, J) and lib.hs_linear_wgrad_supported(T, Cout, J)
+                and lib.hs_linear_wgrad_supported(T, J, K) == 2)
+
+
+def mlp_core(x, fc1, fc2, drop=0.0, seed=None):
+    """``F.linear(dropout(GELU(fc1(x))), fc2.weight)`` (no fc2 bias) through the fused node; check ``mlp_supported``."""
+    drop = float(drop)
+    if drop > 0.0 and seed is None:
+        seed = _next_dropout_seed()
+    return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0))
+
+
 def linear(x, weight, bias=None):
     """``F.linear``.  When TF32 matmuls are enabled and the shape is covered, the weight gradient uses the hand-written
     kernel; everything else is the library GEMM."""

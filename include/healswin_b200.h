@@ -182,6 +182,20 @@ int hs_linear_wgrad_supported(int64_t T, int N, int K);
 int hs_linear_wgrad(const float* dy_dev, const float* x_dev, float* dw_dev, float* dbias_dev, int64_t T, int N, int K,
                     uint32_t flags, void* stream);
 
+/*
+ * Input gradient of the MLP's second half, fused (autograd of fc2(drop(GELU(fc1(x) + b1))) w.r.t. the fc1 output z,
+ * swin_hp_transformer.py:21-44):
+ *     dz[t][j] = (sum_c dy[t][c] * w2[c][j]) * GELU'(z[t][j] + b1[j]) * mask(seed, t, j)
+ * dy: (T, C) gradient of the fc2 output, w2: (C, J) = fc2.weight, z: (T, J) fc1 output without bias, b1: (J) or NULL,
+ * dz: (T, J); all fp32 row-major.  The (T, J) hidden gradient dy @ w2 lives only in tensor memory: this replaces the
+ * fc2 input-gradient GEMM followed by hs_bias_gelu_bwd.  drop / seed: the mask hs_bias_gelu_fwd used.  TF32 tensor
+ * cores.  hs_mlp_dgrad_gelu_supported returns 1 for covered shapes (C a multiple of 32 and <= 192, J a multiple of 128,
+ * T >= 1024).  flags: HS_ATTN_NO_TRUNC_COMP only.
+ */
+int hs_mlp_dgrad_gelu_supported(int64_t T, int C, int J);
+int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_dev, const float* b1_dev, float drop,
+                      uint64_t seed, float* dz_dev, int64_t T, int C, int J, uint32_t flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
