@@ -311,6 +311,8 @@ def run_ours(a):
             return tag[0] * tag[1] * 4 * 2
         if name == "bias_gelu_bwd":    # dh, z in, dz out
             return tag[0] * tag[1] * 4 * 3
+        if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
+            return tag[0] * (tag[1] + 2 * tag[2]) * 4
         return None
 
     families = {}

@@ -6,16 +6,13 @@
 // Thread layout: a thread owns one float4 column group for the whole kernel (so its d(bias) partial sums stay in
 // registers); a block covers blockDim / (C/4) consecutive rows per iteration.
 #include "hs_common.h"
+#include "hs_gelu.cuh"
 
 namespace {
 
-constexpr float kInvSqrt2 = 0.70710678118654752440f;
-constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
 
-__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.0f + erff(u * kInvSqrt2)); }
-__device__ __forceinline__ float gelu_grad_f(float u) {
-  return 0.5f * (1.0f + erff(u * kInvSqrt2)) + u * kInvSqrt2Pi * __expf(-0.5f * u * u);
-}
+__device__ __forceinline__ float gelu_f(float u) { return hs::gelu_fast(u); }
+__device__ __forceinline__ float gelu_grad_f(float u) { return hs::gelu_grad_fast(u); }
 
 struct Drop {
   uint32_t thresh;  // 0 = off

@@ -11,6 +11,7 @@
 //               two TMEM stages and a ring of slab buffers overlap all of it with the next tile's loads and MMAs
 // Warps: 0-15 epilogue (group = warp / 4, TMEM lane quadrant = warp % 4), 16 dy producer, 17 MMA issuer, 18 z producer.
 #include "hs_common.h"
+#include "hs_gelu.cuh"
 #include "hs_sm100.cuh"
 #include "hs_tc_common.cuh"
 
@@ -25,8 +26,6 @@ constexpr int kMaxSlabs = 8;             // z / dz slab buffers (upper bound)
 constexpr int kSub = kBM * 128;          // bytes of one 32-column x 128-row tile (K-major sub-tile, z slab, dz slab)
 constexpr int kEpiWarps = 16;
 constexpr int kThreads = (kEpiWarps + 3) * 32;
-constexpr float kInvSqrt2 = 0.70710678118654752440f;
-constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
 
 struct MdArgs {
   const float* b1;  // (J) or null
@@ -41,9 +40,7 @@ struct MdArgs {
   uint64_t seed;
 };
 
-__device__ __forceinline__ float gelu_grad_f(float u) {
-  return 0.5f * (1.0f + erff(u * kInvSqrt2)) + u * kInvSqrt2Pi * __expf(-0.5f * u * u);
-}
+__device__ __forceinline__ float gelu_grad_f(float u) { return hs::gelu_grad_fast(u); }
 
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_dgrad_gelu_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_w,
