@@ -60,19 +60,23 @@ class Mlp(nn.Module):
         return self.drop.p if self.training else 0.0
 
     def forward_split(self, x):
-        """(fc2 output WITHOUT its bias and WITHOUT the trailing dropout, that bias or None, that dropout's p): the
-        caller applies both (fused into the LayerNorm that follows in the v2 placement).  fc1's bias add, the GELU, the
-        first dropout and (backward) fc1's bias gradient are one kernel."""
+        """(fc2 output WITHOUT its bias and WITHOUT the trailing dropout, that bias or None, that dropout's p, the input
+        as residual shortcut): the caller applies bias and dropout (fused into the LayerNorm that follows in the v2
+        placement) and adds the shortcut, whose gradient is folded into fc1's input-gradient GEMM.  fc1's bias add, the
+        GELU, the first dropout and (backward) fc1's bias gradient are one kernel."""
         if not self._fusable() or self.fc2.bias is None:
-            return self.forward(x), None, 0.0
-        return self._core(x), self.fc2.bias, self._drop_p()
+            return self.forward(x), None, 0.0, x
+        y, shortcut = self._core(x, fork=True)
+        return y, self.fc2.bias, self._drop_p(), shortcut
 
-    def _core(self, x):
+    def _core(self, x, fork=False):
         """fc2(drop(GELU(fc1(x)))) without fc2's bias: one fused autograd node when the shapes allow it."""
         if ops.mlp_supported(x, self.fc1, self.fc2):
-            return ops.mlp_core(x, self.fc1, self.fc2, drop=self._drop_p())
-        h = ops.bias_gelu(ops.linear(x, self.fc1.weight), self.fc1.bias, drop=self._drop_p())
-        return ops.linear(h, self.fc2.weight)
+            return ops.mlp_core(x, self.fc1, self.fc2, drop=self._drop_p(), fork=fork)
+        z = ops.linear(x, self.fc1.weight, fork=fork)
+        z, shortcut = z if fork else (z, None)
+        y = ops.linear(ops.bias_gelu(z, self.fc1.bias, drop=self._drop_p()), self.fc2.weight)
+        return (y, shortcut) if fork else y
 
     def forward(self, x):
         if not self._fusable():
@@ -131,12 +135,14 @@ class WindowAttention(nn.Module):
 
     def forward_tokens_split(self, x, window_size, src=None, groups=None):
         """As forward_tokens, but returns (proj output WITHOUT its bias and WITHOUT proj_drop, that bias or None, the
-        dropout probability still to be applied) so that the caller can fuse both into the LayerNorm that follows (v2
-        norm placement)."""
+        dropout probability still to be applied, the input as residual shortcut) so that the caller can fuse bias and
+        dropout into the LayerNorm that follows (v2 norm placement); the shortcut's gradient is folded into the qkv
+        input-gradient GEMM."""
         if self.proj.bias is None:
-            return self.forward_tokens(x, window_size, src, groups), None, 0.0
-        out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), window_size, src, groups, None)
-        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0)
+            return self.forward_tokens(x, window_size, src, groups), None, 0.0, x
+        qkv, shortcut = ops.linear(x, self.qkv.weight, self.qkv.bias, fork=True)
+        out = self._core(qkv, window_size, src, groups, None)
+        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0), shortcut
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:124-174]"""
@@ -211,7 +217,8 @@ class SwinTransformerBlock(nn.Module):
             x = ops.layer_norm(x, self.norm1)
         # shift + partition + W-MSA/SW-MSA + reverse + shift back, one kernel chain   [:319-330]
         if self.use_v2_norm_placement:
-            x, pre_bias, pdrop = self.attn.forward_tokens_split(x, self.window_size, self._hs_src, self._hs_groups)
+            x, pre_bias, pdrop, shortcut = self.attn.forward_tokens_split(x, self.window_size, self._hs_src,
+                                                                          self._hs_groups)
         else:
             x, pre_bias, pdrop = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups), None, 0.0
         return _residual_tail(self, shortcut, x, pre_bias, pdrop)
@@ -230,7 +237,7 @@ def _residual_tail(blk, shortcut, x, pre_bias=None, pre_drop=0.0):
     scale_of = (lambda t: dp.sample_scale(t)) if isinstance(dp, DropPath) else (lambda t: None)
     if blk.use_v2_norm_placement:
         x = ops.layer_norm(x, blk.norm1, residual=shortcut, pre_bias=pre_bias, row_scale=scale_of(x), in_drop=pre_drop)
-        h, hb, hdrop = blk.mlp.forward_split(x)
+        h, hb, hdrop, x = blk.mlp.forward_split(x)
         return ops.layer_norm(h, blk.norm2, residual=x, pre_bias=hb, row_scale=scale_of(x), in_drop=hdrop)
     x = shortcut + dp(x)
     return x + dp(blk.mlp(ops.layer_norm(x, blk.norm2)))

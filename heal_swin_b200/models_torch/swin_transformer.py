@@ -142,12 +142,14 @@ class WindowAttention(nn.Module):
         return self.proj_drop(ops.linear(out, self.proj.weight, self.proj.bias))
 
     def forward_tokens_split(self, x, n_tokens, src=None, groups=None):
-        """(proj output WITHOUT its bias and proj_drop, that bias or None, the dropout p still to apply): both are fused
-        into the following LayerNorm."""
+        """(proj output WITHOUT its bias and proj_drop, that bias or None, the dropout p still to apply, the input as
+        residual shortcut): bias and dropout are fused into the following LayerNorm, the shortcut's gradient into the qkv
+        input-gradient GEMM."""
         if self.proj.bias is None:
-            return self.forward_tokens(x, n_tokens, src, groups), None, 0.0
-        out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), n_tokens, src, groups, None)
-        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0)
+            return self.forward_tokens(x, n_tokens, src, groups), None, 0.0, x
+        qkv, shortcut = ops.linear(x, self.qkv.weight, self.qkv.bias, fork=True)
+        out = self._core(qkv, n_tokens, src, groups, None)
+        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0), shortcut
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:148-202]"""
@@ -225,7 +227,7 @@ class SwinTransformerBlock(nn.Module):
             x = ops.layer_norm(x, self.norm1)
         n_tok = self.window_size[0] * self.window_size[1]
         if self.use_v2_norm_placement:
-            x, pre_bias, pdrop = self.attn.forward_tokens_split(x, n_tok, self._hs_src, self._hs_groups)
+            x, pre_bias, pdrop, shortcut = self.attn.forward_tokens_split(x, n_tok, self._hs_src, self._hs_groups)
         else:
             x, pre_bias, pdrop = self.attn.forward_tokens(x, n_tok, self._hs_src, self._hs_groups), None, 0.0
         if self.fixup is not None:

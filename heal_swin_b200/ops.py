@@ -304,22 +304,28 @@ _CUSTOM_WGRAD = os.environ.get("HEALSWIN_CUSTOM_WGRAD", "1") == "1"
 class _LinearFn(torch.autograd.Function):
     """F.linear whose weight gradient dW = dY^T X runs on the hand-written token-split tcgen05 kernel
     (csrc/hs_wgrad_tc.cu); forward and input gradient stay library GEMMs (they already sit on the HBM roofline at the
-    large stages, scripts/wgrad_check.py)."""
+    large stages, scripts/wgrad_check.py).  With ``fork`` the input is returned as a second output -- the shortcut of a
+    residual block whose branch starts with this linear -- and the shortcut's gradient is folded into the input-gradient
+    GEMM (beta = 1) instead of a separate accumulation pass over the activation."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, fork):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return torch.nn.functional.linear(x, weight, bias)
+        ctx.set_materialize_grads(False)
+        y = torch.nn.functional.linear(x, weight, bias)
+        return (y, x.view_as(x)) if fork else y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, d_pass=None):
         x, weight = ctx.saved_tensors
         N, K = weight.shape
-        dy2 = _f32c(dy).reshape(-1, N)
         dx = dw = db = None
+        if dy is None:
+            return d_pass, None, None, None
+        dy2 = _f32c(dy).reshape(-1, N)
         if ctx.needs_input_grad[0]:
-            dx = (dy2 @ weight).view(x.shape)
+            dx = _dgrad(dy2, weight, d_pass, x.shape)
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
             x2 = _f32c(x).reshape(-1, K)
@@ -331,7 +337,26 @@ class _LinearFn(torch.autograd.Function):
                          current_stream(), tag=(T, N, K))
         if need_b and db is None:
             db = dy2.sum(0)
-        return dx, dw, db
+        return dx, dw, db, None
+
+
+_LT_WORKSPACE = {}
+
+
+def _dgrad(dy2, weight, d_pass, xshape):
+    """dy2 @ weight (+ the gradient that reached the forked shortcut output), shaped like the input.  With a shortcut
+    gradient the library GEMM reads it as its C operand and writes a fresh D (hs_linear_dgrad_acc): no accumulation pass."""
+    if d_pass is None:
+        return (dy2 @ weight).view(xshape)
+    c = _f32c(d_pass).reshape(-1, weight.shape[1])
+    ws = _LT_WORKSPACE.get(dy2.device)
+    if ws is None:
+        ws = _LT_WORKSPACE[dy2.device] = torch.empty(32 << 20, dtype=torch.uint8, device=dy2.device)
+    dx = torch.empty_like(c)
+    # a library GEMM, not one of this library's kernels: not counted in STATS
+    check(lib.hs_linear_dgrad_acc(ptr(dy2), ptr(weight), ptr(c), ptr(dx), dy2.shape[0], weight.shape[0], weight.shape[1],
+                                  ptr(ws), ws.numel(), current_stream()))
+    return dx.view(xshape)
 
 
 _FUSED_MLP = os.environ.get("HEALSWIN_FUSED_MLP", "1") == "1"
@@ -344,7 +369,8 @@ class _MlpFn(torch.autograd.Function):
     forward GEMMs and the final input gradient are library GEMMs."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, drop, seed):
+    def forward(ctx, x, w1, b1, w2, drop, seed, fork):
+        ctx.set_materialize_grads(False)
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
         T, J = x2.shape[0], w1.shape[0]
@@ -356,10 +382,13 @@ class _MlpFn(torch.autograd.Function):
         ctx.save_for_backward(x2, w1, b1, w2, z, h)
         ctx.drop = (float(drop), int(seed))
         ctx.xshape = x.shape
-        return y.view(*x.shape[:-1], w2.shape[0])
+        y = y.view(*x.shape[:-1], w2.shape[0])
+        return (y, x.view_as(x)) if fork else y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, d_pass=None):
+        if dy is None:
+            return d_pass, None, None, None, None, None, None
         x2, w1, b1, w2, z, h = ctx.saved_tensors
         T, K = x2.shape
         J, Cout = w1.shape[0], w2.shape[0]
@@ -375,8 +404,8 @@ class _MlpFn(torch.autograd.Function):
         db1 = torch.zeros((J,), device=x2.device, dtype=torch.float32)
         STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dz), ptr(x2), ptr(dw1), ptr(db1), T, J, K, 0, stream,
                      tag=(T, J, K))
-        dx = (dz @ w1).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        return dx, dw1, db1, dw2, None, None
+        dx = _dgrad(dz, w1, d_pass, ctx.xshape) if ctx.needs_input_grad[0] else None
+        return dx, dw1, db1, dw2, None, None, None
 
 
 def mlp_supported(x, fc1, fc2):
@@ -393,19 +422,23 @@ def mlp_supported(x, fc1, fc2):
                 and lib.hs_linear_wgrad_supported(T, J, K) == 2)
 
 
-def mlp_core(x, fc1, fc2, drop=0.0, seed=None):
-    """``F.linear(dropout(GELU(fc1(x))), fc2.weight)`` (no fc2 bias) through the fused node; check ``mlp_supported``."""
+def mlp_core(x, fc1, fc2, drop=0.0, seed=None, fork=False):
+    """``F.linear(dropout(GELU(fc1(x))), fc2.weight)`` (no fc2 bias) through the fused node; check ``mlp_supported``.
+    ``fork``: also return the input as the residual shortcut (see ``linear``)."""
     drop = float(drop)
     if drop > 0.0 and seed is None:
         seed = _next_dropout_seed()
-    return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0))
+    return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0), bool(fork))
 
 
-def linear(x, weight, bias=None):
+def linear(x, weight, bias=None, fork=False):
     """``F.linear``.  When TF32 matmuls are enabled and the shape is covered, the weight gradient uses the hand-written
-    kernel; everything else is the library GEMM."""
+    kernel; everything else is the library GEMM.  ``fork=True`` returns ``(y, shortcut)`` where ``shortcut`` is ``x`` for
+    the residual path of a block whose branch starts with this linear: on the custom path its gradient is added inside
+    the input-gradient GEMM."""
     if (_CUSTOM_WGRAD and x.is_cuda and x.dtype == torch.float32 and weight.requires_grad and torch.is_grad_enabled()
             and torch.backends.cuda.matmul.allow_tf32 and weight.dim() == 2 and weight.is_contiguous()
             and lib.hs_linear_wgrad_supported(x.numel() // x.shape[-1], weight.shape[0], weight.shape[1])):
-        return _LinearFn.apply(x, weight, bias)
-    return torch.nn.functional.linear(x, weight, bias)
+        return _LinearFn.apply(x, weight, bias, bool(fork))
+    y = torch.nn.functional.linear(x, weight, bias)
+    return (y, x) if fork else y

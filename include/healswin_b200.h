@@ -196,6 +196,17 @@ int hs_mlp_dgrad_gelu_supported(int64_t T, int C, int J);
 int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_dev, const float* b1_dev, float drop,
                       uint64_t seed, float* dz_dev, int64_t T, int C, int J, uint32_t flags, void* stream);
 
+/*
+ * Input gradient of nn.Linear with the gradient of a residual shortcut folded in (autograd of x + branch(x) where the
+ * branch starts with a Linear: swin_hp_transformer.py:131 / 21-44 inside :333-338):
+ *     dx[t][k] = sum_n dy[t][n] * w[n][k] + c[t][k]        dy: (T, N), w: (N, K), c and dx: (T, K), fp32 row-major
+ * c may be NULL (plain dgrad) or equal to dx (in place).  Library GEMM (cuBLASLt, TF32 tensor cores, out-of-place C/D):
+ * the only point of this entry is that c is read by the GEMM epilogue instead of a separate accumulation pass.
+ * workspace: device scratch for the library (may be NULL / 0).  cuBLASLt is loaded with dlopen at first use.
+ */
+int hs_linear_dgrad_acc(const float* dy_dev, const float* w_dev, const float* c_dev, float* dx_dev, int64_t T, int N, int K,
+                        void* workspace_dev, uint64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,9 +49,11 @@ def main():
     print(f"GPU kernel time per step (sum of durations under the profiler): {busy:.1f} ms over {len(ev) // 2} launches")
     agg = {}
     for e in ev:
-        agg[e.name[:60]] = agg.get(e.name[:60], 0.0) + e.device_time / 1e3 / 2
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:12]:
-        print(f"  {v:7.2f} ms  {k}")
+        k = e.name.replace("(anonymous namespace)::", "").replace("at::native::", "")[:110]
+        t, n = agg.get(k, (0.0, 0))
+        agg[k] = (t + e.device_time / 1e3 / 2, n + 1)
+    for k, (v, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:32]:
+        print(f"  {v:7.2f} ms  x{n // 2:<4d} {k}")
 
 
 if __name__ == "__main__":

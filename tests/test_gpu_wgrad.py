@@ -88,6 +88,60 @@ def test_linear_autograd_uses_the_kernel_under_tf32_and_matches():
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
+@pytest.mark.parametrize("T,N,K", [(8192, 288, 96), (5001, 384, 96), (4096, 96, 384), (777, 1536, 384)])
+def test_dgrad_acc_library_gemm(T, N, K):
+    """hs_linear_dgrad_acc: dx = dy @ W + c out of place, with c == NULL, and in place (c == dx)."""
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T + N)
+    dy = torch.randn(T, N, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) / N ** 0.5).to(dev)
+    c = torch.randn(T, K, generator=g).to(dev)
+    ws = torch.empty(32 << 20, dtype=torch.uint8, device=dev)
+    want = dy.double() @ w.double()
+    dx = torch.full((T, K), float("nan"), device=dev)
+    c0 = c.clone()
+    check(lib.hs_linear_dgrad_acc(ptr(dy), ptr(w), ptr(c), ptr(dx), T, N, K, ptr(ws), ws.numel(), current_stream()))
+    assert torch.equal(c, c0)  # the shortcut gradient is only read
+    assert rel_err(dx.cpu(), (want + c.double()).float().cpu()) < TOL
+    check(lib.hs_linear_dgrad_acc(ptr(dy), ptr(w), None, ptr(dx), T, N, K, None, 0, current_stream()))
+    assert rel_err(dx.cpu(), want.float().cpu()) < TOL
+    check(lib.hs_linear_dgrad_acc(ptr(dy), ptr(w), ptr(c), ptr(c), T, N, K, ptr(ws), ws.numel(), current_stream()))
+    assert rel_err(c.cpu(), (want + c0.double()).float().cpu()) < TOL
+
+
+def test_forked_linear_folds_the_shortcut_gradient_into_the_dgrad():
+    """ops.linear(..., fork=True) returns (y, shortcut): gradients must equal those of using x twice."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(2, 4096, 96, generator=g).to(dev).requires_grad_(True)
+        lin = torch.nn.Linear(96, 288).to(dev)
+        wy = torch.randn(2, 4096, 288, generator=g).to(dev)
+        ws = torch.randn(2, 4096, 96, generator=g).to(dev)
+        y, shortcut = ops.linear(x, lin.weight, lin.bias, fork=True)
+        assert shortcut.data_ptr() == x.data_ptr() and shortcut.grad_fn is y.grad_fn
+        ((y * wy).sum() + (shortcut * ws).sum()).backward()
+        got = (lin.weight.grad.clone(), lin.bias.grad.clone(), x.grad.clone())
+        lin.weight.grad = lin.bias.grad = x.grad = None
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ((torch.nn.functional.linear(x, lin.weight, lin.bias) * wy).sum() + (x * ws).sum()).backward()
+        for a, b in zip(got, (lin.weight.grad, lin.bias.grad, x.grad)):
+            assert rel_err(a.cpu(), b.cpu()) < TOL
+        # only one of the two outputs used
+        x.grad = None
+        y, shortcut = ops.linear(x, lin.weight, lin.bias, fork=True)
+        (shortcut * ws).sum().backward()
+        assert torch.equal(x.grad, ws)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def test_wgrad_full_size_linearity():
     """BASELINE stage-0 token count (8 x 196608): dW is linear in dY (size-independent property)."""
     dev = torch.device("cuda:0")
