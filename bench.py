@@ -311,6 +311,10 @@ def run_ours(a):
             return tag[0] * tag[1] * 4 * 2
         if name == "bias_gelu_bwd":    # dh, z in, dz out
             return tag[0] * tag[1] * 4 * 3
+        if name == "ln_head_fwd":      # x (rows, C) in, logits (rows, K) + mean, rstd out
+            return tag[0] * (tag[1] + tag[2] + 2) * 4
+        if name == "ln_head_bwd":      # x, dlogits, mean, rstd in, dx out
+            return tag[0] * (2 * tag[1] + tag[2] + 2) * 4
         if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
             return tag[0] * (tag[1] + 2 * tag[2]) * 4
         return None

@@ -43,6 +43,10 @@ SIGNATURES = {
     "hs_mlp_dgrad_gelu_supported": [_i64, _i, _i],
     "hs_mlp_dgrad_gelu": [_p, _p, _p, _p, _f, _u64, _p, _i64, _i, _i, _u32, _p],
     "hs_linear_dgrad_acc": [_p, _p, _p, _p, _i64, _i, _i, _p, _u64, _p],
+    "hs_linear_fwd": [_p, _p, _p, _p, _i64, _i, _i, _p, _u64, _p],
+    "hs_ln_head_supported": [_i64, _i, _i],
+    "hs_ln_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _f, _p],
+    "hs_ln_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],
     "hs_bias_gelu_fwd": [_p, _p, _f, _u64, _p, _i64, _i, _p],
     "hs_bias_gelu_bwd": [_p, _p, _p, _f, _u64, _p, _p, _i64, _i, _p],
     "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _f, _u64, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],

@@ -299,10 +299,14 @@ class FinalPatchExpand_X4(nn.Module):
         self.output_dim = dim
         self.norm = norm_layer(self.output_dim)
 
-    def forward(self, x):
+    def forward_pre_norm(self, x):
+        """The expanded tokens before ``self.norm`` (the decoder fuses that LayerNorm with the output projection)."""
         x = ops.linear(x, self.expand.weight, self.expand.bias)
         B, N, C = x.shape
-        return ops.layer_norm(x.contiguous().view(B, N * self.patch_size, C // self.patch_size), self.norm)
+        return x.contiguous().view(B, N * self.patch_size, C // self.patch_size)
+
+    def forward(self, x):
+        return ops.layer_norm(self.forward_pre_norm(x), self.norm)
 
 
 def _make_blocks(dim, input_resolution, depth, num_heads, window_size, base_pix, shift_size, shift_strategy,
@@ -437,11 +441,10 @@ class UnetDecoder(nn.Module):
                 x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
                 x = ops.linear(x, self.concat_back_dim[inx].weight, self.concat_back_dim[inx].bias)
             x = layer_up(x)
-        x = self.up(ops.layer_norm(x, self.norm_up))
-        # Conv1d(kernel 1, no bias) over channels == Linear on the token-major tensor: the (B, N_pix, C) activation is
-        # never transposed, only the f_out-channel result is
-        y = ops.linear(x, self.output.weight[:, :, 0])
-        return y.permute(0, 2, 1).contiguous()
+        x = self.up.forward_pre_norm(ops.layer_norm(x, self.norm_up))
+        # up.norm + Conv1d(kernel 1) over channels in one pass: the normalised (B, N_pix, C) activation is never written,
+        # the f_out-channel result comes out directly as (B, f_out, N_pix)
+        return ops.ln_head(x, self.up.norm, self.output.weight[:, :, 0], self.output.bias)
 
 
 @dataclass

@@ -311,14 +311,17 @@ class FinalPatchExpand_X4(nn.Module):
         self.norm = norm_layer(self.output_dim)
         self.shuffle = _RowTable(_pixel_shuffle_table(input_resolution[0], input_resolution[1], patch_size[0], patch_size[1]))
 
-    def forward(self, x):
+    def forward_pre_norm(self, x):
+        """The pixel-shuffled tokens before ``self.norm`` (the decoder fuses that LayerNorm with the output projection)."""
         H, W = self.input_resolution
         x = ops.linear(x, self.expand.weight, self.expand.bias)
         B, L, C = x.shape
         assert L == H * W, "input feature has wrong size"
         pp = self.patch_size[0] * self.patch_size[1]
-        x = self.shuffle(x.contiguous().view(B, L * pp, C // pp))
-        return ops.layer_norm(x, self.norm)
+        return self.shuffle(x.contiguous().view(B, L * pp, C // pp))
+
+    def forward(self, x):
+        return ops.layer_norm(self.forward_pre_norm(x), self.norm)
 
 
 def _make_blocks(dim, input_resolution, depth, num_heads, window_size, shift_size, mlp_ratio, qkv_bias, qk_scale, drop,
@@ -553,10 +556,9 @@ class SwinTransformerSys(nn.Module):
         B, L, C = x.shape
         assert L == H * W, "input features has wrong size"
         if self.config.final_upsample == "expand_first":
-            x = self.up(x)
-            # 1x1 Conv2d (no bias) == Linear over channels on the token-major tensor; only the result is transposed
-            y = ops.linear(x, self.output.weight[:, :, 0, 0])
-            x = y.view(B, self.config.patch_size[0] * H, self.config.patch_size[1] * W, -1).permute(0, 3, 1, 2).contiguous()
+            # up.norm + 1x1 Conv2d over channels in one pass; the result comes out channel-first, rows in raster order
+            y = ops.ln_head(self.up.forward_pre_norm(x), self.up.norm, self.output.weight[:, :, 0, 0], self.output.bias)
+            x = y.view(B, -1, self.config.patch_size[0] * H, self.config.patch_size[1] * W)
         return x
 
     def forward(self, x):

@@ -251,6 +251,51 @@ def layer_norm(x, norm, residual=None, pre_bias=None, row_scale=None, in_drop=0.
     return y if residual is None else residual + y
 
 
+class LnHeadFn(torch.autograd.Function):
+    """logits (B, K, P) = Conv1d_1x1(LayerNorm(x (B, P, C))) in one pass, csrc/hs_ln_head.cu; the backward is one pass too
+    and never materialises the normalised activation or its gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w, hbias, eps):
+        require_cuda(x, gamma, beta, w)
+        B, P, Cc = x.shape
+        K = w.shape[0]
+        x2 = _f32c(x).reshape(B * P, Cc)
+        gamma, beta, w, hbias = _f32c(gamma), _f32c(beta), _f32c(w), _f32c(hbias)
+        logits = torch.empty((B, K, P), device=x.device, dtype=torch.float32)
+        mean = torch.empty((B * P,), device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        STATS.launch("ln_head_fwd", lib.hs_ln_head_fwd, ptr(x2), ptr(gamma), ptr(beta), ptr(w), ptr(hbias), ptr(logits),
+                     ptr(mean), ptr(rstd), B * P, P, Cc, K, C.c_float(eps), current_stream(), tag=(B * P, Cc, K))
+        ctx.save_for_backward(x2, gamma, beta, w, mean, rstd)
+        ctx.meta = (B, P, Cc, K, hbias is not None)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        x2, gamma, beta, w, mean, rstd = ctx.saved_tensors
+        B, P, Cc, K, has_bias = ctx.meta
+        dl = _f32c(dlogits)
+        dx = torch.empty_like(x2)
+        s_acc = torch.zeros((K, Cc), device=x2.device, dtype=torch.float32)
+        g_acc = torch.zeros((K,), device=x2.device, dtype=torch.float32)
+        STATS.launch("ln_head_bwd", lib.hs_ln_head_bwd, ptr(dl), ptr(x2), ptr(mean), ptr(rstd), ptr(gamma), ptr(w), ptr(dx),
+                     ptr(s_acc), ptr(g_acc), B * P, P, Cc, K, current_stream(), tag=(B * P, Cc, K))
+        dw = gamma * s_acc + beta * g_acc[:, None]
+        dgamma = (w * s_acc).sum(0)
+        dbeta = (w * g_acc[:, None]).sum(0)
+        return dx.view(B, P, Cc), dgamma, dbeta, dw, (g_acc if has_bias else None), None
+
+
+def ln_head(x, norm, weight, bias=None):
+    """``Conv1d_1x1(norm(x).transpose(1, 2))`` for x (B, P, C) and ``weight`` (K, C): logits (B, K, P).  One fused launch
+    when ``norm`` is an affine LayerNorm over C and the shape is covered, else LayerNorm + linear + transpose."""
+    if (x.is_cuda and x.dim() == 3 and _fusable_norm(norm, x)
+            and lib.hs_ln_head_supported(x.shape[0] * x.shape[1], x.shape[2], weight.shape[0])):
+        return LnHeadFn.apply(x, norm.weight, norm.bias, weight, bias, float(norm.eps))
+    return linear(layer_norm(x, norm), weight, bias).permute(0, 2, 1).contiguous()
+
+
 class BiasGeluFn(torch.autograd.Function):
     """h = dropout(GELU(z + bias)) (exact erf GELU), csrc/hs_bias_gelu.cu; backward also yields d(bias)."""
 

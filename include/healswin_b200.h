@@ -207,6 +207,34 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
 int hs_linear_dgrad_acc(const float* dy_dev, const float* w_dev, const float* c_dev, float* dx_dev, int64_t T, int N, int K,
                         void* workspace_dev, uint64_t workspace_bytes, void* stream);
 
+/*
+ * Forward of nn.Linear as a library GEMM (cuBLASLt, TF32 tensor cores, bias in the epilogue):
+ *     y[t][n] = sum_k x[t][k] * w[n][k] + bias[n]          x: (T, K), w: (N, K), bias: (N) or NULL, y: (T, N)
+ * Same plumbing as hs_linear_dgrad_acc; exists because the heuristic-selected cuBLASLt algorithm (with workspace) is
+ * faster than the cuBLAS default for the tall-skinny shapes of this network (scripts/gemm_lt_check.py).
+ */
+int hs_linear_fwd(const float* x_dev, const float* w_dev, const float* bias_dev, float* y_dev, int64_t T, int N, int K,
+                  void* workspace_dev, uint64_t workspace_bytes, void* stream);
+
+/*
+ * Decoder tail, fused: logits = Conv1d_1x1(LayerNorm(x)) (FinalPatchExpand_X4.norm + SwinHPTransformerSys.output,
+ * swin_hp_transformer.py:450, 781-786, 945) in one pass, and its backward in one pass.
+ *   x: (rows, C) fp32 with rows = B * rows_per_sample; gamma, beta: (C); w: (K, C) = output.weight[:, :, 0];
+ *   head_bias: (K) or NULL; logits / dlogits: (B, K, rows_per_sample) -- the layout of the reference's network output;
+ *   mean, rstd: (rows) LayerNorm statistics, written by the forward and read by the backward.
+ * Backward writes dx (rows, C) and ACCUMULATES  s_acc[k][c] += sum_rows dlogits[row][k] * xhat[row][c]  (K, C) and
+ * g_acc[k] += sum_rows dlogits[row][k]  (K) (zero them first), from which
+ *   d(w) = gamma * s_acc + beta * g_acc,  d(gamma) = sum_k w * s_acc,  d(beta) = sum_k w * g_acc,  d(head_bias) = g_acc.
+ * hs_ln_head_supported: 1 for C in {32, 64, 96} and 1 <= K <= 16.
+ */
+int hs_ln_head_supported(int64_t rows, int C, int K);
+int hs_ln_head_fwd(const float* x_dev, const float* gamma_dev, const float* beta_dev, const float* w_dev,
+                   const float* head_bias_dev, float* logits_dev, float* mean_dev, float* rstd_dev, int64_t rows,
+                   int64_t rows_per_sample, int C, int K, float eps, void* stream);
+int hs_ln_head_bwd(const float* dlogits_dev, const float* x_dev, const float* mean_dev, const float* rstd_dev,
+                   const float* gamma_dev, const float* w_dev, float* dx_dev, float* s_acc_dev, float* g_acc_dev,
+                   int64_t rows, int64_t rows_per_sample, int C, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
