@@ -358,7 +358,7 @@ class _LinearFn(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
         ctx.set_materialize_grads(False)
-        y = torch.nn.functional.linear(x, weight, bias)
+        y = _gemm_fwd(_f32c(x).reshape(-1, weight.shape[1]), weight, _f32c(bias)).view(*x.shape[:-1], weight.shape[0])
         return (y, x.view_as(x)) if fork else y
 
     @staticmethod
@@ -386,18 +386,37 @@ class _LinearFn(torch.autograd.Function):
 
 
 _LT_WORKSPACE = {}
+_LT_GEMM = os.environ.get("HEALSWIN_LT_GEMM", "1") == "1"
+
+
+def _lt_workspace(device):
+    ws = _LT_WORKSPACE.get(device)
+    if ws is None:
+        ws = _LT_WORKSPACE[device] = torch.empty(32 << 20, dtype=torch.uint8, device=device)
+    return ws
+
+
+def _gemm_fwd(x2, weight, bias):
+    """x2 (T, K) @ weight (N, K)^T + bias as a library GEMM.  On the custom (TF32) path it is the cuBLASLt heuristic pick
+    with a workspace (hs_linear_fwd): same arithmetic as torch's cuBLAS call, measurably faster for several of this
+    network's tall-skinny shapes (scripts/gemm_lt_check.py).  A library GEMM: not counted in STATS."""
+    if not _LT_GEMM:
+        return torch.nn.functional.linear(x2, weight, bias)
+    y = torch.empty((x2.shape[0], weight.shape[0]), device=x2.device, dtype=torch.float32)
+    ws = _lt_workspace(x2.device)
+    check(lib.hs_linear_fwd(ptr(x2), ptr(weight), ptr(bias), ptr(y), x2.shape[0], weight.shape[0], weight.shape[1],
+                            ptr(ws), ws.numel(), current_stream()))
+    return y
 
 
 def _dgrad(dy2, weight, d_pass, xshape):
     """dy2 @ weight (+ the gradient that reached the forked shortcut output), shaped like the input.  With a shortcut
     gradient the library GEMM reads it as its C operand and writes a fresh D (hs_linear_dgrad_acc): no accumulation pass."""
-    if d_pass is None:
+    if d_pass is None and not _LT_GEMM:
         return (dy2 @ weight).view(xshape)
-    c = _f32c(d_pass).reshape(-1, weight.shape[1])
-    ws = _LT_WORKSPACE.get(dy2.device)
-    if ws is None:
-        ws = _LT_WORKSPACE[dy2.device] = torch.empty(32 << 20, dtype=torch.uint8, device=dy2.device)
-    dx = torch.empty_like(c)
+    c = None if d_pass is None else _f32c(d_pass).reshape(-1, weight.shape[1])
+    ws = _lt_workspace(dy2.device)
+    dx = torch.empty((dy2.shape[0], weight.shape[1]), device=dy2.device, dtype=torch.float32)
     # a library GEMM, not one of this library's kernels: not counted in STATS
     check(lib.hs_linear_dgrad_acc(ptr(dy2), ptr(weight), ptr(c), ptr(dx), dy2.shape[0], weight.shape[0], weight.shape[1],
                                   ptr(ws), ws.numel(), current_stream()))
@@ -419,11 +438,11 @@ class _MlpFn(torch.autograd.Function):
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
         T, J = x2.shape[0], w1.shape[0]
-        z = x2 @ w1.t()
+        z = _gemm_fwd(x2, w1, None)
         h = torch.empty_like(z)
         STATS.launch("bias_gelu_fwd", lib.hs_bias_gelu_fwd, ptr(z), ptr(b1), C.c_float(drop), C.c_uint64(seed), ptr(h),
                      T, J, current_stream(), tag=(T, J))
-        y = h @ w2.t()
+        y = _gemm_fwd(h, w2, None)
         ctx.save_for_backward(x2, w1, b1, w2, z, h)
         ctx.drop = (float(drop), int(seed))
         ctx.xshape = x.shape
