@@ -98,9 +98,27 @@ ln_head_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamm
   const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const long long stride = (long long)gridDim.x * (kThreads / 32) * (4 * R);
   const long long iters = (rows + stride - 1) / stride;
+  // software pipeline: the rows of iteration it + 1 are requested before those of iteration it are processed (16 warps
+  // per SM do not hide the HBM latency of a load-then-compute loop: ncu showed long-scoreboard stalls first)
+  float4 nx[R][V];
+  auto fetch = [&](long long base) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = base + 4 * r + sub;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        nx[r][v] = row < rows ? __ldcs(x + row * C4 + t + kT * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(warp0 * (4 * R));
   for (long long it = 0; it < iters; ++it) {
     const long long base = warp0 * (4 * R) + it * stride;
     float4 a[R][V];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int v = 0; v < V; ++v) a[r][v] = nx[r][v];
+    if (it + 1 < iters) fetch(base + stride);
     float rs[R], acc[R][KP];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -108,10 +126,7 @@ ln_head_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamm
       const bool ok = row < rows;
       float s = 0.f;
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        a[r][v] = ok ? __ldcs(x + row * C4 + t + kT * v) : make_float4(0.f, 0.f, 0.f, 0.f);
-        s += (a[r][v].x + a[r][v].y) + (a[r][v].z + a[r][v].w);
-      }
+      for (int v = 0; v < V; ++v) s += (a[r][v].x + a[r][v].y) + (a[r][v].z + a[r][v].w);
       const float mu = group_sum8(s) * invC;
       float q = 0.f;
 #pragma unroll
@@ -154,24 +169,26 @@ ln_head_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamm
   }
 }
 
+constexpr int kThreadsB = 192;  // backward: 2 x 6 warps per SM leave 170 registers per thread for the prefetch
+
 template <int V, int KQ, int R>
-__global__ void __launch_bounds__(kThreads, (R == 1 ? 2 : 1))
+__global__ void __launch_bounds__(kThreadsB, (R == 1 ? 2 : 1))
 ln_head_bwd_kernel(const float* __restrict__ dlogits, const float4* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float4* __restrict__ gamma, const float* __restrict__ w,
                    float4* __restrict__ dx, float* __restrict__ s_acc, float* __restrict__ g_acc, long long rows,
                    long long P, int K) {
-  constexpr int KP = 4 * KQ, C4 = kT * V, C = 4 * C4, NR = 4 * R, kWarps = kThreads / 32;
+  constexpr int KP = 4 * KQ, C4 = kT * V, C = 4 * C4, NR = 4 * R, kWarps = kThreadsB / 32;
   __shared__ float4 ws[KP][C4];             // W, zero rows for k >= K
   __shared__ float4 xs[kWarps][NR][C4];     // xhat of the warp's rows
   __shared__ float4 g_rk[kWarps][NR][KQ];   // d(logits) [row][k]
   __shared__ float4 g_kr[kWarps][KP][R];    // d(logits) [k][row]
   __shared__ float red_s[KP * C];
   __shared__ float red_g[KP];
-  for (int i = threadIdx.x; i < KP * C4; i += kThreads) {
+  for (int i = threadIdx.x; i < KP * C4; i += kThreadsB) {
     const int k = i / C4, c4 = i - k * C4;
     ws[k][c4] = k < K ? __ldg(reinterpret_cast<const float4*>(w) + (size_t)k * C4 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int i = threadIdx.x; i < KP * C; i += kThreads) red_s[i] = 0.f;
+  for (int i = threadIdx.x; i < KP * C; i += kThreadsB) red_s[i] = 0.f;
   if (threadIdx.x < KP) red_g[threadIdx.x] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, t = lane & (kT - 1), sub = lane >> 3, wid = threadIdx.x >> 5;
@@ -193,32 +210,54 @@ ln_head_bwd_kernel(const float* __restrict__ dlogits, const float4* __restrict__
   const long long warp0 = (long long)blockIdx.x * kWarps + wid;
   const long long stride = (long long)gridDim.x * kWarps * NR;
   const long long iters = (rows + stride - 1) / stride;  // uniform trip count: see the forward kernel
+  // software pipeline (see the forward kernel): x, the statistics and d(logits) of iteration it + 1 are requested before
+  // iteration it is processed
+  float4 nx[R][V];
+  float nmu[R], nrs[R], ng[R][(KP + kT - 1) / kT];
+  auto fetch = [&](long long base) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = base + 4 * r + sub;
+      const bool ok = row < rows;
+      nmu[r] = ok ? __ldg(mean + row) : 0.f;
+      nrs[r] = ok ? __ldg(rstd + row) : 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) nx[r][v] = ok ? __ldcs(x + row * C4 + t + kT * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      long long b, p;
+      split_row(ok ? row : 0, P, small, b, p);
+      const float* gp = dlogits + (b * K) * P + p;
+#pragma unroll
+      for (int jj = 0; jj < (KP + kT - 1) / kT; ++jj) {  // lane t fetches classes t, t + 8
+        const int k = t + kT * jj;
+        ng[r][jj] = (ok && k < K) ? __ldcs(gp + (long long)k * P) : 0.f;
+      }
+    }
+  };
+  fetch(warp0 * NR);
   for (long long it = 0; it < iters; ++it) {
     const long long base = warp0 * NR + it * stride;
     float4 xh[R][V];
     float rs[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const long long row = base + 4 * r + sub;
-      const bool ok = row < rows;
-      const float mu = ok ? __ldg(mean + row) : 0.f;
-      rs[r] = ok ? __ldg(rstd + row) : 0.f;
+      const float mu = nmu[r];
+      rs[r] = nrs[r];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float4 xv = ok ? __ldcs(x + row * C4 + t + kT * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 xv = nx[r][v];
         xh[r][v] = make_float4((xv.x - mu) * rs[r], (xv.y - mu) * rs[r], (xv.z - mu) * rs[r], (xv.w - mu) * rs[r]);
         xs[wid][4 * r + sub][t + kT * v] = xh[r][v];
       }
-      long long b, p;
-      split_row(ok ? row : 0, P, small, b, p);
-      const float* gp = dlogits + (b * K) * P + p;
 #pragma unroll
-      for (int k = t; k < KP; k += kT) {  // lane t fetches classes t, t + 8
-        const float g = (ok && k < K) ? __ldcs(gp + (long long)k * P) : 0.f;
-        grk[(4 * r + sub) * KP + k] = g;
-        gkr[k * NR + 4 * r + sub] = g;
+      for (int jj = 0; jj < (KP + kT - 1) / kT; ++jj) {
+        const int k = t + kT * jj;
+        if (k < KP) {
+          grk[(4 * r + sub) * KP + k] = ng[r][jj];
+          gkr[k * NR + 4 * r + sub] = ng[r][jj];
+        }
       }
     }
+    if (it + 1 < iters) fetch(base + stride);
     __syncwarp();
     // d(LN output) of the own rows, LayerNorm backward, dx
 #pragma unroll
@@ -296,7 +335,7 @@ ln_head_bwd_kernel(const float* __restrict__ dlogits, const float4* __restrict__
     if (t == 0) atomicAdd(red_g + k, G[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < K * C; i += kThreads) atomicAdd(s_acc + i, red_s[i]);
+  for (int i = threadIdx.x; i < K * C; i += kThreadsB) atomicAdd(s_acc + i, red_s[i]);
   if (threadIdx.x < K) atomicAdd(g_acc + threadIdx.x, red_g[threadIdx.x]);
 }
 
@@ -312,7 +351,7 @@ int num_sms() {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-constexpr int kRF = 2;  // rows per lane and iteration, forward
+constexpr int kRF = 1;  // rows per lane and iteration, forward
 
 int bwd_rows_per_lane() {  // backward: 2 (255 registers, 8 warps / SM) or 1 (16 warps / SM); HS_LN_HEAD_RB overrides
   static int r = [] {
@@ -375,12 +414,12 @@ int hs_ln_head_bwd(const float* dlogits, const float* x, const float* mean, cons
   HS_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(w) && aligned16(dx),
              "hs_ln_head_bwd: x, gamma, w and dx must be 16-byte aligned");
   const int rb = bwd_rows_per_lane();
-  const long long per_block = (kThreads / 32) * 4 * rb;
+  const long long per_block = (kThreadsB / 32) * 4 * rb;
   long long blocks = (rows + per_block - 1) / per_block;
   const long long cap = (long long)num_sms() * (rb == 1 ? 2 : 1);
   if (blocks > cap) blocks = cap;
 #define HS_LH_BWD(R_)                                                                                                  \
-  HS_LH_DISPATCH((ln_head_bwd_kernel<V, KQ, R_><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(              \
+  HS_LH_DISPATCH((ln_head_bwd_kernel<V, KQ, R_><<<(unsigned)blocks, kThreadsB, 0, (cudaStream_t)stream>>>(              \
       dlogits, reinterpret_cast<const float4*>(x), mean, rstd, reinterpret_cast<const float4*>(gamma), w,              \
       reinterpret_cast<float4*>(dx), s_acc, g_acc, rows, rows_per_sample, K)))
   if (rb == 1) {
