@@ -12,13 +12,10 @@
 // (logit_k = rstd * sum_c (x_c - mean) gamma_c W_kc + sum_c beta_c W_kc).  Backward: the S accumulators are spread over
 // the whole warp -- lane (sub, t) keeps its 4 V channels for the classes k = sub, sub + 4, ... -- and the lanes exchange
 // xhat and d(logits) of the warp's rows through shared memory, so S costs 4 V * KQ registers instead of 4 V * K.
-#include <cstdlib>
-
 #include "hs_common.h"
 
 namespace {
 
-constexpr int kThreads = 256;
 constexpr int kT = 8;  // lanes per row
 
 __device__ __forceinline__ float group_sum8(float v) {
@@ -58,15 +55,15 @@ __device__ __forceinline__ void split_row(long long row, long long P, bool small
   }
 }
 
-template <int V, int KQ, int R>
-__global__ void __launch_bounds__(kThreads, 2)
+template <int V, int KQ, int R, int TH>
+__global__ void __launch_bounds__(TH, 2)
 ln_head_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamma, const float* __restrict__ beta,
                    const float* __restrict__ w, const float* __restrict__ hbias, float* __restrict__ logits,
                    float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, long long P, int K, float eps) {
   constexpr int KP = 4 * KQ, C4 = kT * V, C = 4 * C4;
   __shared__ float4 wg[KP][C4];  // gamma * W, zero rows for k >= K
   __shared__ float b0[KP];       // sum_c beta_c W_kc + bias_k
-  for (int i = threadIdx.x; i < KP * C4; i += kThreads) {
+  for (int i = threadIdx.x; i < KP * C4; i += TH) {
     const int k = i / C4, c4 = i - k * C4;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (k < K) {
@@ -95,8 +92,8 @@ ln_head_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamm
   const int nmine = up1 ? H1 - H2 : H2;
   // the trip count is the same for every thread (rows beyond the end are predicated off), which lets the compiler
   // prove the warp converged at the shuffles: a thread-dependent loop bound wraps each of them in WARPSYNC.COLLECTIVE
-  const long long warp0 = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
-  const long long stride = (long long)gridDim.x * (kThreads / 32) * (4 * R);
+  const long long warp0 = (long long)blockIdx.x * (TH / 32) + (threadIdx.x >> 5);
+  const long long stride = (long long)gridDim.x * (TH / 32) * (4 * R);
   const long long iters = (rows + stride - 1) / stride;
   // software pipeline: the rows of iteration it + 1 are requested before those of iteration it are processed (16 warps
   // per SM do not hide the HBM latency of a load-then-compute loop: ncu showed long-scoreboard stalls first)
@@ -172,7 +169,7 @@ ln_head_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gamm
 constexpr int kThreadsB = 192;  // backward: 2 x 6 warps per SM leave 170 registers per thread for the prefetch
 
 template <int V, int KQ, int R>
-__global__ void __launch_bounds__(kThreadsB, (R == 1 ? 2 : 1))
+__global__ void __launch_bounds__(kThreadsB, 2)
 ln_head_bwd_kernel(const float* __restrict__ dlogits, const float4* __restrict__ x, const float* __restrict__ mean,
                    const float* __restrict__ rstd, const float4* __restrict__ gamma, const float* __restrict__ w,
                    float4* __restrict__ dx, float* __restrict__ s_acc, float* __restrict__ g_acc, long long rows,
@@ -351,15 +348,9 @@ int num_sms() {
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-constexpr int kRF = 1;  // rows per lane and iteration, forward
+constexpr int kRF = 2, kThreadsF = 192;  // forward: rows per lane and iteration, block size (2 x 6 warps per SM: 170 registers)
 
-int bwd_rows_per_lane() {  // backward: 2 (255 registers, 8 warps / SM) or 1 (16 warps / SM); HS_LN_HEAD_RB overrides
-  static int r = [] {
-    const char* e = getenv("HS_LN_HEAD_RB");
-    return (e && e[0] == '2') ? 2 : 1;
-  }();
-  return r;
-}
+constexpr int kRB = 1;  // backward: rows per lane and iteration (2 needs 255 registers and was slower)
 
 #define HS_LH_DISPATCH_KQ(V_, ...)                                         \
   switch ((K + 3) / 4) {                                                   \
@@ -392,11 +383,11 @@ int hs_ln_head_fwd(const float* x, const float* gamma, const float* beta, const 
   if (!hs_ln_head_supported(rows, C, K))
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_ln_head_fwd: C=%d K=%d is not covered (C in {32, 64, 96}, K <= 16)", C, K);
   HS_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(w), "hs_ln_head_fwd: x, gamma and w must be 16-byte aligned");
-  const long long per_block = (kThreads / 32) * 4 * kRF;
+  const long long per_block = (kThreadsF / 32) * 4 * kRF;
   long long blocks = (rows + per_block - 1) / per_block;
-  const long long cap = (long long)num_sms() * 2 * 4;
+  const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
-  HS_LH_DISPATCH((ln_head_fwd_kernel<V, KQ, kRF><<<(unsigned)blocks, kThreads, 0, (cudaStream_t)stream>>>(
+  HS_LH_DISPATCH((ln_head_fwd_kernel<V, KQ, kRF, kThreadsF><<<(unsigned)blocks, kThreadsF, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gamma), beta, w, head_bias, logits, mean, rstd,
       rows, rows_per_sample, K, eps)));
   HS_LAUNCH_CHECK();
@@ -413,21 +404,13 @@ int hs_ln_head_bwd(const float* dlogits, const float* x, const float* mean, cons
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_ln_head_bwd: C=%d K=%d is not covered (C in {32, 64, 96}, K <= 16)", C, K);
   HS_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(w) && aligned16(dx),
              "hs_ln_head_bwd: x, gamma, w and dx must be 16-byte aligned");
-  const int rb = bwd_rows_per_lane();
-  const long long per_block = (kThreadsB / 32) * 4 * rb;
+  const long long per_block = (kThreadsB / 32) * 4 * kRB;
   long long blocks = (rows + per_block - 1) / per_block;
-  const long long cap = (long long)num_sms() * (rb == 1 ? 2 : 1);
+  const long long cap = (long long)num_sms() * 2;
   if (blocks > cap) blocks = cap;
-#define HS_LH_BWD(R_)                                                                                                  \
-  HS_LH_DISPATCH((ln_head_bwd_kernel<V, KQ, R_><<<(unsigned)blocks, kThreadsB, 0, (cudaStream_t)stream>>>(              \
-      dlogits, reinterpret_cast<const float4*>(x), mean, rstd, reinterpret_cast<const float4*>(gamma), w,              \
-      reinterpret_cast<float4*>(dx), s_acc, g_acc, rows, rows_per_sample, K)))
-  if (rb == 1) {
-    HS_LH_BWD(1);
-  } else {
-    HS_LH_BWD(2);
-  }
-#undef HS_LH_BWD
+  HS_LH_DISPATCH((ln_head_bwd_kernel<V, KQ, kRB><<<(unsigned)blocks, kThreadsB, 0, (cudaStream_t)stream>>>(
+      dlogits, reinterpret_cast<const float4*>(x), mean, rstd, reinterpret_cast<const float4*>(gamma), w,
+      reinterpret_cast<float4*>(dx), s_acc, g_acc, rows, rows_per_sample, K)));
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

@@ -38,7 +38,7 @@ def main():
     tfb, tub = timeit(fb(fused_fwd), 10), timeit(fb(unfused_fwd), 10)
     gb_f = B * P * (Cc + K) * 4 / 1e9
     gb_b = B * P * (2 * Cc + K) * 4 / 1e9
-    print(f"HS_LN_HEAD_RB={os.environ.get('HS_LN_HEAD_RB', '1')}: forward fused {tf:.3f} ms ({gb_f / tf * 1e3:.0f} GB/s) vs "
+    print(f"forward fused {tf:.3f} ms ({gb_f / tf * 1e3:.0f} GB/s) vs "
           f"unfused {tu:.3f} ms | fwd+bwd fused {tfb:.3f} ms (bwd {tfb - tf:.3f} ms, {gb_b / (tfb - tf) * 1e3:.0f} GB/s) vs "
           f"unfused {tub:.3f} ms", flush=True)
 
