@@ -181,6 +181,80 @@ def run_reference(a):
 
 
 # ----------------------------------------------------------------------------- our arm
+def alg_bytes(name, tag):
+    """Algorithmic HBM bytes of one launch of a hand-written kernel family, from its shape tag."""
+    if name == "window_attn_fwd":  # q, k, v in + o out (SURVEY.md 8d: 4*ws*d*elt per window-head)
+        return tag[0] * tag[1] * 4 * tag[2] * 4
+    if name == "window_attn_bwd":  # q, k, v, dO in + dq, dk, dv out
+        return tag[0] * tag[1] * 7 * tag[2] * 4
+    if name == "layernorm_fwd":    # x (+ residual) in, y out
+        return tag[0] * tag[1] * 4 * (2 + tag[2])
+    if name == "layernorm_bwd":    # dy, x in, dx out
+        return tag[0] * tag[1] * 4 * 3
+    if name == "gather_rows":
+        return tag[0] * tag[1] * tag[2] * 4 * 2
+    if name == "linear_wgrad":     # dy (T, N), x (T, K) in; dw negligible
+        return tag[0] * (tag[1] + tag[2]) * 4
+    if name == "bias_gelu_fwd":    # z in, h out
+        return tag[0] * tag[1] * 4 * 2
+    if name == "bias_gelu_bwd":    # dh, z in, dz out
+        return tag[0] * tag[1] * 4 * 3
+    if name == "ln_head_fwd":      # x (rows, C) in, logits (rows, K) + mean, rstd out
+        return tag[0] * (tag[1] + tag[2] + 2) * 4
+    if name == "ln_head_bwd":      # x, dlogits, mean, rstd in, dx out
+        return tag[0] * (2 * tag[1] + tag[2] + 2) * 4
+    if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
+        return tag[0] * (tag[1] + 2 * tag[2]) * 4
+    return None
+
+
+def summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic):
+    """Per-family roofline figures from the CUDA-event durations of the launches inside the timed region
+    ({(family, shape tag): [ms, ...]}) and the headline ``roofline`` object: the family with the largest share of the
+    step, at the shape its ncu DRAM-traffic figure was captured for (profiles/ncu_traffic.json, ``<family>@shape``) when
+    that shape ran, else at its largest shape with ``traffic`` null."""
+    families = {}
+    for (name, tag), times in kernel_ms.items():
+        nb = alg_bytes(name, tag)
+        if nb is None or not times:
+            continue
+        f = families.setdefault(name, {"ms": 0.0, "bytes": 0.0, "launches": 0, "top": None, "shapes": {}})
+        f["ms"] += sum(times)
+        f["bytes"] += nb * len(times)
+        f["launches"] += len(times)
+        f["shapes"][tuple(tag)] = (nb, statistics.mean(times), len(times))
+        if f["top"] is None or nb > f["top"][1]:
+            f["top"] = (tag, nb, statistics.mean(times), len(times))
+    kernels = {}
+    for name, f in families.items():
+        tag, nb, avg_ms, n = f["top"]
+        ach = nb / (avg_ms * 1e-3) / 1e9
+        kernels[name] = {"share_of_step": f["ms"] / ms_dev, "launches": f["launches"],
+                         "family_achieved_GBps": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
+                         "largest_shape": list(tag), "largest_shape_avg_ms": avg_ms, "largest_shape_launches": n,
+                         "largest_shape_algorithmic_bytes": nb, "largest_shape_achieved_GBps": ach,
+                         "largest_shape_frac": ach / hbm_peak}
+    if not kernels:
+        return kernels, None
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    tag, nb, avg_ms, n = families[dom]["top"]
+    dram = None
+    cap_shape = traffic.get(dom + "@shape")
+    if traffic.get(dom) is not None:
+        if cap_shape is None:
+            dram = traffic[dom]
+        elif tuple(cap_shape) in families[dom]["shapes"]:
+            tag = tuple(cap_shape)
+            nb, avg_ms, n = families[dom]["shapes"][tag]
+            dram = traffic[dom]
+    ach = nb / (avg_ms * 1e-3) / 1e9
+    roofline = {"kernel": f"hs_{dom} (shape {list(tag)})", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                "unit": "GB/s", "frac": ach / hbm_peak, "traffic": dram, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": nb, "avg_launch_ms": avg_ms, "launches_timed": n,
+                "share_of_step": kernels[dom]["share_of_step"]}
+    return kernels, roofline
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -294,61 +368,7 @@ def run_ours(a):
     except Exception:
         pass
 
-    def alg_bytes(name, tag):
-        if name == "window_attn_fwd":  # q, k, v in + o out (4*ws*d*elt per window-head)
-            return tag[0] * tag[1] * 4 * tag[2] * 4
-        if name == "window_attn_bwd":  # q, k, v, dO in + dq, dk, dv out
-            return tag[0] * tag[1] * 7 * tag[2] * 4
-        if name == "layernorm_fwd":    # x (+ residual) in, y out
-            return tag[0] * tag[1] * 4 * (2 + tag[2])
-        if name == "layernorm_bwd":    # dy, x in, dx out
-            return tag[0] * tag[1] * 4 * 3
-        if name == "gather_rows":
-            return tag[0] * tag[1] * tag[2] * 4 * 2
-        if name == "linear_wgrad":     # dy (T, N), x (T, K) in; dw negligible
-            return tag[0] * (tag[1] + tag[2]) * 4
-        if name == "bias_gelu_fwd":    # z in, h out
-            return tag[0] * tag[1] * 4 * 2
-        if name == "bias_gelu_bwd":    # dh, z in, dz out
-            return tag[0] * tag[1] * 4 * 3
-        if name == "ln_head_fwd":      # x (rows, C) in, logits (rows, K) + mean, rstd out
-            return tag[0] * (tag[1] + tag[2] + 2) * 4
-        if name == "ln_head_bwd":      # x, dlogits, mean, rstd in, dx out
-            return tag[0] * (2 * tag[1] + tag[2] + 2) * 4
-        if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
-            return tag[0] * (tag[1] + 2 * tag[2]) * 4
-        return None
-
-    families = {}
-    for (name, tag), times in kernel_ms.items():
-        nb = alg_bytes(name, tag)
-        if nb is None:
-            continue
-        f = families.setdefault(name, {"ms": 0.0, "bytes": 0.0, "launches": 0, "top": None})
-        f["ms"] += sum(times)
-        f["bytes"] += nb * len(times)
-        f["launches"] += len(times)
-        if f["top"] is None or nb > f["top"][1]:
-            f["top"] = (tag, nb, statistics.mean(times), len(times))
-    kernels = {}
-    for name, f in families.items():
-        tag, nb, avg_ms, n = f["top"]
-        ach = nb / (avg_ms * 1e-3) / 1e9
-        kernels[name] = {"share_of_step": f["ms"] / ms_dev, "launches": f["launches"],
-                         "family_achieved_GBps": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
-                         "largest_shape": list(tag), "largest_shape_avg_ms": avg_ms, "largest_shape_launches": n,
-                         "largest_shape_algorithmic_bytes": nb, "largest_shape_achieved_GBps": ach,
-                         "largest_shape_frac": ach / hbm_peak}
-    roofline = None
-    if kernels:
-        dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
-        k = kernels[dom]
-        roofline = {"kernel": f"hs_{dom} (largest shape {k['largest_shape']})", "bound": "hbm",
-                    "achieved": k["largest_shape_achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": k["largest_shape_frac"], "traffic": traffic.get(dom), "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": k["largest_shape_algorithmic_bytes"],
-                    "avg_launch_ms": k["largest_shape_avg_ms"], "launches_timed": k["largest_shape_launches"],
-                    "share_of_step": k["share_of_step"]}
+    kernels, roofline = summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic)
 
     cpu_base = None
     if world == 1 and not a.no_cpu_baseline:
