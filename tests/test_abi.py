@@ -35,3 +35,44 @@ def test_library_has_no_torch_or_libcuda_link_dependency():
 
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "torch" not in out and "libc10" not in out
+
+
+def test_shape_predicates_are_host_only():
+    """The *_supported predicates are pure host functions (no device needed): the shapes of BASELINE configs[1] are
+    covered, shapes outside the kernels' tiling are not."""
+    lib = _lib.lib
+    T0 = 8 * 196608
+    # weight gradient: qkv / fc1 (bias fused), fc2 (N < K: no fused bias), stage 3 (min(N, K) = 768: library)
+    assert lib.hs_linear_wgrad_supported(T0, 288, 96) == 2 and lib.hs_linear_wgrad_supported(T0, 384, 96) == 2
+    assert lib.hs_linear_wgrad_supported(T0, 96, 384) == 1
+    assert lib.hs_linear_wgrad_supported(T0 // 64, 2304, 768) == 0 and lib.hs_linear_wgrad_supported(T0, 10, 96) == 0
+    assert lib.hs_linear_wgrad_supported(100, 288, 96) == 0
+    # fused MLP backward: stages 0-1
+    assert lib.hs_mlp_dgrad_gelu_supported(T0, 96, 384) == 1 and lib.hs_mlp_dgrad_gelu_supported(T0 // 4, 192, 768) == 1
+    assert lib.hs_mlp_dgrad_gelu_supported(T0 // 16, 384, 1536) == 0 and lib.hs_mlp_dgrad_gelu_supported(T0, 96, 100) == 0
+    # fused decoder tail: C in {32, 64, 96}, up to 16 output channels
+    assert lib.hs_ln_head_supported(4 * T0, 96, 10) == 1 and lib.hs_ln_head_supported(4 * T0, 96, 1) == 1
+    assert lib.hs_ln_head_supported(4 * T0, 128, 1) == 0 and lib.hs_ln_head_supported(4 * T0, 96, 17) == 0
+
+
+def test_argument_validation_happens_before_any_device_work():
+    """Bad arguments are rejected on the host with HS_ERR_ARG / HS_ERR_UNSUPPORTED and a message (no GPU needed)."""
+    import ctypes as C
+
+    lib = _lib.lib
+    null = None
+    one = C.c_void_p(16)  # a non-null, 16-byte aligned dummy: must never be dereferenced by the checks below
+    rc = lib.hs_ln_head_fwd(null, one, one, one, null, one, one, one, 8, 4, 96, 10, C.c_float(1e-5), null)
+    assert rc == 1 and "null" in _lib.last_error()
+    rc = lib.hs_ln_head_fwd(one, one, one, one, null, one, one, one, 10, 4, 96, 10, C.c_float(1e-5), null)
+    assert rc == 1 and "rows_per_sample" in _lib.last_error()
+    rc = lib.hs_ln_head_fwd(one, one, one, one, null, one, one, one, 8, 4, 48, 10, C.c_float(1e-5), null)
+    assert rc == 3 and "not covered" in _lib.last_error()
+    rc = lib.hs_mlp_dgrad_gelu(one, one, one, null, C.c_float(1.5), 0, one, 8192, 96, 384, 0, null)
+    assert rc == 1 and "drop" in _lib.last_error()
+    rc = lib.hs_mlp_dgrad_gelu(one, one, one, null, C.c_float(0.0), 0, one, 8192, 384, 1536, 0, null)
+    assert rc == 3 and "not covered" in _lib.last_error()
+    rc = lib.hs_linear_dgrad_acc(null, one, null, one, 8, 4, 4, null, 0, null)
+    assert rc == 1
+    rc = lib.hs_linear_fwd(one, one, null, null, 8, 4, 4, null, 0, null)
+    assert rc == 1
