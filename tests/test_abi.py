@@ -76,3 +76,10 @@ def test_argument_validation_happens_before_any_device_work():
     assert rc == 1
     rc = lib.hs_linear_fwd(one, one, null, null, 8, 4, 4, null, 0, null)
     assert rc == 1
+
+
+def test_every_entry_point_is_documented_for_the_integrator():
+    """INTEGRATION.md's table names every exported entry point together with the reference code it replaces."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_functions() if n not in text]
+    assert not missing, f"not mentioned in INTEGRATION.md: {missing}"
