@@ -94,3 +94,39 @@ def test_module_shifters_match_oracle():
     assert np.array_equal(q.shift_idcs.numpy(), o.shift_idcs)
     assert np.array_equal(q.get_mask(False).numpy(), o.groups)
     assert S.NoShift().get_mask() is None
+
+
+def test_shift_tables_sweep_is_bit_exact_and_rejects_what_the_oracle_rejects():
+    """Every strategy over a grid of (nside, base_pix, window, shift), including single-window spheres, 1-pixel shifts and
+    windows larger than a base pixel: the C++ tables equal the oracle's bit for bit, and a configuration is refused by
+    one exactly when it is refused by the other (the reference's asserts, SURVEY 8b error convention)."""
+    checked = rejected = 0
+    for strat, code in CODES.items():
+        for nside in (2, 4, 8, 16, 32):
+            bps = (8,) if strat == "nest_grid_shift" else (1, 2, 4, 8) if strat == "ring_shift" else (1, 8, 12)
+            for bp in bps:
+                N = bp * nside * nside
+                for ws in (4, 16, 64, 256):
+                    if ws > N:
+                        continue
+                    for sh in ((ws // 2,) if strat == "nest_grid_shift" else (1, ws // 4, ws // 2, ws - 1)):
+                        try:
+                            o = (O.nest_roll_tables(sh, N, ws) if strat == "nest_roll" else
+                                 O.nest_grid_tables(nside, bp, ws) if strat == "nest_grid_shift" else
+                                 O.ring_shift_tables(nside, bp, ws, sh))
+                        except (AssertionError, KeyError, IndexError, ValueError):
+                            o = None
+                        try:
+                            got = hp_index.shift_tables(code, nside, bp, ws, sh)
+                        except AssertionError:
+                            got = None
+                        assert (o is None) == (got is None), (strat, nside, bp, ws, sh)
+                        if o is None:
+                            rejected += 1
+                            continue
+                        fwd, back, grp = got
+                        assert np.array_equal(fwd.numpy(), o.shift_idcs), (strat, nside, bp, ws, sh)
+                        assert np.array_equal(back.numpy(), o.back_idcs), (strat, nside, bp, ws, sh)
+                        assert np.array_equal(grp.numpy().astype(np.int64), o.groups), (strat, nside, bp, ws, sh)
+                        checked += 1
+    assert checked > 200 and rejected > 50
