@@ -10,10 +10,14 @@ Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
 * ``value``  : pixels/s with the batch already resident in HBM (device-timed, CUDA events).
 * ``e2e``    : the same step driven from pinned HOST buffers (H2D of the batch and D2H of the loss
                inside the timed region).
-* ``roofline``: the windowed-attention forward kernel at the stage-0 shape, algorithmic bytes /
-               CUDA-event duration measured live in the timed region.
+* ``roofline``: algorithmic bytes / mean CUDA-event duration of the launches inside the timed region, for the
+               hand-written kernel family with the largest share of the step; ``roofline.attention`` carries the same
+               figures for the windowed-attention forward and backward kernels (the kernel BASELINE.json's metric names)
+               with the tensor-pipe utilisation of their committed ncu captures, ``roofline.families`` every family.
 * ``cpu_baseline`` / ``--impl reference``: the CPU oracle port of the reference's models_torch
-               forward+backward (oracle/hp_oracle.py) on the host cores -- a reported baseline only.
+               forward+backward (oracle/hp_oracle.py) on the host cores -- a reported baseline only.  The same leg
+               yields ``config.forward_rel_err_vs_fp32_oracle``: the bench model's forward on one full-size sphere
+               against the oracle's, measured live.
 """
 import argparse
 import json
@@ -49,9 +53,9 @@ def parse_args():
                          "headline number uses 0 so that it is comparable with the dropout-free reference arm)")
     ap.add_argument("--no-cos", action="store_true")
     ap.add_argument("--v1-norm", action="store_true")
-    ap.add_argument("--gemm-precision", default="tf32", choices=["tf32", "fp32"],
-                    help="precision of the library GEMMs (torch.backends.cuda.matmul.allow_tf32); the attention kernels "
-                         "are TF32 tensor-core kernels either way")
+    ap.add_argument("--gemm", default="bf16x3", choices=["bf16x3", "library"],
+                    help="bf16x3: the hand-written tensor-core GEMMs (the product); library: cuBLAS TF32 through torch "
+                         "(diagnostics only: outside the 1e-3 tolerance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -136,13 +140,17 @@ def cpu_oracle_steps(kw, steps, warmup, budget_s):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1, kw["f_in"], kw["dim_in"], generator=g)
     times = []
+    keep = {}
 
     def one():
         for v in sd.values():
             v.grad = None
         t0 = time.perf_counter()
-        O.hp_unet_forward(x, sd, cfg).float().mean().backward()
-        return time.perf_counter() - t0
+        y = O.hp_unet_forward(x, sd, cfg)
+        y.float().mean().backward()
+        dt = time.perf_counter() - t0
+        keep["y"] = y.detach()
+        return dt
 
     t_first = one() if warmup > 0 else None
     est = t_first if t_first is not None else 20.0
@@ -154,9 +162,12 @@ def cpu_oracle_steps(kw, steps, warmup, budget_s):
     for _ in range(k):
         times.append(one())
     t = statistics.median(times)
-    return {"value": kw["dim_in"] / t, "unit": UNIT, "cores": cores, "kind": "port",
+    base = {"value": kw["dim_in"] / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"B=1 full-size sphere ({kw['dim_in']} px) fwd+bwd, {k} timed step(s) after {done_warm} warm-up, "
-                      f"median {t:.2f} s/step, torch CPU fp32 {torch.get_num_threads()} threads"}, k, done_warm, t
+                      f"median {t:.2f} s/step, torch CPU fp32 {torch.get_num_threads()} threads"}
+    # the checker's view of this sample: input, weights and forward output (for the live parity figure of our arm)
+    base_check = {"x": x, "sd": {n: v.detach() for n, v in sd.items()}, "y": keep["y"]}
+    return base, k, done_warm, t, base_check
 
 
 def run_reference(a):
@@ -164,7 +175,7 @@ def run_reference(a):
     if rank != 0:
         return
     kw = model_kwargs(a)
-    base, k, w, t = cpu_oracle_steps(kw, a.steps, a.warmup, a.cpu_budget_s)
+    base, k, w, t, _ = cpu_oracle_steps(kw, a.steps, a.warmup, a.cpu_budget_s)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": k, "warmup": w, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -205,7 +216,14 @@ def alg_bytes(name, tag):
         return tag[0] * (2 * tag[1] + tag[2] + 2) * 4
     if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
         return tag[0] * (tag[1] + 2 * tag[2]) * 4
+    if name == "gemm3":            # tag (T, N, K, mode): a (T, K) in, d (T, N) out, + aux in (modes 1, 3) / d2 out (mode 2)
+        return tag[0] * (tag[2] + tag[1] * (1 if tag[3] == 0 else 2)) * 4
     return None
+
+
+def gemm3_flops(tag):
+    """bf16 tensor-core flops one hs_gemm3 launch executes: three MMAs per product (hi*hi + lo*hi + hi*lo)."""
+    return 3 * 2.0 * tag[0] * tag[1] * tag[2]
 
 
 def summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic):
@@ -252,6 +270,23 @@ def summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic):
                 "unit": "GB/s", "frac": ach / hbm_peak, "traffic": dram, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nb, "avg_launch_ms": avg_ms, "launches_timed": n,
                 "share_of_step": kernels[dom]["share_of_step"]}
+    # the kernel BASELINE.json's metric names: windowed attention forward + backward at their largest (stage-0) shape
+    att = {}
+    for key, fam in (("fwd", "window_attn_fwd"), ("bwd", "window_attn_bwd")):
+        if fam in families:
+            t_, nb_, ms_, n_ = families[fam]["top"]
+            att[key] = {"shape": list(t_), "avg_launch_ms": ms_, "launches_timed": n_, "algorithmic_bytes_per_launch": nb_,
+                        "achieved_GBps": nb_ / (ms_ * 1e-3) / 1e9, "frac": nb_ / (ms_ * 1e-3) / 1e9 / hbm_peak,
+                        "traffic": traffic.get(fam), "share_of_step": kernels[fam]["share_of_step"],
+                        "tensor_pipe_pct_ncu": traffic.get(fam + "@tensor_pipe_pct")}
+    if "fwd" in att and "bwd" in att:
+        nb_ = att["fwd"]["algorithmic_bytes_per_launch"] + att["bwd"]["algorithmic_bytes_per_launch"]
+        ms_ = att["fwd"]["avg_launch_ms"] + att["bwd"]["avg_launch_ms"]
+        att["fwd_plus_bwd_frac"] = nb_ / (ms_ * 1e-3) / 1e9 / hbm_peak
+    if att:
+        att["bound"] = "hbm (the stand-alone core has 16 flop/B; the tensor pipe is reported as measured by ncu)"
+        roofline["attention"] = att
+    roofline["families"] = kernels
     return kernels, roofline
 
 
@@ -260,9 +295,8 @@ def run_ours(a):
     import torch.distributed as dist
 
     from heal_swin_b200 import _lib, ops
-    from tests.util import build_product_model
-
     from heal_swin_b200 import dist as hsdist
+    from heal_swin_b200.factory import build_hp_model
 
     rank, local, world = hsdist.env_world()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -270,14 +304,15 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     _lib.check(_lib.lib.hs_device_info(None, None, None, None, 0))
     hsdist.init_from_env("nccl", dev)
-    # library GEMMs (cuBLAS through torch): TF32 like the reference's own container did (torch 1.8 default), or fp32
-    torch.backends.cuda.matmul.allow_tf32 = a.gemm_precision == "tf32"
-    torch.backends.cudnn.allow_tf32 = a.gemm_precision == "tf32"
+    ops.set_gemm_mode(a.gemm)
+    # only matters for --gemm library (diagnostics) and for the few linears outside the hand-written GEMM's coverage (none
+    # in this model): TF32 like the reference's own container did (torch 1.8 default)
+    torch.backends.cuda.matmul.allow_tf32 = a.gemm == "library"
 
     kw = model_kwargs(a)
     torch.manual_seed(0)
-    model = build_product_model(dict(kw, drop_rate=a.drop_rate, attn_drop_rate=a.drop_rate, drop_path_rate=a.drop_rate),
-                                None, dev)
+    model = build_hp_model(dict(kw, drop_rate=a.drop_rate, attn_drop_rate=a.drop_rate, drop_path_rate=a.drop_rate),
+                           None, dev)
     with torch.no_grad():  # the reference zero-initialises the bias tables; give them signal
         gen = torch.Generator(device="cpu").manual_seed(1)
         for n, p in model.named_parameters():
@@ -288,9 +323,15 @@ def run_ours(a):
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     B, npix = a.batch, kw["dim_in"]
     gen = torch.Generator().manual_seed(1234 + rank)
-    host_x = torch.randn(B, kw["f_in"], npix, generator=gen).pin_memory()
-    host_t = torch.randint(0, kw["f_out"], (B, npix), generator=gen).pin_memory()
-    dev_x, dev_t = host_x.to(dev), host_t.to(dev)
+    # the data pipeline delivers 8-bit images and class ids (the Lightning wrapper casts on the device: self.model(x.float()),
+    # models_lightning/segmentation/model_lightning_swin_hp.py:61): the host feed is uint8, normalised on the device
+    host_x = torch.randint(0, 256, (B, kw["f_in"], npix), generator=gen, dtype=torch.uint8).pin_memory()
+    host_t = torch.randint(0, kw["f_out"], (B, npix), generator=gen, dtype=torch.uint8).pin_memory()
+
+    def to_model_inputs(xu8, tu8):
+        return (xu8.float() - 127.5) * (1.0 / 73.9), tu8.long()  # zero mean, unit variance for uniform bytes
+
+    dev_x, dev_t = to_model_inputs(host_x.to(dev), host_t.to(dev))
     loss_fn = torch.nn.CrossEntropyLoss()
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
 
@@ -335,8 +376,7 @@ def run_ours(a):
     barrier()
     e0.record()
     for _ in range(a.steps):
-        x = host_x.to(dev, non_blocking=True)
-        t = host_t.to(dev, non_blocking=True)
+        x, t = to_model_inputs(host_x.to(dev, non_blocking=True), host_t.to(dev, non_blocking=True))
         loss = step(x, t)
         host_loss.copy_(loss.detach(), non_blocking=True)
     e1.record()
@@ -370,23 +410,37 @@ def run_ours(a):
 
     kernels, roofline = summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic)
 
-    cpu_base = None
+    cpu_base, fwd_err = None, None
     if world == 1 and not a.no_cpu_baseline:
-        cpu_base, _, _, _ = cpu_oracle_steps(kw, 1, 1, min(a.cpu_budget_s, 60.0))
+        cpu_base, _, _, _, chk = cpu_oracle_steps(kw, 1, 1, min(a.cpu_budget_s, 60.0))
+        # live parity of the benchmarked configuration: the same architecture with the checker's weights, one full-size
+        # sphere, forward through the product path vs the oracle's forward of the CPU sample above
+        del net, opt
+        model.load_state_dict(chk["sd"], strict=False)
+        ops.invalidate_weight_splits()
+        model.eval()
+        with torch.no_grad():
+            got = model(chk["x"].to(dev)).float().cpu()
+        fwd_err = float((got.double() - chk["y"].double()).norm() / chk["y"].double().norm())
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32", "data": "synthetic",
+        "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, kw), "global_batch": world * B, "pixels_per_sample": npix,
                    "parallelism": f"dp{world}", "step": "fwd + CE loss + bwd + (NCCL grad all-reduce) + Adam",
-                   "library_gemm_precision": a.gemm_precision, "drop_rates": a.drop_rate,
-                   "forward_rel_err_vs_fp32_oracle": "4-6e-4 with fp32 library GEMMs, 1.1-1.4e-3 with TF32 ones "
-                                                     "(scripts/tf32_model_check.py, tests/test_gpu_model.py)",
+                   "arithmetic": "fp32 in HBM; dense linears: hand-written bf16x3 tcgen05 GEMM (hi/lo split operands, 3 MMAs, "
+                                 "fp32 accumulate); attention: tcgen05 TF32; LayerNorm / softmax / GELU fp32"
+                                 if a.gemm == "bf16x3" else "fp32 in HBM; cuBLAS TF32 GEMMs (diagnostic mode)",
+                   "gemm": a.gemm, "drop_rates": a.drop_rate,
+                   "forward_rel_err_vs_fp32_oracle": fwd_err,
+                   "forward_rel_err_note": "measured in this run: bench model, B=1 full-size sphere, vs the CPU oracle "
+                                           "(tolerance 1e-3); null when the CPU leg is skipped",
+                   "host_feed": "uint8 images + uint8 class ids from pinned host memory, cast on the device",
                    "l2_policy": "inputs larger than L2 (activations 0.6-2.4 GB per tensor at stage 0), no flush needed",
                    "final_loss": final_loss},
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": host_x.numel() * 4 + host_t.numel() * 8, "d2h_bytes_per_step": 4},
+                "h2d_bytes_per_step": host_x.numel() + host_t.numel(), "d2h_bytes_per_step": 4},
         "gpu_launches": launches,
         "roofline": roofline,
         "kernels": kernels,

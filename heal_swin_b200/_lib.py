@@ -15,6 +15,7 @@ SHIFT_NONE, SHIFT_NEST_ROLL, SHIFT_NEST_GRID, SHIFT_RING = 0, 1, 2, 3
 ATTN_COS = 1
 ATTN_NO_TC = 2
 ATTN_NO_TRUNC_COMP = 4
+GEMM_PLAIN, GEMM_ADD, GEMM_GELU, GEMM_GELU_GRAD = 0, 1, 2, 3
 
 STRATEGY_CODES = {"nest_roll": SHIFT_NEST_ROLL, "nest_grid_shift": SHIFT_NEST_GRID, "ring_shift": SHIFT_RING}
 
@@ -42,11 +43,13 @@ SIGNATURES = {
     "hs_linear_wgrad": [_p, _p, _p, _p, _i64, _i, _i, _u32, _p],
     "hs_mlp_dgrad_gelu_supported": [_i64, _i, _i],
     "hs_mlp_dgrad_gelu": [_p, _p, _p, _p, _f, _u64, _p, _i64, _i, _i, _u32, _p],
-    "hs_linear_dgrad_acc": [_p, _p, _p, _p, _i64, _i, _i, _p, _u64, _p],
-    "hs_linear_fwd": [_p, _p, _p, _p, _i64, _i, _i, _p, _u64, _p],
+    "hs_weight_split": [_p, _i, _i, _i, _i, _p, _p],
+    "hs_gemm3_supported": [_i64, _i, _i],
+    "hs_gemm3": [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _f, _u64, _p],
     "hs_ln_head_supported": [_i64, _i, _i],
     "hs_ln_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _f, _p],
     "hs_ln_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],
+    "hs_bias_gelu_supported": [_i64, _i],
     "hs_bias_gelu_fwd": [_p, _p, _f, _u64, _p, _i64, _i, _p],
     "hs_bias_gelu_bwd": [_p, _p, _p, _f, _u64, _p, _p, _i64, _i, _p],
     "hs_window_attn_fwd": [_p, _p, _p, _p, _p, _p, _f, _f, _u64, _p, _p, _i, _i64, _i, _i, _i, _u32, _p],

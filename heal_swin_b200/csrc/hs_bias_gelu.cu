@@ -112,6 +112,8 @@ static Drop make_drop(float p, uint64_t seed) {
   return d;
 }
 
+int hs_bias_gelu_supported(int64_t rows, int C) { return (rows > 0 && C > 0 && C % 4 == 0 && pick_block(C / 4) > 0) ? 1 : 0; }
+
 int hs_bias_gelu_fwd(const float* z, const float* bias, float drop, uint64_t seed, float* h, int64_t rows, int C,
                      void* stream) {
   HS_REQUIRE(z && h && rows > 0 && C > 0, "hs_bias_gelu_fwd: bad arguments");

@@ -1,0 +1,545 @@
+// Dense linear layers of the hot path on the sm_100a tensor cores at fp32-class accuracy ("bf16x3"):
+//     D[t][n] = sum_k A[t][k] * W[n][k]   (+ epilogue)        A: (T, K) fp32, W: (N, K), D: (T, N) fp32
+// Serves the forward of every nn.Linear of the block (qkv / proj: swin_hp_transformer.py:131-135, 172; Mlp fc1 / fc2:
+// :21-44; PatchMerging.reduction :394; PatchExpand.expand :421; FinalPatchExpand_X4.expand :444; concat_back_dim :774)
+// and, with the transposed split weight, their input gradients.
+//
+// Why not kind::tf32: tcgen05 TF32 truncates both operands to 10 mantissa bits; through the 22 blocks of the network
+// that puts the output 1.1-1.4e-3 from the fp32 reference (tolerance 1e-3).  Here every fp32 operand is split into two
+// bf16 terms, x = hi + lo (+ O(2^-17 x)), and the product is accumulated in fp32 from three kind::f16 MMAs
+//     A_hi W_hi + A_lo W_hi + A_hi W_lo                    (the dropped lo*lo term is O(2^-16))
+// i.e. ~2^-16 relative per product instead of 2^-11, at 1.5x the tensor-pipe time of one TF32 MMA (bf16 runs at twice
+// the TF32 rate) -- free where the GEMM is HBM-bound (stages 0-1).
+//
+// Operand staging.  W is split once per optimizer step by hs_weight_split into rows of [hi(32) | lo(32)] bf16 per
+// 32-wide K chunk (128 B: one SWIZZLE_128B row), so it comes in by TMA ready to use.  A arrives as raw fp32: a
+// 128-row x 32-column chunk (16 KB, TMA SWIZZLE_128B) is rewritten IN PLACE by 8 converter warps into
+// [hi(32) | lo(32)] bf16 rows with the same swizzle -- the K=16 MMA steps then address hi at +0/+32 B and lo at +64/+96 B.
+//
+// A CTA owns one column chunk (n_tile <= 256 columns) and walks over 128-token tiles; its W chunk stays resident in shared
+// memory when it fits, otherwise the K slices of W ride in the ring slots beside the A chunks (L2 hits).  Two 256-column
+// TMEM stages overlap the epilogue of one tile with the MMAs of the next.  The epilogue (groups of 4 warps, one 32-column
+// slab at a time; every warp has private 4 KB staging regions and issues its own TMA stores / aux loads, so the warps never
+// synchronise with each other) goes TMEM -> registers -> swizzled staging region -> TMA store, and can
+//     MODE_PLAIN      add the bias
+//     MODE_ADD        add the bias and an fp32 tensor of D's shape (aux) -- the residual-shortcut gradient in a dgrad
+//     MODE_GELU       write z = acc (D) and h = dropout(GELU(acc + bias)) (D2): Mlp fc1 + act + drop in one pass
+//     MODE_GELU_GRAD  D = acc * GELU'(aux + bias) * dropmask: the fc2 input gradient through the activation
+// aux sub-slabs are brought in by TMA into the staging regions ahead of time and combined in place.
+//
+// Warps: [0, E) epilogue (TMEM lane quadrant = warp % 4), [E, E+8) converters, E+8 A producer, E+9 MMA issuer,
+// E+10 W producer.
+#include <cstdlib>
+
+#include "hs_common.h"
+#include "hs_gelu.cuh"
+#include "hs_sm100.cuh"
+#include "hs_tc_common.cuh"
+
+namespace {
+
+using namespace hs::sm100;
+
+constexpr int kBM = 128;               // tokens per tile
+constexpr int kChunk = kBM * 128;      // 16 KB: one A chunk, one staging slab
+constexpr int kMaxRing = 10;
+constexpr int kMaxWRing = 4;            // streamed W slices (L2 hits: a short ring is enough)
+constexpr int kMaxRw = 3;              // staging regions per epilogue warp
+constexpr int kRegion = 32 * 128;      // 4 KB: 32 rows x 32 columns, one warp's part of a slab
+constexpr int kCvtWarps = 8;
+constexpr int kStageCols = 256;        // TMEM columns per accumulator stage
+
+enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3 };
+
+struct G3Args {
+  const float* bias;  // (N) or null
+  long long T;
+  int N, K;
+  int n_stride, n_box, n_chunks;  // column chunks start every n_stride columns and compute n_box (multiple of 32)
+  long long tiles;
+  int ring, rw, resident, wring;  // A ring depth, staging regions per epilogue warp, W resident?, W ring depth
+  uint32_t drop_thresh;
+  float drop_scale;
+  uint64_t seed;
+};
+
+// instruction descriptor: D = f32, A = B = bf16, both K-major
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// {bf16(hi_of_pair), bf16(lo_of_pair)}: first argument lands in the upper 16 bits
+__device__ __forceinline__ uint32_t cvt_bf16x2(float upper, float lower) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+  return d;
+}
+// split two consecutive fp32 values (e0 at the lower address) into a packed hi word and a packed lo word
+__device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_bf16x2(e1, e0);
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  lo = cvt_bf16x2(e1 - h1, e0 - h0);
+}
+
+template <int E, int MODE>
+__global__ void __launch_bounds__((E + kCvtWarps + 3) * 32, 1)
+gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+             const __grid_constant__ CUtensorMap map_aux, const __grid_constant__ CUtensorMap map_d,
+             const __grid_constant__ CUtensorMap map_d2, const G3Args a) {
+  constexpr bool kAux = (MODE == MODE_ADD || MODE == MODE_GELU_GRAD);
+  constexpr int NG = E / 4;                    // epilogue groups (4 warps = the 4 TMEM lane quadrants)
+  constexpr int kStores = (MODE == MODE_GELU) ? 2 : 1;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int nk = (a.K + 31) / 32;              // K chunks (TMA zero-fills the tail of a ragged last chunk)
+  const int w_slice = a.n_box * 128;           // bytes of one K slice of the W chunk
+  uint8_t* s_w = sm;                           // resident: nk slices; streamed: a ring of wring slices
+  uint8_t* s_ring = s_w + (a.resident ? nk : a.wring) * w_slice;
+  uint8_t* s_buf = s_ring + a.ring * kChunk;   // E warps x rw regions of 4 KB
+  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], cvt_full[kMaxRing],
+      slot_empty[kMaxRing], acc_full[2], acc_empty[2], aux_full[E * kMaxRw];
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x % a.n_chunks;
+  const long long t0 = blockIdx.x / a.n_chunks, tstep = gridDim.x / a.n_chunks;
+  // column chunk of this CTA: starts every n_stride columns and computes n_box >= n_stride of them (a multiple of 32);
+  // where n_box > n_stride the first columns of the next chunk are computed -- and stored -- twice, with identical values
+  const int n0 = chunk * a.n_stride;
+  const int n_this = min(a.n_box, a.N - n0);
+  const int S = (n_this + 31) / 32;            // 32-column slabs (stores clip a ragged last slab at N)
+  const int ring = a.ring;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&w_full, 1);
+    for (int i = 0; i < kMaxWRing; ++i) {
+      mbar_init(&wr_full[i], 1);
+      mbar_init(&wr_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxRing; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&cvt_full[i], kCvtWarps);
+      mbar_init(&slot_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], E * 32);
+    }
+    for (int i = 0; i < E * kMaxRw; ++i) mbar_init(&aux_full[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == E + kCvtWarps + 1) tmem_alloc(&tmem_base, 512);
+  if (warp == E + kCvtWarps && lane == 0) tma_prefetch_desc(&map_a);
+  if (warp == E + kCvtWarps + 2 && lane == 0) tma_prefetch_desc(&map_w);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_d);
+    if (kAux) tma_prefetch_desc(&map_aux);
+    if (MODE == MODE_GELU) tma_prefetch_desc(&map_d2);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base;
+
+  if (warp == E + kCvtWarps) {
+    // ================================================================ A producer
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (long long tile = t0; tile < a.tiles; tile += tstep)
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&slot_empty[slot], ph ^ 1);
+          mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kChunk);
+          tma_load_2d(s_ring + slot * kChunk, &map_a, &raw_full[slot], 32 * kc, (int)(tile * kBM));
+          if (++slot == ring) { slot = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == E + kCvtWarps + 2) {
+    // ================================================================ W producer: resident chunk once, or a ring of K slices
+    if (elect_one()) {
+      if (a.resident) {
+        mbar_arrive_expect_tx(&w_full, (uint32_t)(nk * w_slice));
+        for (int kc = 0; kc < nk; ++kc) tma_load_2d(s_w + kc * w_slice, &map_w, &w_full, 64 * kc, n0);
+      } else {
+        int ws = 0;
+        uint32_t wph = 0;
+        for (long long tile = t0; tile < a.tiles; tile += tstep)
+          for (int kc = 0; kc < nk; ++kc) {
+            mbar_wait(&wr_empty[ws], wph ^ 1);
+            mbar_arrive_expect_tx(&wr_full[ws], (uint32_t)w_slice);
+            tma_load_2d(s_w + ws * w_slice, &map_w, &wr_full[ws], 64 * kc, n0);
+            if (++ws == a.wring) { ws = 0; wph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == E + kCvtWarps + 1) {
+    // ================================================================ MMA issuer
+    if (elect_one()) {
+      constexpr uint64_t kDesc = umma_smem_desc(16, 1024, kLayoutSw128);
+      const uint32_t idesc = idesc_bf16(128, 32 * S);
+      if (a.resident) mbar_wait(&w_full, 0);
+      const uint32_t wb = smem_u32(s_w), rb = smem_u32(s_ring);
+      int slot = 0, ws = 0;
+      uint32_t ph = 0, wph = 0;
+      long long it = 0;
+      for (long long tile = t0; tile < a.tiles; tile += tstep, ++it) {
+        const int as = (int)(it & 1);
+        mbar_wait(&acc_empty[as], (((uint32_t)(it >> 1)) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem + (uint32_t)as * kStageCols;
+        for (int kc = 0; kc < nk; ++kc) {
+          if (!a.resident) mbar_wait(&wr_full[ws], wph);
+          mbar_wait(&cvt_full[slot], ph);
+          tc_fence_after();
+          const uint32_t ab = rb + slot * kChunk;
+          const uint32_t wk = wb + (a.resident ? kc : ws) * w_slice;
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t a_hi = umma_desc_at(kDesc, ab + 32 * ks), a_lo = umma_desc_at(kDesc, ab + 64 + 32 * ks);
+            const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
+            umma_bf16_ss(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_ss(d, a_hi, w_lo, idesc, 1u);
+            umma_bf16_ss(d, a_hi, w_hi, idesc, 1u);
+          }
+          umma_commit(&slot_empty[slot]);
+          if (++slot == ring) { slot = 0; ph ^= 1; }
+          if (!a.resident) {
+            umma_commit(&wr_empty[ws]);
+            if (++ws == a.wring) { ws = 0; wph ^= 1; }
+          }
+        }
+        umma_commit(&acc_full[as]);
+      }
+    }
+  } else if (warp >= E) {
+    // ================================================================ converters: fp32 chunk -> [hi | lo] bf16, in place
+    const int cw = warp - E;
+    const int row = cw * 16 + (lane & 15), half = lane >> 4;
+    const int sw = row & 7;
+    const uint32_t ring_u32 = smem_u32(s_ring);
+    int slot = 0;
+    uint32_t ph = 0;
+    for (long long tile = t0; tile < a.tiles; tile += tstep)
+      for (int kc = 0; kc < nk; ++kc) {
+        mbar_wait(&raw_full[slot], ph);
+        const uint32_t base = ring_u32 + slot * kChunk + row * 128;
+        float4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = lds_f4(base + (((4 * half + j) ^ sw) << 4));
+        __syncwarp();  // every lane of the row pair has read before anyone overwrites
+        uint4 hi[2], lo[2];
+        split2(v[0].x, v[0].y, hi[0].x, lo[0].x);
+        split2(v[0].z, v[0].w, hi[0].y, lo[0].y);
+        split2(v[1].x, v[1].y, hi[0].z, lo[0].z);
+        split2(v[1].z, v[1].w, hi[0].w, lo[0].w);
+        split2(v[2].x, v[2].y, hi[1].x, lo[1].x);
+        split2(v[2].z, v[2].w, hi[1].y, lo[1].y);
+        split2(v[3].x, v[3].y, hi[1].z, lo[1].z);
+        split2(v[3].z, v[3].w, hi[1].w, lo[1].w);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          sts_u4(base + (((2 * half + j) ^ sw) << 4), hi[j]);
+          sts_u4(base + (((4 + 2 * half + j) ^ sw) << 4), lo[j]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&cvt_full[slot]);
+        if (++slot == ring) { slot = 0; ph ^= 1; }
+      }
+  } else {
+    // ================================================================ epilogue
+    // Warp (g, q) owns rows [32q, 32q + 32) (its TMEM lane quadrant) of the slabs g, g + NG, ... of every tile, and rw
+    // private 4 KB staging regions used round-robin: its own TMA stores (and aux loads), no cross-warp synchronisation.
+    const int g = warp >> 2, q = warp & 3;
+    const int sw = lane & 7;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int rw = a.rw;
+    uint8_t* my = s_buf + warp * rw * kRegion;
+    const uint32_t my_u32 = smem_u32(my);
+    uint64_t* my_full = aux_full + warp * kMaxRw;
+    const int spw = S > g ? (S - g + NG - 1) / NG : 0;            // slabs of this warp per tile
+    const long long my_tiles = a.tiles > t0 ? (a.tiles - t0 + tstep - 1) / tstep : 0;
+    const long long total = my_tiles * spw;                       // aux loads of this warp over the whole launch
+    auto issue_aux = [&](long long u) {                           // slab use u -> its staging region (lane 0 only)
+      const long long tile = t0 + (u / spw) * tstep;
+      const int s = g + NG * (int)(u % spw);
+      const int reg = (int)(u % rw);
+      mbar_arrive_expect_tx(&my_full[reg], kRegion);
+      tma_load_2d(my + reg * kRegion, &map_aux, &my_full[reg], n0 + 32 * s, (int)(tile * kBM) + 32 * q);
+    };
+    if (kAux && lane == 0)
+      for (long long u = 0; u < rw && u < total; ++u) issue_aux(u);
+    long long cnt = 0;  // staging-region uses so far
+    long long it = 0;
+    for (long long tile = t0; tile < a.tiles; tile += tstep, ++it) {
+      const int as = (int)(it & 1);
+      mbar_wait(&acc_full[as], ((uint32_t)(it >> 1)) & 1);
+      tc_fence_after();
+      const long long grow = tile * kBM + q * 32 + lane;
+      uint32_t dkey = 0;
+      if (MODE == MODE_GELU || MODE == MODE_GELU_GRAD) dkey = a.drop_thresh ? hs::drop_row_key(a.seed, grow) : 0u;
+      if (spw == 0) {  // more groups than slabs: stay in step with the accumulator stages
+        tc_fence_before();
+        mbar_arrive(&acc_empty[as]);
+      }
+      for (int s = g; s < S; s += NG) {
+        uint32_t acc[32];
+        tmem_ld32(tmem + lane_addr + (uint32_t)as * kStageCols + 32 * s, acc);
+        tmem_wait_ld();
+        if (s + NG >= S) {  // this thread's last slab of the tile is in registers
+          tc_fence_before();
+          mbar_arrive(&acc_empty[as]);
+        }
+        const int jc = n0 + 32 * s;
+#pragma unroll
+        for (int st = 0; st < kStores; ++st, ++cnt) {
+          const int reg = (int)(cnt % rw);
+          if (kAux) {
+            mbar_wait(&my_full[reg], ((uint32_t)(cnt / rw)) & 1);  // the aux sub-slab has landed
+          } else {
+            // the store that used this region rw uses ago must have read it
+            if (lane == 0) {
+              if (rw == 1) tma_store_wait_read<0>();
+              else if (rw == 2) tma_store_wait_read<1>();
+              else tma_store_wait_read<2>();
+            }
+            __syncwarp();
+          }
+          const uint32_t brow = my_u32 + reg * kRegion + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t p = brow + ((c ^ sw) << 4);
+            float4 o = make_float4(__uint_as_float(acc[4 * c + 0]), __uint_as_float(acc[4 * c + 1]),
+                                   __uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3]));
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.bias && !(MODE == MODE_GELU && st == 0) && jc + 4 * c < a.N)
+              bv = __ldg(reinterpret_cast<const float4*>(a.bias + jc + 4 * c));
+            if (MODE == MODE_PLAIN) {
+              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            } else if (MODE == MODE_ADD) {
+              const float4 x = lds_f4(p);
+              o.x += bv.x + x.x; o.y += bv.y + x.y; o.z += bv.z + x.z; o.w += bv.w + x.w;
+            } else if (MODE == MODE_GELU) {
+              if (st == 1) {
+                o.x = hs::gelu_fast(o.x + bv.x); o.y = hs::gelu_fast(o.y + bv.y);
+                o.z = hs::gelu_fast(o.z + bv.z); o.w = hs::gelu_fast(o.w + bv.w);
+                if (a.drop_thresh) {
+                  o.x = hs::drop_keep_elem(dkey, jc + 4 * c + 0, a.drop_thresh) ? o.x * a.drop_scale : 0.f;
+                  o.y = hs::drop_keep_elem(dkey, jc + 4 * c + 1, a.drop_thresh) ? o.y * a.drop_scale : 0.f;
+                  o.z = hs::drop_keep_elem(dkey, jc + 4 * c + 2, a.drop_thresh) ? o.z * a.drop_scale : 0.f;
+                  o.w = hs::drop_keep_elem(dkey, jc + 4 * c + 3, a.drop_thresh) ? o.w * a.drop_scale : 0.f;
+                }
+              }
+            } else {  // MODE_GELU_GRAD
+              const float4 z = lds_f4(p);
+              o.x *= hs::gelu_grad_fast(z.x + bv.x); o.y *= hs::gelu_grad_fast(z.y + bv.y);
+              o.z *= hs::gelu_grad_fast(z.z + bv.z); o.w *= hs::gelu_grad_fast(z.w + bv.w);
+              if (a.drop_thresh) {
+                o.x = hs::drop_keep_elem(dkey, jc + 4 * c + 0, a.drop_thresh) ? o.x * a.drop_scale : 0.f;
+                o.y = hs::drop_keep_elem(dkey, jc + 4 * c + 1, a.drop_thresh) ? o.y * a.drop_scale : 0.f;
+                o.z = hs::drop_keep_elem(dkey, jc + 4 * c + 2, a.drop_thresh) ? o.z * a.drop_scale : 0.f;
+                o.w = hs::drop_keep_elem(dkey, jc + 4 * c + 3, a.drop_thresh) ? o.w * a.drop_scale : 0.f;
+              }
+            }
+            sts_f4(p, o);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();  // all 32 rows of the sub-slab are in the staging region
+          if (lane == 0) {
+            tma_store_2d((MODE == MODE_GELU && st == 1) ? &map_d2 : &map_d, my + reg * kRegion, jc,
+                         (int)(tile * kBM) + 32 * q);
+            tma_store_commit();
+            if (kAux && cnt + rw < total) {  // refill this region with the aux sub-slab of the use rw ahead
+              tma_store_wait_read<0>();
+              issue_aux(cnt + rw);
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == E + kCvtWarps + 1) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// W (rows x cols fp32, row stride ld; element (r, c) = w[r * ld + c], or w[c * ld + r] when transposed) ->
+// out (rows, ceil(cols / 32), 64) bf16 = [hi(32) | lo(32)] per 32-wide chunk of the contraction axis (zero padded).
+__global__ void weight_split_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int rows, int cols, int ld,
+                                    int transposed) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    float v = 0.f;
+    if (!transposed) {
+      if (r0 + i < rows && c0 + tx < cols) v = w[(long long)(r0 + i) * ld + c0 + tx];
+      tile[i][tx] = v;
+    } else {  // coalesced along the source's fast axis (= output rows), transposed through shared memory
+      if (c0 + i < cols && r0 + tx < rows) v = w[(long long)(c0 + i) * ld + r0 + tx];
+      tile[tx][i] = v;
+    }
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    if (r0 + i >= rows) continue;
+    const float x = tile[i][tx];
+    const uint32_t hb = cvt_bf16x2(0.f, x) & 0xffffu;
+    const float h = __uint_as_float(hb << 16);
+    const uint32_t lb = cvt_bf16x2(0.f, x - h) & 0xffffu;
+    uint16_t* o = out + ((long long)(r0 + i) * gridDim.x + blockIdx.x) * 64;
+    o[tx] = (uint16_t)hb;
+    o[32 + tx] = (uint16_t)lb;
+  }
+}
+
+int make_map_bf16(CUtensorMap* m, const uint16_t* base, long long rows, long long cols, int box_cols, int box_rows) {
+  hs::tc::EncodeTiledFn enc = hs::tc::encode_fn();
+  if (!enc) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+  return HS_OK;
+}
+
+constexpr int kSmemAvail = 232448 - 1024 - 1024;  // dynamic shared memory minus alignment slack and the static barriers
+
+// column chunking + shared-memory plan: the widest balanced column chunk (<= 256) that leaves an A ring of >= 4 slots
+int plan(G3Args& a, int mode, int E) {
+  a.tiles = (a.T + kBM - 1) / kBM;
+  const int nk = (a.K + 31) / 32;
+  const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
+  const int rw_min = aux ? 2 : 1, rw_max = aux ? 3 : 2;
+  int first = (a.N + 255) / 256;                       // number of chunks
+  first = (((a.N + first - 1) / first) + 15) / 16 * 16;  // equal chunks, 16-column granularity
+  if (const char* e = getenv("HEALSWIN_GEMM3_NTILE")) {  // experiments only
+    const int v = atoi(e);
+    if (v >= 32 && v <= 256 && v % 16 == 0 && v < first) first = v;
+  }
+  const int cand[6] = {first, 192, 128, 96, 64, 32};
+  int best_ring = 0;
+  for (int ci = 0; ci < 6; ++ci) {
+    const int stride = cand[ci];
+    if (stride > first || (ci > 0 && stride == first)) continue;
+    const int box = (stride + 31) / 32 * 32;
+    const int w_slice = box * 128;
+    const long long staging_min = (long long)E * rw_min * kRegion;
+    const int resident = ((long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
+    const int wring = nk < 3 ? nk : 3;
+    const long long w_bytes = (long long)(resident ? nk : wring) * w_slice;
+    long long left = kSmemAvail - w_bytes - staging_min;
+    int ring = left > 0 ? (int)(left / kChunk) : 0;
+    if (ring > kMaxRing) ring = kMaxRing;
+    if (ring <= best_ring) continue;
+    best_ring = ring;
+    a.n_stride = stride;
+    a.n_box = box;
+    a.n_chunks = (a.N + stride - 1) / stride;
+    a.resident = resident;
+    a.wring = wring;
+    a.ring = ring;
+    left -= (long long)ring * kChunk;
+    a.rw = rw_min + (int)(left / ((long long)E * kRegion));
+    if (a.rw > rw_max) a.rw = rw_max;
+    if (ring >= 4) break;
+  }
+  if (best_ring < 2) return hs::fail(HS_ERR_UNSUPPORTED, "hs_gemm3: no shared-memory plan for N=%d K=%d", a.N, a.K);
+  return HS_OK;
+}
+
+template <int E>
+size_t smem_bytes(const G3Args& a) {
+  const int nk = (a.K + 31) / 32, w_slice = a.n_box * 128;
+  return (size_t)(a.resident ? nk : a.wring) * w_slice + (size_t)a.ring * kChunk + (size_t)E * a.rw * kRegion + 1024;
+}
+
+struct Maps {
+  CUtensorMap a, w, aux, d, d2;
+};
+
+template <int E, int MODE>
+int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, float* d_dev, float* d2_dev, G3Args& a,
+           cudaStream_t stream) {
+  int rc;
+  if ((rc = plan(a, MODE, E))) return rc;
+  Maps m;
+  if ((rc = hs::tc::make_map(&m.a, a_dev, a.T, a.K, CU_TENSOR_MAP_SWIZZLE_128B, 32, kBM))) return rc;
+  if ((rc = make_map_bf16(&m.w, w_dev, a.N, 2ll * ((a.K + 31) / 32 * 32), 64, a.n_box))) return rc;
+  if ((rc = hs::tc::make_map(&m.d, d_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
+  m.aux = m.d;
+  m.d2 = m.d;
+  if (aux_dev && (rc = hs::tc::make_map(&m.aux, aux_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
+  if (d2_dev && (rc = hs::tc::make_map(&m.d2, d2_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
+  const size_t smem = smem_bytes<E>(a);
+  HS_CUDA(cudaFuncSetAttribute(gemm3_kernel<E, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_chunk = hs::tc::sm_count() / a.n_chunks;
+  if (per_chunk < 1) per_chunk = 1;
+  if (per_chunk > a.tiles) per_chunk = (int)a.tiles;
+  gemm3_kernel<E, MODE><<<a.n_chunks * per_chunk, (E + kCvtWarps + 3) * 32, smem, stream>>>(m.a, m.w, m.aux, m.d, m.d2, a);
+  HS_LAUNCH_CHECK();
+  return HS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hs_weight_split(const float* w, int rows, int cols, int ld, int transposed, uint16_t* out, void* stream) {
+  HS_REQUIRE(w && out && rows > 0 && cols > 0 && ld > 0, "hs_weight_split: bad arguments");
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  weight_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, out, rows, cols, ld, transposed);
+  HS_LAUNCH_CHECK();
+  return HS_OK;
+}
+
+int hs_gemm3_supported(int64_t T, int N, int K) {
+  return (T >= 1 && N >= 8 && K >= 4 && N % 4 == 0 && K % 4 == 0 && K <= 8192 && N <= 65536) ? 1 : 0;
+}
+
+int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
+             float* d2_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream) {
+  HS_REQUIRE(a_dev && wsplit_dev && d_dev && T > 0, "hs_gemm3: bad arguments");
+  HS_REQUIRE(mode >= MODE_PLAIN && mode <= MODE_GELU_GRAD, "hs_gemm3: unknown mode %d", mode);
+  HS_REQUIRE(drop >= 0.f && drop < 1.f, "hs_gemm3: drop must be in [0, 1), got %f", drop);
+  if (!hs_gemm3_supported(T, N, K))
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_gemm3: shape T=%lld N=%d K=%d is not covered (N, K multiples of 4)",
+                    (long long)T, N, K);
+  const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
+  HS_REQUIRE(!aux || aux_dev, "hs_gemm3: mode %d needs the aux tensor", mode);
+  HS_REQUIRE(mode != MODE_GELU || d2_dev, "hs_gemm3: MODE_GELU needs the second output");
+  HS_REQUIRE(!((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(wsplit_dev) |
+                reinterpret_cast<uintptr_t>(bias_dev) | reinterpret_cast<uintptr_t>(aux_dev) |
+                reinterpret_cast<uintptr_t>(d_dev) | reinterpret_cast<uintptr_t>(d2_dev)) & 15),
+             "hs_gemm3: tensors must be 16-byte aligned");
+  G3Args a{};
+  a.bias = bias_dev; a.T = T; a.N = N; a.K = K;
+  a.drop_thresh = drop > 0.f ? hs::drop_thresh(drop) : 0u;
+  a.drop_scale = 1.0f / (1.0f - drop);
+  a.seed = seed;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (mode) {
+    case MODE_PLAIN: return launch<8, MODE_PLAIN>(a_dev, wsplit_dev, nullptr, d_dev, nullptr, a, st);
+    case MODE_ADD: return launch<8, MODE_ADD>(a_dev, wsplit_dev, aux_dev, d_dev, nullptr, a, st);
+    case MODE_GELU: return launch<16, MODE_GELU>(a_dev, wsplit_dev, nullptr, d_dev, d2_dev, a, st);
+    default:
+      // the GELU' arithmetic wants 16 epilogue warps where the launch is HBM-bound (short contraction); with a long
+      // contraction it is tensor-bound and the shared memory is better spent on the operand rings
+      if (K <= 256) return launch<16, MODE_GELU_GRAD>(a_dev, wsplit_dev, aux_dev, d_dev, nullptr, a, st);
+      return launch<8, MODE_GELU_GRAD>(a_dev, wsplit_dev, aux_dev, d_dev, nullptr, a, st);
+  }
+}
+
+}  // extern "C"

@@ -6,6 +6,7 @@ tensors are not on a CUDA device.
 """
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -19,15 +20,18 @@ class _Stats:
 
     def __init__(self):
         self.launches = 0
+        self.by_name = {}
         self.timing = False
         self.events = {}
 
     def reset(self):
         self.launches = 0
+        self.by_name = {}
         self.events = {}
 
     def launch(self, name, fn, *args, tag=None):
         self.launches += 1
+        self.by_name[name] = self.by_name.get(name, 0) + 1
         if self.timing and tag is not None:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -328,30 +332,147 @@ class BiasGeluFn(torch.autograd.Function):
 
 
 def bias_gelu(z, bias, drop=0.0, seed=None):
+    """``dropout(GELU(z + bias))``: one fused launch for widths the kernel covers (C % 4 == 0, C <= 4096), torch ops for
+    the rest (e.g. embed_dim 192 with four stages gives a hidden width of 6144)."""
     drop = float(drop)
+    if not (z.is_cuda and lib.hs_bias_gelu_supported(z.numel() // z.shape[-1], z.shape[-1])):
+        h = torch.nn.functional.gelu(z if bias is None else z + bias)
+        return torch.nn.functional.dropout(h, drop, True) if drop > 0.0 else h
     if drop > 0.0 and seed is None:
         seed = _next_dropout_seed()
     return BiasGeluFn.apply(z, bias, drop, int(seed or 0))
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# Library GEMMs (cuBLAS through torch): the one place the drop-in modules call a dense linear through, so that a
-# hand-written GEMM can replace it later.  Whether they run in fp32 or TF32 is torch's global switch
-# (torch.backends.cuda.matmul.allow_tf32; bench.py turns it on, as torch <= 1.11 -- the reference's pinned 1.8 -- did by
-# default).  Measured whole-network forward error vs the fp32 oracle (scripts/tf32_model_check.py): 3.5-5.5e-4 with fp32
-# GEMMs, 1.1-1.4e-3 with TF32 GEMMs (cuBLAS rounds its TF32 operands to nearest, so there is no truncation bias to
-# compensate there; keeping only the qkv projection in fp32 gains 6 % error for 28 % time: not worth it).
+# Dense linears.  Forward and input-gradient products run on the hand-written bf16x3 tensor-core GEMM
+# (csrc/hs_gemm3_tc.cu: every fp32 operand split into two bf16 terms, three MMAs, ~2^-16 relative per product -- the
+# network output stays at fp32-GEMM accuracy, which the TF32 library GEMMs they replace did not: 1.1-1.4e-3 against a
+# tolerance of 1e-3), with the bias, the residual-shortcut gradient and the GELU of the MLP in their epilogues; weight
+# gradients on the token-split TF32 kernel (csrc/hs_wgrad_tc.cu).  HEALSWIN_GEMM=library (or set_gemm_mode) sends all
+# of them through cuBLAS instead (diagnostics: torch's global allow_tf32 switch then decides their precision).
 
-
+_GEMM_MODE = os.environ.get("HEALSWIN_GEMM", "bf16x3")
 _CUSTOM_WGRAD = os.environ.get("HEALSWIN_CUSTOM_WGRAD", "1") == "1"
+_FUSED_MLP = os.environ.get("HEALSWIN_FUSED_MLP", "1") == "1"
+_TF32_MLP_DGRAD = os.environ.get("HEALSWIN_TF32_MLP_DGRAD", "1") == "1"
+
+
+def set_gemm_mode(mode: str) -> None:
+    """"bf16x3": the hand-written tensor-core GEMMs (default); "library": cuBLAS through torch."""
+    global _GEMM_MODE
+    assert mode in ("bf16x3", "library"), mode
+    _GEMM_MODE = mode
+
+
+def get_gemm_mode() -> str:
+    return _GEMM_MODE
+
+
+_SPLITS = {}  # (id(weight), transposed) -> (weakref, version, data_ptr, split tensor)
+
+
+def split_weight(weight, transposed=False):
+    """The bf16 [hi | lo] operand of ``weight`` (N, K) for hs_gemm3: (N, 2 * ceil32(K)) for the forward, or with
+    ``transposed`` (K, 2 * ceil32(N)) for the input gradient.  Cached per parameter and redone when the parameter's
+    version counter moves (optimizer step, load_state_dict, DDP broadcast); the buffer is reused so that its address is
+    stable.  Call ``invalidate_weight_splits()`` after writing through ``.data``."""
+    w = weight.detach()
+    N, K = w.shape
+    key = (id(weight), bool(transposed))
+    ent = _SPLITS.get(key)
+    ver = weight._version
+    if ent is not None and ent[0]() is weight and ent[2] == w.data_ptr():
+        if ent[1] == ver:
+            return ent[3]
+        out = ent[3]
+    else:
+        rows, cols = (K, N) if transposed else (N, K)
+        out = torch.empty((rows, 2 * ((cols + 31) // 32 * 32)), device=w.device, dtype=torch.bfloat16)
+    rows, cols = (K, N) if transposed else (N, K)
+    STATS.launch("weight_split", lib.hs_weight_split, ptr(_f32c(w)), rows, cols, K, 1 if transposed else 0, ptr(out),
+                 current_stream())
+    if weight.is_leaf:  # views of a parameter (patch embedding) are new objects every call: not worth caching
+        if len(_SPLITS) > 1024:
+            for k in [k for k, v in _SPLITS.items() if v[0]() is None]:
+                del _SPLITS[k]
+        _SPLITS[key] = (weakref.ref(weight), ver, w.data_ptr(), out)
+    return out
+
+
+def invalidate_weight_splits() -> None:
+    _SPLITS.clear()
+
+
+def _on_device(t) -> bool:
+    return t.is_cuda
+
+
+def gemm3_ok(x, weight) -> bool:
+    """Whether ``F.linear(x, weight)`` is covered by the hand-written GEMM."""
+    return bool(_GEMM_MODE == "bf16x3" and _on_device(x) and x.dtype == torch.float32 and weight.dtype == torch.float32
+                and weight.dim() == 2 and weight.is_contiguous()
+                and lib.hs_gemm3_supported(x.numel() // x.shape[-1], weight.shape[0], weight.shape[1]))
+
+
+def _dgrad_ok(dy2, weight) -> bool:
+    return bool(_GEMM_MODE == "bf16x3" and _on_device(dy2) and weight.is_contiguous() and weight.dtype == torch.float32
+                and lib.hs_gemm3_supported(dy2.shape[0], weight.shape[1], weight.shape[0]))
+
+
+def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, seed=0):
+    """hs_gemm3 on a (T, K) activation and a split weight; returns d, or (d, d2) for GEMM_GELU."""
+    T, K = a2.shape
+    d = torch.empty((T, N), device=a2.device, dtype=torch.float32)
+    d2 = torch.empty_like(d) if mode == _lib.GEMM_GELU else None
+    STATS.launch("gemm3", lib.hs_gemm3, ptr(a2), ptr(wsplit), ptr(bias), ptr(aux), ptr(d), ptr(d2), T, N, K, mode,
+                 C.c_float(drop), C.c_uint64(seed), current_stream(), tag=(T, N, K, mode))
+    return (d, d2) if mode == _lib.GEMM_GELU else d
+
+
+def _gemm_fwd(x2, weight, bias):
+    """x2 (T, K) @ weight (N, K)^T + bias."""
+    if gemm3_ok(x2, weight):
+        return _gemm3(x2, split_weight(weight), weight.shape[0], _f32c(bias))
+    return torch.nn.functional.linear(x2, weight, bias)
+
+
+def _dgrad(dy2, weight, d_pass, xshape):
+    """dy2 @ weight (+ the gradient that reached the forked shortcut output), shaped like the input.  The shortcut
+    gradient is added in the GEMM's epilogue (GEMM_ADD): no accumulation pass over the activation."""
+    N, K = weight.shape
+    c = None if d_pass is None else _f32c(d_pass).reshape(-1, K)
+    if _dgrad_ok(dy2, weight):
+        dx = _gemm3(dy2, split_weight(weight, transposed=True), K, None, c,
+                    _lib.GEMM_PLAIN if c is None else _lib.GEMM_ADD)
+    else:
+        dx = dy2 @ weight if c is None else torch.addmm(c, dy2, weight)
+    return dx.view(xshape)
+
+
+def _wgrad(dy2, x2, need_bias):
+    """(dW, db or None) of a linear: the token-split tensor-core kernel where it covers the shape, else the library."""
+    T, N = dy2.shape
+    K = x2.shape[1]
+    db = None
+    cover = lib.hs_linear_wgrad_supported(T, N, K) if (_CUSTOM_WGRAD and _on_device(dy2)) else 0
+    if cover:
+        dw = torch.zeros((N, K), device=x2.device, dtype=torch.float32)
+        if need_bias and cover == 2:  # bias gradient in the same pass over dy
+            db = torch.zeros((N,), device=x2.device, dtype=torch.float32)
+        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, 0,
+                     current_stream(), tag=(T, N, K))
+    else:
+        dw = dy2.t() @ x2
+    if need_bias and db is None:
+        db = dy2.sum(0)
+    return dw, db
 
 
 class _LinearFn(torch.autograd.Function):
-    """F.linear whose weight gradient dW = dY^T X runs on the hand-written token-split tcgen05 kernel
-    (csrc/hs_wgrad_tc.cu); forward and input gradient stay library GEMMs (they already sit on the HBM roofline at the
-    large stages, scripts/wgrad_check.py).  With ``fork`` the input is returned as a second output -- the shortcut of a
-    residual block whose branch starts with this linear -- and the shortcut's gradient is folded into the input-gradient
-    GEMM (beta = 1) instead of a separate accumulation pass over the activation."""
+    """F.linear on this library's GEMMs: forward and input gradient on the bf16x3 kernel (bias in the epilogue), weight
+    (and bias) gradient on the token-split kernel.  With ``fork`` the input is returned as a second output -- the
+    shortcut of a residual block whose branch starts with this linear -- and the shortcut's gradient is added in the
+    input-gradient GEMM's epilogue instead of a separate accumulation pass over the activation."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, fork):
@@ -373,76 +494,26 @@ class _LinearFn(torch.autograd.Function):
             dx = _dgrad(dy2, weight, d_pass, x.shape)
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if ctx.needs_input_grad[1]:
-            x2 = _f32c(x).reshape(-1, K)
-            T = x2.shape[0]
-            dw = torch.zeros((N, K), device=x.device, dtype=torch.float32)
-            if need_b and lib.hs_linear_wgrad_supported(T, N, K) == 2:  # bias gradient in the same pass over dy
-                db = torch.zeros((N,), device=x.device, dtype=torch.float32)
-            STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, 0,
-                         current_stream(), tag=(T, N, K))
-        if need_b and db is None:
+            dw, db = _wgrad(dy2, _f32c(x).reshape(-1, K), need_b)
+        elif need_b:
             db = dy2.sum(0)
         return dx, dw, db, None
 
 
-_LT_WORKSPACE = {}
-_LT_GEMM = os.environ.get("HEALSWIN_LT_GEMM", "1") == "1"
-
-
-def _lt_workspace(device):
-    ws = _LT_WORKSPACE.get(device)
-    if ws is None:
-        ws = _LT_WORKSPACE[device] = torch.empty(32 << 20, dtype=torch.uint8, device=device)
-    return ws
-
-
-def _gemm_fwd(x2, weight, bias):
-    """x2 (T, K) @ weight (N, K)^T + bias as a library GEMM.  On the custom (TF32) path it is the cuBLASLt heuristic pick
-    with a workspace (hs_linear_fwd): same arithmetic as torch's cuBLAS call, measurably faster for several of this
-    network's tall-skinny shapes (scripts/gemm_lt_check.py).  A library GEMM: not counted in STATS."""
-    if not _LT_GEMM:
-        return torch.nn.functional.linear(x2, weight, bias)
-    y = torch.empty((x2.shape[0], weight.shape[0]), device=x2.device, dtype=torch.float32)
-    ws = _lt_workspace(x2.device)
-    check(lib.hs_linear_fwd(ptr(x2), ptr(weight), ptr(bias), ptr(y), x2.shape[0], weight.shape[0], weight.shape[1],
-                            ptr(ws), ws.numel(), current_stream()))
-    return y
-
-
-def _dgrad(dy2, weight, d_pass, xshape):
-    """dy2 @ weight (+ the gradient that reached the forked shortcut output), shaped like the input.  With a shortcut
-    gradient the library GEMM reads it as its C operand and writes a fresh D (hs_linear_dgrad_acc): no accumulation pass."""
-    if d_pass is None and not _LT_GEMM:
-        return (dy2 @ weight).view(xshape)
-    c = None if d_pass is None else _f32c(d_pass).reshape(-1, weight.shape[1])
-    ws = _lt_workspace(dy2.device)
-    dx = torch.empty((dy2.shape[0], weight.shape[1]), device=dy2.device, dtype=torch.float32)
-    # a library GEMM, not one of this library's kernels: not counted in STATS
-    check(lib.hs_linear_dgrad_acc(ptr(dy2), ptr(weight), ptr(c), ptr(dx), dy2.shape[0], weight.shape[0], weight.shape[1],
-                                  ptr(ws), ws.numel(), current_stream()))
-    return dx.view(xshape)
-
-
-_FUSED_MLP = os.environ.get("HEALSWIN_FUSED_MLP", "1") == "1"
-
-
 class _MlpFn(torch.autograd.Function):
-    """``fc2(dropout(GELU(fc1(x) + b1)))`` WITHOUT fc2's bias, as one autograd node, so that the backward never
-    materialises the (T, 4C) hidden gradient: d(fc1 output) comes from the fused dgrad + GELU' kernel
-    (csrc/hs_mlp_dgrad_tc.cu), both weight gradients (and fc1's bias gradient) from the token-split wgrad kernel; the two
-    forward GEMMs and the final input gradient are library GEMMs."""
+    """``fc2(dropout(GELU(fc1(x) + b1)))`` WITHOUT fc2's bias, as one autograd node.  Forward: fc1 with the bias add,
+    GELU and dropout in its epilogue (z and h each written once, hs_gemm3 GEMM_GELU), then fc2.  Backward: the (T, 4C)
+    hidden gradient is never materialised -- d(fc1 output) = (dy @ W2) * GELU'(z + b1) * mask comes out of one GEMM
+    epilogue (csrc/hs_mlp_dgrad_tc.cu where it covers the shape, else hs_gemm3 GEMM_GELU_GRAD); both weight gradients
+    (and fc1's bias gradient) from the token-split wgrad kernel."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, drop, seed, fork):
         ctx.set_materialize_grads(False)
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
-        T, J = x2.shape[0], w1.shape[0]
-        z = _gemm_fwd(x2, w1, None)
-        h = torch.empty_like(z)
-        STATS.launch("bias_gelu_fwd", lib.hs_bias_gelu_fwd, ptr(z), ptr(b1), C.c_float(drop), C.c_uint64(seed), ptr(h),
-                     T, J, current_stream(), tag=(T, J))
-        y = _gemm_fwd(h, w2, None)
+        z, h = _gemm3(x2, split_weight(w1), w1.shape[0], _f32c(b1), None, _lib.GEMM_GELU, drop, seed)
+        y = _gemm3(h, split_weight(w2), w2.shape[0])
         ctx.save_for_backward(x2, w1, b1, w2, z, h)
         ctx.drop = (float(drop), int(seed))
         ctx.xshape = x.shape
@@ -457,33 +528,28 @@ class _MlpFn(torch.autograd.Function):
         T, K = x2.shape
         J, Cout = w1.shape[0], w2.shape[0]
         dy2 = _f32c(dy).reshape(T, Cout)
-        stream = current_stream()
-        dw2 = torch.zeros((Cout, J), device=x2.device, dtype=torch.float32)
-        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(h), ptr(dw2), None, T, Cout, J, 0, stream,
-                     tag=(T, Cout, J))
-        dz = torch.empty_like(z)
-        STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1), C.c_float(ctx.drop[0]),
-                     C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, 0, stream, tag=(T, Cout, J))
-        dw1 = torch.zeros((J, K), device=x2.device, dtype=torch.float32)
-        db1 = torch.zeros((J,), device=x2.device, dtype=torch.float32)
-        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dz), ptr(x2), ptr(dw1), ptr(db1), T, J, K, 0, stream,
-                     tag=(T, J, K))
+        dw2, _ = _wgrad(dy2, h, False)
+        if _TF32_MLP_DGRAD and lib.hs_mlp_dgrad_gelu_supported(T, Cout, J):
+            dz = torch.empty_like(z)
+            STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1),
+                         C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, 0, current_stream(),
+                         tag=(T, Cout, J))
+        else:
+            dz = _gemm3(dy2, split_weight(w2, transposed=True), J, _f32c(b1), z, _lib.GEMM_GELU_GRAD, *ctx.drop)
+        dw1, db1 = _wgrad(dz, x2, True)
         dx = _dgrad(dz, w1, d_pass, ctx.xshape) if ctx.needs_input_grad[0] else None
         return dx, dw1, db1, dw2, None, None, None
 
 
 def mlp_supported(x, fc1, fc2):
-    """Whether ``mlp_core`` covers this MLP: TF32 GEMMs enabled, training, and every shape inside the fused kernels."""
-    if not (_FUSED_MLP and _CUSTOM_WGRAD and x.is_cuda and x.dtype == torch.float32 and torch.is_grad_enabled()
-            and torch.backends.cuda.matmul.allow_tf32 and fc1.bias is not None):
+    """Whether ``mlp_core`` covers this MLP (both linears inside the hand-written GEMM)."""
+    if not (_FUSED_MLP and fc1.bias is not None and gemm3_ok(x, fc1.weight)):
         return False
-    w1, w2 = fc1.weight, fc2.weight
-    if not (w1.requires_grad and w2.requires_grad and fc1.bias.requires_grad and w1.is_contiguous() and w2.is_contiguous()):
-        return False
-    T, K = x.numel() // x.shape[-1], x.shape[-1]
-    J, Cout = w1.shape[0], w2.shape[0]
-    return bool(lib.hs_mlp_dgrad_gelu_supported(T, Cout, J) and lib.hs_linear_wgrad_supported(T, Cout, J)
-                and lib.hs_linear_wgrad_supported(T, J, K) == 2)
+    T = x.numel() // x.shape[-1]
+    w2 = fc2.weight
+    return bool(w2.is_contiguous() and w2.dtype == torch.float32
+                and lib.hs_gemm3_supported(T, w2.shape[0], w2.shape[1])
+                and lib.hs_gemm3_supported(T, w2.shape[1], w2.shape[0]))
 
 
 def mlp_core(x, fc1, fc2, drop=0.0, seed=None, fork=False):
@@ -496,13 +562,10 @@ def mlp_core(x, fc1, fc2, drop=0.0, seed=None, fork=False):
 
 
 def linear(x, weight, bias=None, fork=False):
-    """``F.linear``.  When TF32 matmuls are enabled and the shape is covered, the weight gradient uses the hand-written
-    kernel; everything else is the library GEMM.  ``fork=True`` returns ``(y, shortcut)`` where ``shortcut`` is ``x`` for
-    the residual path of a block whose branch starts with this linear: on the custom path its gradient is added inside
-    the input-gradient GEMM."""
-    if (_CUSTOM_WGRAD and x.is_cuda and x.dtype == torch.float32 and weight.requires_grad and torch.is_grad_enabled()
-            and torch.backends.cuda.matmul.allow_tf32 and weight.dim() == 2 and weight.is_contiguous()
-            and lib.hs_linear_wgrad_supported(x.numel() // x.shape[-1], weight.shape[0], weight.shape[1])):
+    """``F.linear`` on the hand-written GEMMs where the shape is covered (feature dimensions multiples of 4), else
+    through torch.  ``fork=True`` returns ``(y, shortcut)`` where ``shortcut`` is ``x`` for the residual path of a block
+    whose branch starts with this linear: its gradient is added inside the input-gradient GEMM."""
+    if gemm3_ok(x, weight):
         return _LinearFn.apply(x, weight, bias, bool(fork))
     y = torch.nn.functional.linear(x, weight, bias)
     return (y, x) if fork else y

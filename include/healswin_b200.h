@@ -14,7 +14,8 @@
  *     exit()/abort().
  *   - "host" pointers are plain CPU memory, "dev" pointers are CUDA device memory of
  *     the current device.  All device entry points take the CUDA stream explicitly
- *     (cudaStream_t passed as void*), keep no mutable global state and are
+ *     (cudaStream_t passed as void*), keep no mutable global state (only immutable
+ *     caches: the driver entry point for TMA descriptors, the SM count) and are
  *     re-entrant (forward runs on the main thread, backward on the autograd thread).
  *   - tensors are dense row-major fp32 unless said otherwise.
  */
@@ -163,7 +164,9 @@ int hs_layernorm_bwd(const float* dy_dev, const float* x_dev, const float* pre_b
  * h = dropout(GELU(z + bias)) with the exact erf GELU of nn.GELU (swin_hp_transformer.py:21-44, Mlp: fc1 -> act -> drop),
  * z: (rows, C) the bias-free fc1 GEMM output, bias: (C) or NULL, drop = 0 disables the dropout (mask: a pure function of
  * (seed, row, col)); and its adjoint dz = dh * mask * GELU'(z + bias), dbias (C) += column sums of dz (may be NULL).
+ * Covered: C % 4 == 0 and C <= 4096 (hs_bias_gelu_supported); other widths return HS_ERR_UNSUPPORTED.
  */
+int hs_bias_gelu_supported(int64_t rows, int C); /* 1 when C % 4 == 0 and C <= 4096; else the caller uses torch ops */
 int hs_bias_gelu_fwd(const float* z_dev, const float* bias_dev, float drop, uint64_t seed, float* h_dev, int64_t rows,
                      int C, void* stream);
 int hs_bias_gelu_bwd(const float* dh_dev, const float* z_dev, const float* bias_dev, float drop, uint64_t seed,
@@ -175,7 +178,7 @@ int hs_bias_gelu_bwd(const float* dh_dev, const float* z_dev, const float* bias_
  * and optionally the bias gradient in the same pass:   dbias[n] += sum_t dy[t][n]   (dbias may be NULL).
  * TF32 tensor-core kernel with the token range split over the SMs; dw / dbias are ACCUMULATED into (zero them for a
  * plain gradient).  hs_linear_wgrad_supported returns 0 when the shape is not covered (it then stays with the library
- * GEMM; covered: min(N, K) a multiple of 32 and <= 256, T >= 4096), 1 when dw is covered, 2 when dbias can be fused too
+ * GEMM; covered: min(N, K) a multiple of 32 and <= 512, T >= 4096), 1 when dw is covered, 2 when dbias can be fused too
  * (N >= K, K <= 224).  flags: HS_ATTN_NO_TRUNC_COMP only.
  */
 int hs_linear_wgrad_supported(int64_t T, int N, int K);
@@ -197,24 +200,31 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
                       uint64_t seed, float* dz_dev, int64_t T, int C, int J, uint32_t flags, void* stream);
 
 /*
- * Input gradient of nn.Linear with the gradient of a residual shortcut folded in (autograd of x + branch(x) where the
- * branch starts with a Linear: swin_hp_transformer.py:131 / 21-44 inside :333-338):
- *     dx[t][k] = sum_n dy[t][n] * w[n][k] + c[t][k]        dy: (T, N), w: (N, K), c and dx: (T, K), fp32 row-major
- * c may be NULL (plain dgrad) or equal to dx (in place).  Library GEMM (cuBLASLt, TF32 tensor cores, out-of-place C/D):
- * the only point of this entry is that c is read by the GEMM epilogue instead of a separate accumulation pass.
- * workspace: device scratch for the library (may be NULL / 0).  cuBLASLt is loaded with dlopen at first use.
+ * Dense linear layers on the tensor cores at fp32-class accuracy (csrc/hs_gemm3_tc.cu): every fp32 operand is split
+ * into two bf16 terms and the product accumulated in fp32 from three tcgen05 kind::f16 MMAs (hi*hi + lo*hi + hi*lo),
+ * ~2^-16 relative per product -- this is what replaces the library (cuBLASLt TF32) GEMMs behind F.linear at
+ * swin_hp_transformer.py:131-135 (qkv), :172 (proj), :21-44 (Mlp.fc1 / fc2), :394 (PatchMerging.reduction), :421
+ * (PatchExpand.expand), :444 (FinalPatchExpand_X4.expand), :774 (concat_back_dim) and their input gradients.
+ *
+ * hs_weight_split prepares the weight operand once per optimizer step:
+ *     out[r][c / 32][0:32] = bf16_hi(m(r, c)),  out[r][c / 32][32:64] = bf16_lo(m(r, c))      out: (rows, 2 * cols) bf16
+ * with m(r, c) = w[r * ld + c] (transposed = 0: the forward operand of a (rows = N, cols = K) weight) or
+ * m(r, c) = w[c * ld + r] (transposed = 1: the input-gradient operand, rows = K, cols = N, ld = K); the chunk count is
+ * ceil(cols / 32) and the tail of a ragged last chunk is zero, i.e. out is (rows, 2 * ceil32(cols)).
+ *
+ * hs_gemm3:   acc[t][n] = sum_k a[t][k] * m(n, k)            a: (T, K) fp32, wsplit: (N, 2 ceil32(K)) bf16
+ *   mode 0 (plain)      d = acc + bias
+ *   mode 1 (add)        d = acc + bias + aux                  aux: (T, N) fp32, e.g. the residual-shortcut gradient
+ *   mode 2 (gelu)       d = acc,  d2 = dropout(GELU(acc + bias))      Mlp fc1 + act + drop (:39-41); exact erf GELU
+ *   mode 3 (gelu grad)  d = acc * GELU'(aux + bias) * dropmask        aux = the bias-free fc1 output z
+ * bias: (N) or NULL.  drop / seed: the element dropout of modes 2 / 3 (mask = pure function of (seed, row, col), as
+ * hs_bias_gelu_fwd).  All of d, d2, aux are (T, N) fp32 row-major.  hs_gemm3_supported: N, K multiples of 4 (TMA row pitch);
+ * ragged 32-wide chunks are zero-filled on load and clipped on store by the TMA unit.
  */
-int hs_linear_dgrad_acc(const float* dy_dev, const float* w_dev, const float* c_dev, float* dx_dev, int64_t T, int N, int K,
-                        void* workspace_dev, uint64_t workspace_bytes, void* stream);
-
-/*
- * Forward of nn.Linear as a library GEMM (cuBLASLt, TF32 tensor cores, bias in the epilogue):
- *     y[t][n] = sum_k x[t][k] * w[n][k] + bias[n]          x: (T, K), w: (N, K), bias: (N) or NULL, y: (T, N)
- * Same plumbing as hs_linear_dgrad_acc; exists because the heuristic-selected cuBLASLt algorithm (with workspace) is
- * faster than the cuBLAS default for the tall-skinny shapes of this network (scripts/gemm_lt_check.py).
- */
-int hs_linear_fwd(const float* x_dev, const float* w_dev, const float* bias_dev, float* y_dev, int64_t T, int N, int K,
-                  void* workspace_dev, uint64_t workspace_bytes, void* stream);
+int hs_weight_split(const float* w_dev, int rows, int cols, int ld, int transposed, uint16_t* out_dev, void* stream);
+int hs_gemm3_supported(int64_t T, int N, int K);
+int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
+             float* d2_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream);
 
 /*
  * Decoder tail, fused: logits = Conv1d_1x1(LayerNorm(x)) (FinalPatchExpand_X4.norm + SwinHPTransformerSys.output,

@@ -8,7 +8,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
-from tests.util import build_product_model  # noqa: E402
+from heal_swin_b200.factory import build_hp_model as build_product_model  # noqa: E402
 
 
 def main():

@@ -22,7 +22,10 @@ def _exact_fp32_kernels():
     from heal_swin_b200 import ops
 
     ops.set_attention_precision("fp32")
+    prev = ops._CUSTOM_WGRAD
+    ops._CUSTOM_WGRAD = False  # fp32 library weight gradients: the TF32 wgrad kernel has its own file and tolerance
     yield
+    ops._CUSTOM_WGRAD = prev
     ops.set_attention_precision("tf32")
 
 

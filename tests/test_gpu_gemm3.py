@@ -1,0 +1,133 @@
+"""GPU parity of the bf16x3 tensor-core GEMM (csrc/hs_gemm3_tc.cu) through the C-ABI against an fp64 product.
+Tolerance 2e-5 relative L2: every operand is split into two bf16 terms (residual <= 2^-17) and the lo*lo term is dropped,
+so each product is good to ~2^-16 -- fp32-class, unlike TF32 (2e-4 on the same data).  Covers all four epilogue modes,
+ragged token counts (TMA clips the last 128-row tile), feature dimensions that are not multiples of 32 (zero-filled
+chunk tails, clipped stores), resident and streamed weight chunks, several column chunks, and the dropout masks."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+
+def _split(w, transposed=False):
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    w = w.contiguous()
+    n, k = w.shape
+    rows, cols = (k, n) if transposed else (n, k)
+    out = torch.empty((rows, 2 * ((cols + 31) // 32 * 32)), device=w.device, dtype=torch.bfloat16)
+    check(lib.hs_weight_split(ptr(w), rows, cols, k, 1 if transposed else 0, ptr(out), current_stream()))
+    return out
+
+
+def _gemm3(a, ws, N, bias=None, aux=None, mode=0, drop=0.0, seed=0):
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    T, K = a.shape
+    d = torch.full((T, N), float("nan"), device=a.device)
+    d2 = torch.full((T, N), float("nan"), device=a.device) if mode == 2 else None
+    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), T, N, K, mode, C.c_float(drop),
+                       C.c_uint64(seed), current_stream()))
+    return (d, d2) if mode == 2 else d
+
+
+def _data(T, N, K, seed=0):
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(seed + T + 3 * N + 7 * K)
+    a = torch.randn(T, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    b = torch.randn(N, generator=g).to(dev)
+    return a, w, b
+
+
+def test_weight_split_layout_and_accuracy():
+    """hi + lo reproduces the weight to 2^-16; layout (rows, chunks, [hi 32 | lo 32]); transposed form; zero padding."""
+    dev = torch.device("cuda:0")
+    w = torch.randn(40, 72, generator=torch.Generator().manual_seed(0)).to(dev)
+    for transposed in (False, True):
+        m = w.t() if transposed else w
+        rows, cols = m.shape
+        out = _split(w, transposed).view(rows, -1, 64).float()
+        assert out.shape[1] == (cols + 31) // 32
+        hi, lo = out[:, :, :32].reshape(rows, -1), out[:, :, 32:].reshape(rows, -1)
+        assert torch.equal(hi[:, :cols], m.bfloat16().float())  # hi is the round-to-nearest bf16
+        assert float((hi + lo)[:, :cols].sub(m).abs().max() / m.abs().max()) < 2.0 ** -16
+        assert float(hi[:, cols:].abs().max()) == 0.0 and float(lo[:, cols:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("T,N,K", [
+    (128, 32, 32), (300, 96, 96), (1000, 288, 64),        # ragged tokens, two column chunks (160 + 128)
+    (4096, 384, 96), (4096, 96, 384),                     # resident W / streamed W (12 K slices)
+    (2048, 1152, 384), (1024, 768, 3072),                 # 5 column chunks; 96 K chunks
+    (777, 144, 48), (512, 96, 12), (640, 200, 100),       # feature dims that are not multiples of 32
+])
+def test_plain_and_add_match_fp64(T, N, K):
+    a, w, b = _data(T, N, K)
+    want = a.double() @ w.double().t()
+    got = _gemm3(a, _split(w), N, b)
+    assert rel_err(got.cpu(), (want + b.double()).cpu()) < TOL
+    got = _gemm3(a, _split(w), N)
+    assert rel_err(got.cpu(), want.cpu()) < TOL
+    aux = torch.randn(T, N, device=a.device)
+    got = _gemm3(a, _split(w), N, b, aux, mode=1)
+    assert rel_err(got.cpu(), (want + b.double() + aux.double()).cpu()) < TOL
+    # input-gradient form: dy @ w through the transposed split
+    dy = torch.randn(T, N, device=a.device)
+    got = _gemm3(dy, _split(w, transposed=True), K)
+    assert rel_err(got.cpu(), (dy.double() @ w.double()).cpu()) < TOL
+
+
+@pytest.mark.parametrize("T,N,K", [(300, 96, 96), (4096, 384, 96), (2048, 768, 192), (1000, 1536, 384), (600, 192, 48)])
+def test_gelu_epilogues_match_fp64(T, N, K):
+    a, w, b = _data(T, N, K, seed=1)
+    z_want = a.double() @ w.double().t()
+    z, h = _gemm3(a, _split(w), N, b, mode=2)
+    assert rel_err(z.cpu(), z_want.cpu()) < TOL  # z is the bias-free fc1 output, as hs_bias_gelu_fwd expects
+    assert rel_err(h.cpu(), torch.nn.functional.gelu(z_want + b.double()).cpu()) < TOL
+    zz = torch.randn(T, N, device=a.device)
+    got = _gemm3(a, _split(w), N, b, zz, mode=3)
+    u = (zz.double() + b.double()).requires_grad_(True)
+    torch.nn.functional.gelu(u).sum().backward()
+    assert rel_err(got.cpu(), (z_want * u.grad).cpu()) < TOL
+
+
+def test_dropout_masks_match_the_bias_gelu_kernels():
+    """Modes 2 / 3 with drop > 0 use the same counter-based mask as hs_bias_gelu_fwd / bwd (pure function of seed, row,
+    column): the fused epilogues must reproduce the two-launch results element for element (up to GEMM rounding)."""
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    T, N, K = 1500, 384, 96
+    a, w, b = _data(T, N, K, seed=2)
+    drop, seed = 0.25, 0x1234_5678_9ABC
+    z, h = _gemm3(a, _split(w), N, b, mode=2, drop=drop, seed=seed)
+    h_ref = torch.empty_like(z)
+    check(lib.hs_bias_gelu_fwd(ptr(z), ptr(b), C.c_float(drop), C.c_uint64(seed), ptr(h_ref), T, N, current_stream()))
+    assert torch.equal(h == 0, h_ref == 0) and 0.2 < float((h == 0).float().mean()) < 0.3
+    assert rel_err(h.cpu(), h_ref.cpu()) < 1e-6
+    dh = a.double() @ w.double().t()  # any (T, N) "hidden gradient": reuse the product
+    got = _gemm3(a, _split(w), N, b, z, mode=3, drop=drop, seed=seed)
+    dz_ref = torch.empty_like(z)
+    check(lib.hs_bias_gelu_bwd(ptr(dh.float().contiguous()), ptr(z), ptr(b), C.c_float(drop), C.c_uint64(seed), ptr(dz_ref),
+                               None, T, N, current_stream()))
+    assert torch.equal(got == 0, dz_ref == 0)
+    assert rel_err(got.cpu(), dz_ref.cpu()) < TOL
+
+
+def test_linearity_and_exactness_on_bf16_data_at_full_size():
+    """BASELINE configs[1] stage-0 qkv shape (1.57 M tokens): operands that are exactly representable in bf16 with small
+    integer values give exact fp32 sums -- the result must be bit-exact, on every tile of the full-size launch."""
+    dev = torch.device("cuda:0")
+    T, N, K = 8 * 196608, 288, 96
+    g = torch.Generator(device=dev).manual_seed(5)
+    a = torch.randint(-8, 9, (T, K), generator=g, device=dev).float()
+    w = torch.randint(-8, 9, (N, K), generator=g, device=dev).float()
+    got = _gemm3(a, _split(w), N)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = a @ w.t()  # exact: |sum| <= 96 * 64 < 2^24
+    assert torch.equal(got, want)

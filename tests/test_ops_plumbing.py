@@ -24,6 +24,7 @@ class FakeLib:
 
     def __init__(self):
         self.calls = []
+        self.splits = 0
 
     def hs_linear_wgrad_supported(self, T, N, K):
         return 2
@@ -41,14 +42,44 @@ class FakeLib:
             db += dy.sum(0)
         return 0
 
-    def hs_linear_fwd(self, x, w, b, y, T, N, K, ws, ws_bytes, stream):
-        self.calls.append("fwd")
-        y.copy_(x @ w.t() + (b if b is not None else 0))
+    def hs_gemm3_supported(self, T, N, K):
+        return 1 if (N % 4 == 0 and K % 4 == 0) else 0
+
+    def hs_bias_gelu_supported(self, rows, Cc):
+        return 1
+
+    def hs_weight_split(self, w, rows, cols, ld, transposed, out, stream):
+        """[hi(32) | lo(32)] bf16 per 32-wide chunk of the contraction axis, zero padded (include/healswin_b200.h)."""
+        self.splits += 1
+        m = (w.t() if transposed else w).float()
+        assert m.shape == (rows, cols) and ld == w.shape[1]
+        nk = (cols + 31) // 32
+        pad = torch.zeros(rows, nk * 32)
+        pad[:, :cols] = m
+        hi = pad.bfloat16()
+        lo = (pad - hi.float()).bfloat16()
+        assert out.shape == (rows, 2 * nk * 32) and out.dtype == torch.bfloat16
+        o = out.view(rows, nk, 64)
+        o[:, :, :32] = hi.view(rows, nk, 32)
+        o[:, :, 32:] = lo.view(rows, nk, 32)
         return 0
 
-    def hs_linear_dgrad_acc(self, dy, w, c, dx, T, N, K, ws, ws_bytes, stream):
-        self.calls.append("dgrad_acc" if c is not None else "dgrad")
-        dx.copy_(dy @ w + (c if c is not None else 0))
+    def hs_gemm3(self, a, ws, bias, aux, d, d2, T, N, K, mode, drop, seed, stream):
+        self.calls.append(f"gemm3:{mode}")
+        assert _val(drop) == 0.0 and a.shape == (T, K) and ws.shape[0] == N
+        o = ws.view(N, -1, 64).float()
+        w = (o[:, :, :32] + o[:, :, 32:]).reshape(N, -1)[:, :K]   # hi + lo: the weight to ~2^-17
+        acc = a @ w.t()
+        b = bias if bias is not None else 0
+        if mode == 0:
+            d.copy_(acc + b)
+        elif mode == 1:
+            d.copy_(acc + b + aux)
+        elif mode == 2:
+            d.copy_(acc)
+            d2.copy_(F.gelu(acc + b))
+        else:
+            d.copy_(acc * _gelu_grad(aux + b))
         return 0
 
     def hs_bias_gelu_fwd(self, z, b, drop, seed, h, rows, Cc, stream):
@@ -90,7 +121,9 @@ def fake(monkeypatch):
     monkeypatch.setattr(ops, "require_cuda", lambda *a: None)
     monkeypatch.setattr(ops, "check", lambda rc: None)
     monkeypatch.setattr(ops.STATS, "launch", lambda name, fn, *a, tag=None: fn(*a))
-    monkeypatch.setattr(ops, "_LT_GEMM", True)
+    monkeypatch.setattr(ops, "_GEMM_MODE", "bf16x3")
+    monkeypatch.setattr(ops, "_on_device", lambda t: True)
+    ops.invalidate_weight_splits()
     return lib
 
 
@@ -101,42 +134,42 @@ def _close(a, b, tol=1e-5):
 def test_forked_linear_routes_the_shortcut_gradient_through_the_dgrad_gemm(fake):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(2, 5, 8, generator=g, requires_grad=True)
-    w = torch.randn(6, 8, generator=g, requires_grad=True)
-    b = torch.randn(6, generator=g, requires_grad=True)
-    wy, wsc = torch.randn(2, 5, 6, generator=g), torch.randn(2, 5, 8, generator=g)
+    w = torch.randn(12, 8, generator=g, requires_grad=True)
+    b = torch.randn(12, generator=g, requires_grad=True)
+    wy, wsc = torch.randn(2, 5, 12, generator=g), torch.randn(2, 5, 8, generator=g)
     y, shortcut = ops._LinearFn.apply(x, w, b, True)
     ((y * wy).sum() + (shortcut * wsc).sum()).backward()
-    assert fake.calls == ["fwd", "dgrad_acc", "wgrad"]
+    assert fake.calls == ["gemm3:0", "gemm3:1", "wgrad"]  # forward, dgrad with the shortcut gradient as aux, wgrad
     got = (x.grad.clone(), w.grad.clone(), b.grad.clone())
     x.grad = w.grad = b.grad = None
     ((F.linear(x, w, b) * wy).sum() + (x * wsc).sum()).backward()
     for a, ref in zip(got, (x.grad, w.grad, b.grad)):
-        assert _close(a, ref)
+        assert _close(a, ref, 1e-4)  # the emulated split weight is hi + lo in bf16: ~2^-17 relative
 
 
 def test_forked_linear_with_only_one_output_used(fake):
     x = torch.randn(3, 8, requires_grad=True)
-    w = torch.randn(6, 8, requires_grad=True)
+    w = torch.randn(12, 8, requires_grad=True)
     y, shortcut = ops._LinearFn.apply(x, w, None, True)
     shortcut.sum().backward()  # the branch is unused: no GEMM at all in the backward
-    assert fake.calls == ["fwd"] and torch.equal(x.grad, torch.ones_like(x)) and w.grad is None
+    assert fake.calls == ["gemm3:0"] and torch.equal(x.grad, torch.ones_like(x)) and w.grad is None
     x.grad = None
     fake.calls.clear()
     y, shortcut = ops._LinearFn.apply(x, w, None, True)
     y.sum().backward()  # the shortcut is unused: plain dgrad, no C operand
-    assert fake.calls == ["fwd", "dgrad", "wgrad"] and _close(x.grad, torch.ones(3, 6) @ w.detach())
+    assert fake.calls == ["gemm3:0", "gemm3:0", "wgrad"] and _close(x.grad, torch.ones(3, 12) @ w.detach(), 1e-4)
 
 
 def test_plain_linear_node_matches_torch(fake):
     x = torch.randn(7, 8, requires_grad=True)
-    w = torch.randn(4, 8, requires_grad=True)
+    w = torch.randn(8, 8, requires_grad=True)
     y = ops._LinearFn.apply(x, w, None, False)
     assert isinstance(y, torch.Tensor)
     y.square().sum().backward()
     got = (x.grad.clone(), w.grad.clone())
     x.grad = w.grad = None
     F.linear(x, w).square().sum().backward()
-    assert _close(got[0], x.grad) and _close(got[1], w.grad)
+    assert _close(got[0], x.grad, 1e-4) and _close(got[1], w.grad, 1e-4)
 
 
 @pytest.mark.parametrize("fork", [False, True])
@@ -150,14 +183,14 @@ def test_fused_mlp_node_matches_torch_autograd(fake, fork):
     out = ops._MlpFn.apply(x, w1, b1, w2, 0.0, 0, fork)
     y = out[0] + out[1] if fork else out
     y.backward(gy)
-    # wgrad(fc2), fused dgrad + GELU', wgrad(fc1) + bias, library dgrad (with the shortcut gradient when forked)
-    assert fake.calls == ["fwd", "fwd", "wgrad", "mlp_dgrad_gelu", "wgrad", "dgrad_acc" if fork else "dgrad"]
+    # fc1 + GELU epilogue, fc2 | wgrad(fc2), fused dgrad + GELU', wgrad(fc1) + bias, dgrad (+ shortcut gradient when forked)
+    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "mlp_dgrad_gelu", "wgrad", "gemm3:1" if fork else "gemm3:0"]
     got = [t.grad.clone() for t in (x, w1, b1, w2)]
     for t in (x, w1, b1, w2):
         t.grad = None
     ref = F.linear(F.gelu(F.linear(x, w1, b1)), w2)
     (ref + x if fork else ref).backward(gy)
-    assert _close(y.detach(), (ref + x if fork else ref).detach())
+    assert _close(y.detach(), (ref + x if fork else ref).detach(), 1e-4)
     for a, t in zip(got, (x, w1, b1, w2)):
         assert _close(a, t.grad, 1e-4)
 
@@ -184,3 +217,34 @@ def test_decoder_tail_parameter_gradients_follow_from_s_and_g(fake, bias):
     assert _close(y.detach(), ref.detach())
     for a, t in zip(got, params):
         assert _close(a, t.grad, 1e-4)
+
+
+def test_mlp_node_uses_the_gelu_grad_epilogue_where_the_tf32_kernel_does_not_cover(fake, monkeypatch):
+    monkeypatch.setattr(fake, "hs_mlp_dgrad_gelu_supported", lambda T, Cc, J: 0)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5, 8, generator=g, requires_grad=True)
+    w1 = (torch.randn(32, 8, generator=g) / 3).requires_grad_(True)
+    b1 = torch.randn(32, generator=g, requires_grad=True)
+    w2 = (torch.randn(8, 32, generator=g) / 6).requires_grad_(True)
+    ops._MlpFn.apply(x, w1, b1, w2, 0.0, 0, False).sum().backward()
+    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "gemm3:3", "wgrad", "gemm3:0"]
+    got = [t.grad.clone() for t in (x, w1, b1, w2)]
+    for t in (x, w1, b1, w2):
+        t.grad = None
+    F.linear(F.gelu(F.linear(x, w1, b1)), w2).sum().backward()
+    for a, t in zip(got, (x, w1, b1, w2)):
+        assert _close(a, t.grad, 1e-4)
+
+
+def test_weight_splits_are_cached_until_the_parameter_changes(fake):
+    w = torch.nn.Parameter(torch.randn(8, 12))
+    a = ops.split_weight(w)
+    assert ops.split_weight(w) is a and fake.splits == 1
+    at = ops.split_weight(w, transposed=True)
+    assert at.shape == (12, 64) and a.shape == (8, 64) and fake.splits == 2
+    with torch.no_grad():
+        w.mul_(2.0)  # an optimizer step bumps the version counter
+    b = ops.split_weight(w)
+    assert fake.splits == 3 and b is a  # same buffer (stable address), new contents
+    hi_lo = b.view(8, 1, 64).float()
+    assert _close((hi_lo[:, 0, :32] + hi_lo[:, 0, 32:])[:, :12], w.detach(), 1e-4)

@@ -27,16 +27,6 @@ def load_model_case(name):
 
 
 def build_product_model(kw, sd=None, device="cpu"):
-    from heal_swin_b200.data_spec import DataSpec
-    from heal_swin_b200.models_torch import swin_hp_transformer as M
+    from heal_swin_b200.factory import build_hp_model
 
-    cfgkw = {k: v for k, v in kw.items() if k not in ("dim_in", "f_in", "f_out", "base_pix")}
-    cfgkw.setdefault("drop_path_rate", 0.0)
-    cfg = M.SwinHPTransformerConfig(**cfgkw)
-    spec = DataSpec(dim_in=kw["dim_in"], f_in=kw["f_in"], f_out=kw["f_out"], base_pix=kw["base_pix"])
-    model = M.SwinHPTransformerSys(cfg, data_spec=spec)
-    if sd is not None:
-        missing, unexpected = model.load_state_dict(sd, strict=False)
-        assert not unexpected, unexpected
-        assert all(("attn_mask" in m) or ("relative_position_index" in m) for m in missing), missing
-    return model.to(device)
+    return build_hp_model(kw, sd, device)
