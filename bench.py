@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--gemm", default="bf16x3", choices=["bf16x3", "library"],
                     help="bf16x3: the hand-written tensor-core GEMMs (the product); library: cuBLAS TF32 through torch "
                          "(diagnostics only: outside the 1e-3 tolerance)")
+    ap.add_argument("--no-cuda-graph", action="store_true",
+                    help="time eager steps (torch DDP) instead of heal_swin_b200.graph.GraphedTrainStep replays")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=150.0)
     return ap.parse_args()
@@ -251,7 +253,10 @@ def summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic):
                          "family_achieved_GBps": f["bytes"] / (f["ms"] * 1e-3) / 1e9,
                          "largest_shape": list(tag), "largest_shape_avg_ms": avg_ms, "largest_shape_launches": n,
                          "largest_shape_algorithmic_bytes": nb, "largest_shape_achieved_GBps": ach,
-                         "largest_shape_frac": ach / hbm_peak}
+                         "largest_shape_frac": ach / hbm_peak,
+                         # every shape of the family: [shape tag, launches, mean ms, fraction of the HBM roofline]
+                         "shapes": [[list(t_), n_, round(ms_, 4), round(nb_ / (ms_ * 1e-3) / 1e9 / hbm_peak, 3)]
+                                    for t_, (nb_, ms_, n_) in sorted(f["shapes"].items(), key=lambda kv: -kv[1][1] * kv[1][2])]}
     if not kernels:
         return kernels, None
     dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
@@ -319,7 +324,6 @@ def run_ours(a):
             if n.endswith("relative_position_bias_table"):
                 p.copy_((torch.randn(p.shape, generator=gen) * 0.02).to(dev))
     model.train()
-    net = hsdist.wrap_ddp(model, local)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     B, npix = a.batch, kw["dim_in"]
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -331,16 +335,32 @@ def run_ours(a):
     def to_model_inputs(xu8, tu8):
         return (xu8.float() - 127.5) * (1.0 / 73.9), tu8.long()  # zero mean, unit variance for uniform bytes
 
-    dev_x, dev_t = to_model_inputs(host_x.to(dev), host_t.to(dev))
     loss_fn = torch.nn.CrossEntropyLoss()
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
 
-    def step(x, t):
-        opt.zero_grad(set_to_none=True)
-        loss = loss_fn(net(x), t)
-        loss.backward()
-        opt.step()
-        return loss
+    use_graph = (not a.no_cuda_graph) and a.drop_rate == 0.0
+    if use_graph:
+        # the public training-step API of the package: forward + loss + backward replayed as one CUDA graph, one flat
+        # NCCL all-reduce of the gradients, fused Adam
+        from heal_swin_b200.graph import GraphedTrainStep
+
+        dev_xu8, dev_tu8 = host_x.to(dev), host_t.to(dev)
+        stepper = GraphedTrainStep(model, loss_fn, opt, dev_xu8, dev_tu8, warmup=3, preprocess=to_model_inputs)
+
+        def step(x, t, eager=False):  # x, t: the raw uint8 batch, resident (dev_*u8) or in pinned host memory (host_*)
+            return stepper(x, t, eager=eager)
+    else:
+        net = hsdist.wrap_ddp(model, local)
+
+        dev_xu8, dev_tu8 = host_x.to(dev), host_t.to(dev)
+
+        def step(xu8, tu8, eager=True):
+            x, t = to_model_inputs(xu8.to(dev, non_blocking=True), tu8.to(dev, non_blocking=True))
+            opt.zero_grad(set_to_none=True)
+            loss = loss_fn(net(x), t)
+            loss.backward()
+            opt.step()
+            return loss
 
     def barrier():
         hsdist.barrier()
@@ -349,40 +369,54 @@ def run_ours(a):
     def max_over_ranks(ms):
         return hsdist.max_over_ranks(ms, dev)
 
-    for _ in range(a.warmup):
-        step(dev_x, dev_t)
-    barrier()
-
-    # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- per-kernel durations behind `roofline`: K steps launched eagerly with a CUDA-event pair around every launch of
+    # this library's kernels (individual kernels cannot be bracketed inside a graph replay), and the launch count.  Same
+    # process and clocks as the timed region that follows, under the same clock sampler.  (Run first: the eager step and
+    # the graph's private pool each hold ~90 GB of activations, they do not fit side by side.)
+    for _ in range(a.warmup):
+        step(dev_xu8, dev_tu8, eager=True)
     ops.STATS.reset()
     ops.STATS.timing = True
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(a.steps):
-        step(dev_x, dev_t)
+        step(dev_xu8, dev_tu8, eager=True)
     e1.record()
     barrier()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    ms_eager = max_over_ranks(e0.elapsed_time(e1))
     launches = ops.STATS.launches
     kernel_ms = ops.STATS.elapsed_ms()
     ops.STATS.timing = False
-    clocks = sampler.stop() if rank == 0 else None
+    ops.STATS.events = {}
+    torch.cuda.empty_cache()
+
+    # ---- timed region 1: inputs resident in HBM
+    for _ in range(a.warmup):
+        step(dev_xu8, dev_tu8)  # (the first call captures the graph)
+    barrier()
+    e0.record()
+    for _ in range(a.steps):
+        step(dev_xu8, dev_tu8)
+    e1.record()
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- timed region 2: end to end from pinned host buffers (H2D batch, D2H loss each step)
     barrier()
     e0.record()
     for _ in range(a.steps):
-        x, t = to_model_inputs(host_x.to(dev, non_blocking=True), host_t.to(dev, non_blocking=True))
-        loss = step(x, t)
+        loss = step(host_x, host_t)  # H2D of the raw batch into the step's input buffers, then the step
         host_loss.copy_(loss.detach(), non_blocking=True)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
     final_loss = float(host_loss)
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -408,14 +442,20 @@ def run_ours(a):
     except Exception:
         pass
 
-    kernels, roofline = summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic)
+    kernels, roofline = summarize_kernels(kernel_ms, ms_eager, hbm_peak, peak_src, traffic)
+    if roofline is not None:
+        roofline["timed_in"] = (f"{a.steps} eager steps with a CUDA-event pair around every launch, directly before the timed "
+                                f"region ({ms_eager / a.steps:.1f} ms/step eager vs {ms_dev / a.steps:.1f} ms/step "
+                                f"{'graph replay' if use_graph else 'eager'} in the timed region)")
 
     cpu_base, fwd_err = None, None
     if world == 1 and not a.no_cpu_baseline:
+        if use_graph:  # release the graph's private pool before the parity forward
+            stepper.graph = None
+        torch.cuda.empty_cache()
         cpu_base, _, _, _, chk = cpu_oracle_steps(kw, 1, 1, min(a.cpu_budget_s, 60.0))
         # live parity of the benchmarked configuration: the same architecture with the checker's weights, one full-size
         # sphere, forward through the product path vs the oracle's forward of the CPU sample above
-        del net, opt
         model.load_state_dict(chk["sd"], strict=False)
         ops.invalidate_weight_splits()
         model.eval()
@@ -429,6 +469,9 @@ def run_ours(a):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a, kw), "global_batch": world * B, "pixels_per_sample": npix,
                    "parallelism": f"dp{world}", "step": "fwd + CE loss + bwd + (NCCL grad all-reduce) + Adam",
+                   "launch": "heal_swin_b200.graph.GraphedTrainStep: fwd + loss + bwd replayed as one CUDA graph, flat "
+                             "gradient all-reduce, fused Adam" if use_graph else "eager (torch DDP)",
+                   "ms_per_step_eager": ms_eager / a.steps,
                    "arithmetic": "fp32 in HBM; dense linears: hand-written bf16x3 tcgen05 GEMM (hi/lo split operands, 3 MMAs, "
                                  "fp32 accumulate); attention: tcgen05 TF32; LayerNorm / softmax / GELU fp32"
                                  if a.gemm == "bf16x3" else "fp32 in HBM; cuBLAS TF32 GEMMs (diagnostic mode)",

@@ -45,7 +45,7 @@ SIGNATURES = {
     "hs_mlp_dgrad_gelu": [_p, _p, _p, _p, _f, _u64, _p, _i64, _i, _i, _u32, _p],
     "hs_weight_split": [_p, _i, _i, _i, _i, _p, _p],
     "hs_gemm3_supported": [_i64, _i, _i],
-    "hs_gemm3": [_p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _f, _u64, _p],
+    "hs_gemm3": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _f, _u64, _p],
     "hs_ln_head_supported": [_i64, _i, _i],
     "hs_ln_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _f, _p],
     "hs_ln_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],
@@ -105,9 +105,20 @@ def current_stream():
 
 
 def require_cuda(*tensors):
+    import torch
+
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError(
                 "heal_swin_b200 runs on CUDA tensors only (B200 / sm_100a); there is no CPU fallback. "
                 "Move the module and its inputs to a CUDA device."
+            )
+        if t.device.index != torch.cuda.current_device():
+            # kernels are launched on the current device's stream: a tensor of another device would be a silent
+            # wrong-device access (one process per GPU is the supported layout, heal_swin/train.py:187)
+            raise RuntimeError(
+                f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: call "
+                "torch.cuda.set_device(...) (or wrap the call in torch.cuda.device(...)) first"
             )

@@ -1,6 +1,4 @@
 // C-ABI entry points of the attention kernels: argument validation + kernel-family dispatch.
-#include <cstdlib>
-
 #include "hs_common.h"
 #include "hs_kernels.h"
 
@@ -25,14 +23,9 @@ int hs_window_attn_bwd(const float* qkv, const float* out, const float* lse, con
   HS_REQUIRE(attn_drop >= 0.f && attn_drop < 1.f, "hs_window_attn_bwd: attn_drop must be in [0, 1), got %f", attn_drop);
   const hs::DropCfg drop{attn_drop, seed};
   if (!(flags & HS_ATTN_NO_TC) && out && lse && hs::window_attn_tc_supported(qkv, dqkv, mask, B, N, C, H, ws) &&
-      !((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(out)) & 15)) {
-    static const bool v2 = [] { const char* e = getenv("HEALSWIN_ATTN_BWD_V2"); return e && e[0] == '1'; }();
-    if (v2)
-      return hs::window_attn_bwd_tc_v2(qkv, out, lse, dout, src, groups, bias, logit_scale, scale, drop, dqkv, dbias,
-                                       dlogit_scale, B, N, C, H, flags, (cudaStream_t)stream);
+      !((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(out)) & 15))
     return hs::window_attn_bwd_tc(qkv, out, lse, dout, src, groups, bias, logit_scale, scale, drop, dqkv, dbias,
                                   dlogit_scale, B, N, C, H, flags, (cudaStream_t)stream);
-  }
   return hs::window_attn_bwd_simt(qkv, dout, src, groups, mask, bias, logit_scale, scale, drop, dqkv, dbias,
                                   dlogit_scale, B, N, C, H, ws, flags, (cudaStream_t)stream);
 }

@@ -12,12 +12,15 @@
 // the TF32 rate) -- free where the GEMM is HBM-bound (stages 0-1).
 //
 // Operand staging.  W is split once per optimizer step by hs_weight_split into rows of [hi(32) | lo(32)] bf16 per
-// 32-wide K chunk (128 B: one SWIZZLE_128B row), so it comes in by TMA ready to use.  A arrives as raw fp32: a
-// 128-row x 32-column chunk (16 KB, TMA SWIZZLE_128B) is rewritten IN PLACE by 8 converter warps into
-// [hi(32) | lo(32)] bf16 rows with the same swizzle -- the K=16 MMA steps then address hi at +0/+32 B and lo at +64/+96 B.
+// 32-wide K chunk (128 B: one SWIZZLE_128B row), so it comes in by TMA ready to use as the shared-memory B operand (hi at
+// +0/+32 B, lo at +64/+96 B for the two K=16 steps).  A arrives as raw fp32: a 128-row x 32-column chunk (16 KB, TMA
+// SWIZZLE_128B) is read by 8 converter warps (thread = row, two warps per TMEM lane quadrant, 16 columns each), split, and
+// written with tcgen05.st into a ring of 32-column TENSOR-MEMORY slots (columns 0-15 hi, 16-31 lo, two bf16 per column):
+// the MMAs take A from tensor memory.  Shared memory bandwidth (128 B/clk) is the co-limiter of this kernel -- with A in
+// shared memory the operand reads of the three MMAs were 35 % of all shared-memory traffic.
 //
-// A CTA owns one column chunk (n_tile <= 256 columns) and walks over 128-token tiles; its W chunk stays resident in shared
-// memory when it fits, otherwise the K slices of W ride in the ring slots beside the A chunks (L2 hits).  Two 256-column
+// A CTA owns one column chunk (<= 192 columns) and walks over 128-token tiles; its W chunk stays resident in shared
+// memory when it fits, otherwise its K slices stream through a short ring of their own (L2 hits).  Two 192-column
 // TMEM stages overlap the epilogue of one tile with the MMAs of the next.  The epilogue (groups of 4 warps, one 32-column
 // slab at a time; every warp has private 4 KB staging regions and issues its own TMA stores / aux loads, so the warps never
 // synchronise with each other) goes TMEM -> registers -> swizzled staging region -> TMA store, and can
@@ -47,16 +50,20 @@ constexpr int kMaxWRing = 4;            // streamed W slices (L2 hits: a short r
 constexpr int kMaxRw = 3;              // staging regions per epilogue warp
 constexpr int kRegion = 32 * 128;      // 4 KB: 32 rows x 32 columns, one warp's part of a slab
 constexpr int kCvtWarps = 8;
-constexpr int kStageCols = 256;        // TMEM columns per accumulator stage
+constexpr int kStageCols = 192;        // TMEM columns per accumulator stage (2 stages) ...
+constexpr int kASlots = 4;             // ... + 4 A-operand slots of 32 columns = 512
+constexpr int kACol0 = 2 * kStageCols;
 
 enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3 };
 
 struct G3Args {
   const float* bias;  // (N) or null
+  float* colsum;      // (K) or null: += column sums of A (the bias gradient when A is the output gradient of a linear)
   long long T;
   int N, K;
   int n_stride, n_box, n_chunks;  // column chunks start every n_stride columns and compute n_box (multiple of 32)
   long long tiles;
+  int cluster;  // CTAs per cluster (1, 2 or 4): streamed W slices are loaded once per cluster and multicast
   int ring, rw, resident, wring;  // A ring depth, staging regions per epilogue warp, W resident?, W ring depth
   uint32_t drop_thresh;
   float drop_scale;
@@ -73,6 +80,15 @@ __device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // {bf16(hi_of_pair), bf16(lo_of_pair)}: first argument lands in the upper 16 bits
@@ -103,12 +119,18 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   uint8_t* s_w = sm;                           // resident: nk slices; streamed: a ring of wring slices
   uint8_t* s_ring = s_w + (a.resident ? nk : a.wring) * w_slice;
   uint8_t* s_buf = s_ring + a.ring * kChunk;   // E warps x rw regions of 4 KB
-  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], cvt_full[kMaxRing],
-      slot_empty[kMaxRing], acc_full[2], acc_empty[2], aux_full[E * kMaxRw];
+  float* s_colsum = reinterpret_cast<float*>(s_buf + E * a.rw * kRegion);  // nk * 32 floats (chunk-0 CTAs with a.colsum)
+  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], slot_empty[kMaxRing],
+      a_full[kASlots], a_empty[kASlots], acc_full[2], acc_empty[2], aux_full[E * kMaxRw];
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x % a.n_chunks;
-  const long long t0 = blockIdx.x / a.n_chunks, tstep = gridDim.x / a.n_chunks;
+  // CTAs of a cluster share the column chunk and take neighbouring token tiles; every CTA of a cluster runs the same number
+  // of tile iterations (a tile index beyond the end is harmless: TMA zero-fills its loads and clips its stores)
+  const int cs = a.cluster, crank = cs > 1 ? (int)cluster_ctarank() : 0;
+  const int chunk = (blockIdx.x / cs) % a.n_chunks;
+  const long long t0 = (long long)(blockIdx.x / (cs * a.n_chunks)) * cs + crank, tstep = gridDim.x / a.n_chunks;
+  const long long t_end = cs > 1 ? t0 + ((a.tiles + tstep - 1) / tstep) * tstep : a.tiles;
+  const uint16_t cmask = (uint16_t)((1u << cs) - 1);
   // column chunk of this CTA: starts every n_stride columns and computes n_box >= n_stride of them (a multiple of 32);
   // where n_box > n_stride the first columns of the next chunk are computed -- and stored -- twice, with identical values
   const int n0 = chunk * a.n_stride;
@@ -120,12 +142,15 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     mbar_init(&w_full, 1);
     for (int i = 0; i < kMaxWRing; ++i) {
       mbar_init(&wr_full[i], 1);
-      mbar_init(&wr_empty[i], 1);
+      mbar_init(&wr_empty[i], cs);  // released by the MMA issuers of all CTAs of the cluster (multicast commit)
     }
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&cvt_full[i], kCvtWarps);
-      mbar_init(&slot_empty[i], 1);
+      mbar_init(&slot_empty[i], kCvtWarps);  // released by the converters: the chunk is in their registers
+    }
+    for (int i = 0; i < kASlots; ++i) {
+      mbar_init(&a_full[i], kCvtWarps);
+      mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -144,6 +169,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // every CTA's barriers are initialised before any multicast touches them
   tc_fence_after();
   const uint32_t tmem = tmem_base;
 
@@ -152,7 +178,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     if (elect_one()) {
       int slot = 0;
       uint32_t ph = 0;
-      for (long long tile = t0; tile < a.tiles; tile += tstep)
+      for (long long tile = t0; tile < t_end; tile += tstep)
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&slot_empty[slot], ph ^ 1);
           mbar_arrive_expect_tx(&raw_full[slot], (uint32_t)kChunk);
@@ -169,11 +195,18 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       } else {
         int ws = 0;
         uint32_t wph = 0;
-        for (long long tile = t0; tile < a.tiles; tile += tstep)
+        // with a cluster this CTA loads rows [crank, crank + 1) * n_box / cs of every slice and multicasts them to all
+        // CTAs of the cluster; its own barrier expects the whole slice (the other parts arrive from the peers)
+        const int part_rows = a.n_box / cs;
+        for (long long tile = t0; tile < t_end; tile += tstep)
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&wr_empty[ws], wph ^ 1);
             mbar_arrive_expect_tx(&wr_full[ws], (uint32_t)w_slice);
-            tma_load_2d(s_w + ws * w_slice, &map_w, &wr_full[ws], 64 * kc, n0);
+            if (cs > 1)
+              tma_load_2d_multicast(s_w + ws * w_slice + crank * part_rows * 128, &map_w, &wr_full[ws], 64 * kc,
+                                    n0 + crank * part_rows, cmask);
+            else
+              tma_load_2d(s_w + ws * w_slice, &map_w, &wr_full[ws], 64 * kc, n0);
             if (++ws == a.wring) { ws = 0; wph ^= 1; }
           }
       }
@@ -184,74 +217,112 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       constexpr uint64_t kDesc = umma_smem_desc(16, 1024, kLayoutSw128);
       const uint32_t idesc = idesc_bf16(128, 32 * S);
       if (a.resident) mbar_wait(&w_full, 0);
-      const uint32_t wb = smem_u32(s_w), rb = smem_u32(s_ring);
-      int slot = 0, ws = 0;
-      uint32_t ph = 0, wph = 0;
+      const uint32_t wb = smem_u32(s_w);
+      int as_ = 0, ws = 0;
+      uint32_t aph = 0, wph = 0;
       long long it = 0;
-      for (long long tile = t0; tile < a.tiles; tile += tstep, ++it) {
-        const int as = (int)(it & 1);
-        mbar_wait(&acc_empty[as], (((uint32_t)(it >> 1)) & 1) ^ 1);
+      for (long long tile = t0; tile < t_end; tile += tstep, ++it) {
+        const int st = (int)(it & 1);
+        mbar_wait(&acc_empty[st], (((uint32_t)(it >> 1)) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + (uint32_t)as * kStageCols;
+        const uint32_t d = tmem + (uint32_t)st * kStageCols;
         for (int kc = 0; kc < nk; ++kc) {
           if (!a.resident) mbar_wait(&wr_full[ws], wph);
-          mbar_wait(&cvt_full[slot], ph);
+          mbar_wait(&a_full[as_], aph);
           tc_fence_after();
-          const uint32_t ab = rb + slot * kChunk;
+          const uint32_t at = tmem + kACol0 + 32 * as_;
           const uint32_t wk = wb + (a.resident ? kc : ws) * w_slice;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t a_hi = umma_desc_at(kDesc, ab + 32 * ks), a_lo = umma_desc_at(kDesc, ab + 64 + 32 * ks);
+            const uint32_t a_hi = at + 8 * ks, a_lo = at + 16 + 8 * ks;
             const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
-            umma_bf16_ss(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-            umma_bf16_ss(d, a_hi, w_lo, idesc, 1u);
-            umma_bf16_ss(d, a_hi, w_hi, idesc, 1u);
+            umma_bf16_ts(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_ts(d, a_hi, w_lo, idesc, 1u);
+            umma_bf16_ts(d, a_hi, w_hi, idesc, 1u);
           }
-          umma_commit(&slot_empty[slot]);
-          if (++slot == ring) { slot = 0; ph ^= 1; }
+          umma_commit(&a_empty[as_]);
+          if (++as_ == kASlots) { as_ = 0; aph ^= 1; }
           if (!a.resident) {
-            umma_commit(&wr_empty[ws]);
+            if (cs > 1) umma_commit_multicast(&wr_empty[ws], cmask);
+            else umma_commit(&wr_empty[ws]);
             if (++ws == a.wring) { ws = 0; wph ^= 1; }
           }
         }
-        umma_commit(&acc_full[as]);
+        umma_commit(&acc_full[st]);
       }
     }
   } else if (warp >= E) {
-    // ================================================================ converters: fp32 chunk -> [hi | lo] bf16, in place
+    // ================================================================ converters: fp32 chunk (smem) -> hi / lo bf16 (TMEM)
+    // warp cw: TMEM lane quadrant cw & 3 (= warp % 4, the tcgen05.st restriction), K half cw >> 2 (16 of the 32 columns)
     const int cw = warp - E;
-    const int row = cw * 16 + (lane & 15), half = lane >> 4;
+    const int q = cw & 3, half = cw >> 2;
+    const int row = q * 32 + lane;
     const int sw = row & 7;
     const uint32_t ring_u32 = smem_u32(s_ring);
-    int slot = 0;
-    uint32_t ph = 0;
-    for (long long tile = t0; tile < a.tiles; tile += tstep)
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int slot = 0, as_ = 0;
+    uint32_t ph = 0, aph = 0;
+    const bool do_colsum = a.colsum != nullptr && chunk == 0;
+    const uint32_t cs_u32 = smem_u32(s_colsum);
+    if (do_colsum) {
+      for (int i = threadIdx.x - E * 32; i < nk * 32; i += kCvtWarps * 32) s_colsum[i] = 0.f;
+      named_bar_sync(1, kCvtWarps * 32);
+    }
+    for (long long tile = t0; tile < t_end; tile += tstep)
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(&raw_full[slot], ph);
         const uint32_t base = ring_u32 + slot * kChunk + row * 128;
         float4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = lds_f4(base + (((4 * half + j) ^ sw) << 4));
-        __syncwarp();  // every lane of the row pair has read before anyone overwrites
-        uint4 hi[2], lo[2];
-        split2(v[0].x, v[0].y, hi[0].x, lo[0].x);
-        split2(v[0].z, v[0].w, hi[0].y, lo[0].y);
-        split2(v[1].x, v[1].y, hi[0].z, lo[0].z);
-        split2(v[1].z, v[1].w, hi[0].w, lo[0].w);
-        split2(v[2].x, v[2].y, hi[1].x, lo[1].x);
-        split2(v[2].z, v[2].w, hi[1].y, lo[1].y);
-        split2(v[3].x, v[3].y, hi[1].z, lo[1].z);
-        split2(v[3].z, v[3].w, hi[1].w, lo[1].w);
+        if (do_colsum) {
+          // column sums of this warp's 32 rows x 16 columns: a reduce-scatter over the lanes (8 + 4 + 2 + 1 + 1 shuffles)
+          // leaves one column per even lane, which adds it to the CTA's running sums
+          const float c[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
+                               v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
+          const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+          float k8[8], k4[4], k2[2];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          sts_u4(base + (((2 * half + j) ^ sw) << 4), hi[j]);
-          sts_u4(base + (((4 + 2 * half + j) ^ sw) << 4), lo[j]);
+          for (int i = 0; i < 8; ++i)
+            k8[i] = (b4 ? c[i + 8] : c[i]) + __shfl_xor_sync(0xffffffffu, b4 ? c[i] : c[i + 8], 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            k4[i] = (b3 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k8[i] : k8[i + 4], 8);
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            k2[i] = (b2 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? k4[i] : k4[i + 2], 4);
+          float k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? k2[0] : k2[1], 2);
+          k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
+          const int col = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+          if (!(lane & 1)) red_add_shared_f32(cs_u32 + 4 * (32 * kc + 16 * half + col), k1);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&cvt_full[slot]);
+        uint32_t hi[8], lo[8];
+        split2(v[0].x, v[0].y, hi[0], lo[0]);
+        split2(v[0].z, v[0].w, hi[1], lo[1]);
+        split2(v[1].x, v[1].y, hi[2], lo[2]);
+        split2(v[1].z, v[1].w, hi[3], lo[3]);
+        split2(v[2].x, v[2].y, hi[4], lo[4]);
+        split2(v[2].z, v[2].w, hi[5], lo[5]);
+        split2(v[3].x, v[3].y, hi[6], lo[6]);
+        split2(v[3].z, v[3].w, hi[7], lo[7]);
+        __syncwarp();  // every lane holds its part of the chunk in registers: the shared-memory slot can be refilled
+        if (lane == 0) mbar_arrive(&slot_empty[slot]);
         if (++slot == ring) { slot = 0; ph ^= 1; }
+        mbar_wait(&a_empty[as_], aph ^ 1);  // the MMAs that read this tensor-memory slot have completed
+        tc_fence_after();
+        const uint32_t at = tmem + lane_addr + kACol0 + 32 * as_;
+        tmem_st8(at + 8 * half, hi);
+        tmem_st8(at + 16 + 8 * half, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[as_]);
+        if (++as_ == kASlots) { as_ = 0; aph ^= 1; }
       }
+    if (do_colsum) {
+      named_bar_sync(1, kCvtWarps * 32);
+      for (int i = threadIdx.x - E * 32; i < a.K; i += kCvtWarps * 32) atomicAdd(a.colsum + i, s_colsum[i]);
+    }
   } else {
     // ================================================================ epilogue
     // Warp (g, q) owns rows [32q, 32q + 32) (its TMEM lane quadrant) of the slabs g, g + NG, ... of every tile, and rw
@@ -264,7 +335,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const uint32_t my_u32 = smem_u32(my);
     uint64_t* my_full = aux_full + warp * kMaxRw;
     const int spw = S > g ? (S - g + NG - 1) / NG : 0;            // slabs of this warp per tile
-    const long long my_tiles = a.tiles > t0 ? (a.tiles - t0 + tstep - 1) / tstep : 0;
+    const long long my_tiles = t_end > t0 ? (t_end - t0 + tstep - 1) / tstep : 0;
     const long long total = my_tiles * spw;                       // aux loads of this warp over the whole launch
     auto issue_aux = [&](long long u) {                           // slab use u -> its staging region (lane 0 only)
       const long long tile = t0 + (u / spw) * tstep;
@@ -277,7 +348,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       for (long long u = 0; u < rw && u < total; ++u) issue_aux(u);
     long long cnt = 0;  // staging-region uses so far
     long long it = 0;
-    for (long long tile = t0; tile < a.tiles; tile += tstep, ++it) {
+    for (long long tile = t0; tile < t_end; tile += tstep, ++it) {
       const int as = (int)(it & 1);
       mbar_wait(&acc_full[as], ((uint32_t)(it >> 1)) & 1);
       tc_fence_after();
@@ -367,6 +438,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
   if (warp == E + kCvtWarps + 1) tmem_dealloc(tmem, 512);
 }
 
@@ -417,26 +489,26 @@ int make_map_bf16(CUtensorMap* m, const uint16_t* base, long long rows, long lon
 
 constexpr int kSmemAvail = 232448 - 1024 - 1024;  // dynamic shared memory minus alignment slack and the static barriers
 
-// column chunking + shared-memory plan: the widest balanced column chunk (<= 256) that leaves an A ring of >= 4 slots
+// column chunking + shared-memory plan: the widest balanced column chunk (<= 192) that leaves an A ring of >= 4 slots
 int plan(G3Args& a, int mode, int E) {
   a.tiles = (a.T + kBM - 1) / kBM;
   const int nk = (a.K + 31) / 32;
   const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
   const int rw_min = aux ? 2 : 1, rw_max = aux ? 3 : 2;
-  int first = (a.N + 255) / 256;                       // number of chunks
+  int first = (a.N + kStageCols - 1) / kStageCols;     // number of chunks (an accumulator stage has 192 columns)
   first = (((a.N + first - 1) / first) + 15) / 16 * 16;  // equal chunks, 16-column granularity
   if (const char* e = getenv("HEALSWIN_GEMM3_NTILE")) {  // experiments only
     const int v = atoi(e);
-    if (v >= 32 && v <= 256 && v % 16 == 0 && v < first) first = v;
+    if (v >= 32 && v <= kStageCols && v % 16 == 0 && v < first) first = v;
   }
-  const int cand[6] = {first, 192, 128, 96, 64, 32};
+  const int cand[6] = {first, 160, 128, 96, 64, 32};
   int best_ring = 0;
   for (int ci = 0; ci < 6; ++ci) {
     const int stride = cand[ci];
     if (stride > first || (ci > 0 && stride == first)) continue;
     const int box = (stride + 31) / 32 * 32;
     const int w_slice = box * 128;
-    const long long staging_min = (long long)E * rw_min * kRegion;
+    const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0);
     const int resident = ((long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
     const int wring = nk < 3 ? nk : 3;
     const long long w_bytes = (long long)(resident ? nk : wring) * w_slice;
@@ -452,18 +524,27 @@ int plan(G3Args& a, int mode, int E) {
     a.wring = wring;
     a.ring = ring;
     left -= (long long)ring * kChunk;
-    a.rw = rw_min + (int)(left / ((long long)E * kRegion));
+    a.rw = rw_min + (int)(left / ((long long)E * kRegion));  // (staging_min already holds rw_min regions + the column sums)
+    // streamed W with a long contraction = the tensor-bound shapes, whose limit is L2 -> SM bandwidth: share the W slices
+    a.cluster = 1;
+    if (!resident && box % 64 == 0 && a.tiles >= 2 * 148) a.cluster = 2;
     if (a.rw > rw_max) a.rw = rw_max;
     if (ring >= 4) break;
   }
   if (best_ring < 2) return hs::fail(HS_ERR_UNSUPPORTED, "hs_gemm3: no shared-memory plan for N=%d K=%d", a.N, a.K);
+  if (const char* e = getenv("HEALSWIN_GEMM3_CLUSTER")) {  // experiments only
+    const int v = atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && !a.resident && a.n_box % (16 * v) == 0) a.cluster = v;
+    if (v == 1) a.cluster = 1;
+  }
   return HS_OK;
 }
 
 template <int E>
 size_t smem_bytes(const G3Args& a) {
   const int nk = (a.K + 31) / 32, w_slice = a.n_box * 128;
-  return (size_t)(a.resident ? nk : a.wring) * w_slice + (size_t)a.ring * kChunk + (size_t)E * a.rw * kRegion + 1024;
+  return (size_t)(a.resident ? nk : a.wring) * w_slice + (size_t)a.ring * kChunk + (size_t)E * a.rw * kRegion +
+         (a.colsum ? (size_t)nk * 128 : 0) + 1024;
 }
 
 struct Maps {
@@ -477,18 +558,40 @@ int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, floa
   if ((rc = plan(a, MODE, E))) return rc;
   Maps m;
   if ((rc = hs::tc::make_map(&m.a, a_dev, a.T, a.K, CU_TENSOR_MAP_SWIZZLE_128B, 32, kBM))) return rc;
-  if ((rc = make_map_bf16(&m.w, w_dev, a.N, 2ll * ((a.K + 31) / 32 * 32), 64, a.n_box))) return rc;
   if ((rc = hs::tc::make_map(&m.d, d_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
   m.aux = m.d;
   m.d2 = m.d;
   if (aux_dev && (rc = hs::tc::make_map(&m.aux, aux_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
   if (d2_dev && (rc = hs::tc::make_map(&m.d2, d2_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
   const size_t smem = smem_bytes<E>(a);
-  HS_CUDA(cudaFuncSetAttribute(gemm3_kernel<E, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // the dynamic shared-memory limit is raised once per (instantiation, device) to the largest plan; an immutable cache
+  // (the value never changes afterwards), so that no attribute call happens inside a CUDA-graph capture
+  static bool raised[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !raised[dev]) {
+    HS_CUDA(cudaFuncSetAttribute(gemm3_kernel<E, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAvail + 1024));
+    if (dev >= 0 && dev < 64) raised[dev] = true;
+  }
+  const int cs = a.cluster;
   int per_chunk = hs::tc::sm_count() / a.n_chunks;
-  if (per_chunk < 1) per_chunk = 1;
   if (per_chunk > a.tiles) per_chunk = (int)a.tiles;
-  gemm3_kernel<E, MODE><<<a.n_chunks * per_chunk, (E + kCvtWarps + 3) * 32, smem, stream>>>(m.a, m.w, m.aux, m.d, m.d2, a);
+  per_chunk = per_chunk / cs * cs;
+  if (per_chunk < cs) per_chunk = cs;
+  if ((rc = make_map_bf16(&m.w, w_dev, a.N, 2ll * ((a.K + 31) / 32 * 32), 64, a.n_box / cs))) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(a.n_chunks * per_chunk));
+  cfg.blockDim = dim3((E + kCvtWarps + 3) * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  HS_CUDA(cudaLaunchKernelEx(&cfg, gemm3_kernel<E, MODE>, m.a, m.w, m.aux, m.d, m.d2, a));
   HS_LAUNCH_CHECK();
   return HS_OK;
 }
@@ -510,7 +613,7 @@ int hs_gemm3_supported(int64_t T, int N, int K) {
 }
 
 int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
-             float* d2_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream) {
+             float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream) {
   HS_REQUIRE(a_dev && wsplit_dev && d_dev && T > 0, "hs_gemm3: bad arguments");
   HS_REQUIRE(mode >= MODE_PLAIN && mode <= MODE_GELU_GRAD, "hs_gemm3: unknown mode %d", mode);
   HS_REQUIRE(drop >= 0.f && drop < 1.f, "hs_gemm3: drop must be in [0, 1), got %f", drop);
@@ -525,7 +628,7 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
                 reinterpret_cast<uintptr_t>(d_dev) | reinterpret_cast<uintptr_t>(d2_dev)) & 15),
              "hs_gemm3: tensors must be 16-byte aligned");
   G3Args a{};
-  a.bias = bias_dev; a.T = T; a.N = N; a.K = K;
+  a.bias = bias_dev; a.colsum = colsum_dev; a.T = T; a.N = N; a.K = K;
   a.drop_thresh = drop > 0.f ? hs::drop_thresh(drop) : 0u;
   a.drop_scale = 1.0f / (1.0f - drop);
   a.seed = seed;

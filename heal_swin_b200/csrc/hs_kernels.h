@@ -29,10 +29,5 @@ int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, con
                        const uint8_t* groups, const float* bias, const float* logit_scale, float scale, DropCfg drop,
                        float* dqkv, float* dbias, float* dlogit, int B, int64_t N, int C, int H, uint32_t flags,
                        cudaStream_t stream);
-// 16 elementwise warps, two warpgroups per unit (hs_attn_bwd_tc_v2.cu); HEALSWIN_ATTN_BWD_V2 selects it
-int window_attn_bwd_tc_v2(const float* qkv, const float* out, const float* lse, const float* dout, const int32_t* src,
-                          const uint8_t* groups, const float* bias, const float* logit_scale, float scale, DropCfg drop,
-                          float* dqkv, float* dbias, float* dlogit, int B, int64_t N, int C, int H, uint32_t flags,
-                          cudaStream_t stream);
 
 }  // namespace hs

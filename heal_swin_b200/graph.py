@@ -1,0 +1,103 @@
+"""Whole-step CUDA-graph replay for training the drop-in model.
+
+An eager training step of the N_side=256 network is ~900 kernel launches; at the small stages the GPU waits for the host
+between them (5 % of the step, profiles/r1s_step_composition.log).  ``GraphedTrainStep`` captures forward + loss +
+backward once and replays it: one launch per step, no host work in between.
+
+What makes the capture legal: every hs_* entry point takes its stream explicitly (``ops.current_stream()`` is the
+capturing stream, also on the autograd thread), allocates nothing and never synchronises; TMA descriptors are kernel
+parameters built on the host from addresses that torch serves from the graph's private pool, hence stable across replays;
+the weight-split cache re-launches its (cheap) split kernels inside a capture instead of trusting the host-side version
+check, so a replay always sees the weights the optimizer just wrote.
+
+Data parallelism: the captured part is rank-local.  Gradients live in ONE flat buffer (each ``p.grad`` is a view), so the
+exchange step after the replay is a single NCCL all-reduce over NVLink, followed by the (eager, fused) optimizer step.
+The reference gets the same semantics from Lightning's DDP plugin (heal_swin/train.py:187).
+
+Limits: dropout / stochastic depth draw their mask seeds on the host, so a replay would repeat the captured masks --
+models with a non-zero drop probability in training mode are refused (use the eager path for those).
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _active_drop_probability(model):
+    worst = 0.0
+    for m in model.modules():
+        p = m.p if isinstance(m, torch.nn.Dropout) else getattr(m, "drop_prob", None)
+        if p and m.training:
+            worst = max(worst, float(p))
+    return worst
+
+
+class GraphedTrainStep:
+    """``loss = step(x, t)``: copies the batch into static buffers, replays forward + loss + backward, all-reduces the flat
+    gradient over the data-parallel ranks and runs ``optimizer.step()``.  ``loss`` is a static device tensor (read it after
+    the call; it is overwritten by the next one).
+
+    ``x`` / ``t`` may be HOST tensors (pinned memory): they are copied straight into the static device buffers.  With
+    ``preprocess`` the static buffers hold the RAW batch (e.g. uint8 images and class ids, as the data pipeline delivers
+    them) and ``x, t = preprocess(raw_x, raw_t)`` -- the ``x.float()`` of the Lightning wrapper,
+    models_lightning/segmentation/model_lightning_swin_hp.py:61 -- runs inside the captured graph."""
+
+    def __init__(self, model, loss_fn, optimizer, example_x, example_t, warmup=3, preprocess=None):
+        p = _active_drop_probability(model)
+        assert p == 0.0, (f"the model has an active drop probability of {p}: a graph replay would repeat the captured "
+                          "dropout masks; train such configurations eagerly")
+        self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.params = [q for q in model.parameters() if q.requires_grad]
+        total = sum(q.numel() for q in self.params)
+        self.flat_grad = torch.zeros(total, device=example_x.device, dtype=torch.float32)
+        off = 0
+        for q in self.params:
+            assert q.dtype == torch.float32
+            q.grad = self.flat_grad[off:off + q.numel()].view_as(q)
+            off += q.numel()
+        self.x = example_x.clone()
+        self.t = example_t.clone()
+        self.warmup = warmup
+        self.preprocess = preprocess
+        self.graph = None
+        self.loss = torch.zeros((), device=example_x.device, dtype=torch.float32)
+
+    def capture(self):
+        """Warm-up on a side stream, then capture (done lazily by the first replaying call)."""
+        was_timing, ops.STATS.timing = ops.STATS.timing, False
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # eager warm-up on a side stream, as torch.cuda.graphs requires
+            for _ in range(self.warmup):
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            loss = self._fwd_bwd()
+            self.loss.copy_(loss)
+        self.flat_grad.zero_()
+        ops.STATS.timing = was_timing
+
+    def _fwd_bwd(self):
+        self.flat_grad.zero_()
+        x, t = (self.x, self.t) if self.preprocess is None else self.preprocess(self.x, self.t)
+        loss = self.loss_fn(self.model(x), t)
+        loss.backward()  # accumulates in place into the views of flat_grad
+        return loss.detach()
+
+    def __call__(self, x, t, eager=False):
+        """``eager=True`` runs the very same step without the graph (per-kernel timing, debugging)."""
+        self.x.copy_(x, non_blocking=True)
+        self.t.copy_(t, non_blocking=True)
+        if eager:
+            self.loss.copy_(self._fwd_bwd())
+        else:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        if self.world > 1:
+            dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)
+            self.flat_grad.mul_(1.0 / self.world)
+        self.optimizer.step()
+        return self.loss

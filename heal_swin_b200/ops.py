@@ -368,21 +368,36 @@ def get_gemm_mode() -> str:
     return _GEMM_MODE
 
 
-_SPLITS = {}  # (id(weight), transposed) -> (weakref, version, data_ptr, split tensor)
+_SPLITS = {}  # (id(weight), transposed) -> (weakref, version, data_ptr, split tensor, epoch)
+_SPLIT_EPOCH = [0]
+
+
+def _on_optimizer_step(*_):
+    """Global torch.optim post-step hook: fused optimizers (Adam(fused=True), the one bench.py uses) update the parameters
+    WITHOUT bumping their version counters, so every optimizer step starts a new epoch of the split cache."""
+    _SPLIT_EPOCH[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_step  # noqa: E402
+
+_register_post_step(_on_optimizer_step)
 
 
 def split_weight(weight, transposed=False):
     """The bf16 [hi | lo] operand of ``weight`` (N, K) for hs_gemm3: (N, 2 * ceil32(K)) for the forward, or with
-    ``transposed`` (K, 2 * ceil32(N)) for the input gradient.  Cached per parameter and redone when the parameter's
-    version counter moves (optimizer step, load_state_dict, DDP broadcast); the buffer is reused so that its address is
-    stable.  Call ``invalidate_weight_splits()`` after writing through ``.data``."""
+    ``transposed`` (K, 2 * ceil32(N)) for the input gradient.  Cached per parameter; redone when the parameter's version
+    counter moves (load_state_dict, DDP broadcast, any in-place op), after every torch optimizer step (see above), and on
+    every use inside a CUDA-graph capture (a replay cannot consult the host).  The buffer is reused, so its address is
+    stable.  Call ``invalidate_weight_splits()`` after writing parameters in a way neither mechanism sees (``.data``
+    assignment from a custom optimizer that is not a torch.optim.Optimizer)."""
     w = weight.detach()
     N, K = w.shape
     key = (id(weight), bool(transposed))
     ent = _SPLITS.get(key)
     ver = weight._version
     if ent is not None and ent[0]() is weight and ent[2] == w.data_ptr():
-        if ent[1] == ver:
+        if (ent[1] == ver and ent[4] == _SPLIT_EPOCH[0]
+                and not (w.is_cuda and torch.cuda.is_current_stream_capturing())):
             return ent[3]
         out = ent[3]
     else:
@@ -395,7 +410,7 @@ def split_weight(weight, transposed=False):
         if len(_SPLITS) > 1024:
             for k in [k for k, v in _SPLITS.items() if v[0]() is None]:
                 del _SPLITS[k]
-        _SPLITS[key] = (weakref.ref(weight), ver, w.data_ptr(), out)
+        _SPLITS[key] = (weakref.ref(weight), ver, w.data_ptr(), out, _SPLIT_EPOCH[0])
     return out
 
 
@@ -419,13 +434,14 @@ def _dgrad_ok(dy2, weight) -> bool:
                 and lib.hs_gemm3_supported(dy2.shape[0], weight.shape[1], weight.shape[0]))
 
 
-def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, seed=0):
-    """hs_gemm3 on a (T, K) activation and a split weight; returns d, or (d, d2) for GEMM_GELU."""
+def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, seed=0, colsum=None):
+    """hs_gemm3 on a (T, K) activation and a split weight; returns d, or (d, d2) for GEMM_GELU.  ``colsum`` (K floats,
+    zero or a running sum) receives the column sums of ``a2`` in the same pass."""
     T, K = a2.shape
     d = torch.empty((T, N), device=a2.device, dtype=torch.float32)
     d2 = torch.empty_like(d) if mode == _lib.GEMM_GELU else None
-    STATS.launch("gemm3", lib.hs_gemm3, ptr(a2), ptr(wsplit), ptr(bias), ptr(aux), ptr(d), ptr(d2), T, N, K, mode,
-                 C.c_float(drop), C.c_uint64(seed), current_stream(), tag=(T, N, K, mode))
+    STATS.launch("gemm3", lib.hs_gemm3, ptr(a2), ptr(wsplit), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K,
+                 mode, C.c_float(drop), C.c_uint64(seed), current_stream(), tag=(T, N, K, mode))
     return (d, d2) if mode == _lib.GEMM_GELU else d
 
 
@@ -436,17 +452,29 @@ def _gemm_fwd(x2, weight, bias):
     return torch.nn.functional.linear(x2, weight, bias)
 
 
-def _dgrad(dy2, weight, d_pass, xshape):
+def _dgrad(dy2, weight, d_pass, xshape, want_bias_grad=False):
     """dy2 @ weight (+ the gradient that reached the forked shortcut output), shaped like the input.  The shortcut
-    gradient is added in the GEMM's epilogue (GEMM_ADD): no accumulation pass over the activation."""
+    gradient is added in the GEMM's epilogue (GEMM_ADD): no accumulation pass over the activation.  With
+    ``want_bias_grad`` the column sums of dy2 -- the bias gradient of this linear -- are taken in the same pass over dy2 (the
+    GEMM's operand converters see every element anyway); returns (dx, db)."""
     N, K = weight.shape
     c = None if d_pass is None else _f32c(d_pass).reshape(-1, K)
+    db = None
     if _dgrad_ok(dy2, weight):
+        if want_bias_grad:
+            db = torch.zeros((N,), device=dy2.device, dtype=torch.float32)
         dx = _gemm3(dy2, split_weight(weight, transposed=True), K, None, c,
-                    _lib.GEMM_PLAIN if c is None else _lib.GEMM_ADD)
+                    _lib.GEMM_PLAIN if c is None else _lib.GEMM_ADD, colsum=db)
     else:
         dx = dy2 @ weight if c is None else torch.addmm(c, dy2, weight)
-    return dx.view(xshape)
+        if want_bias_grad:
+            db = dy2.sum(0)
+    return (dx.view(xshape), db) if want_bias_grad else dx.view(xshape)
+
+
+def _wgrad_fuses_bias(dy2, x2) -> bool:
+    return bool(_CUSTOM_WGRAD and _on_device(dy2)
+                and lib.hs_linear_wgrad_supported(dy2.shape[0], dy2.shape[1], x2.shape[1]) == 2)
 
 
 def _wgrad(dy2, x2, need_bias):
@@ -490,12 +518,20 @@ class _LinearFn(torch.autograd.Function):
         if dy is None:
             return d_pass, None, None, None
         dy2 = _f32c(dy).reshape(-1, N)
-        if ctx.needs_input_grad[0]:
-            dx = _dgrad(dy2, weight, d_pass, x.shape)
+        x2 = _f32c(x).reshape(-1, K)
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        # the bias gradient rides along with the weight-gradient kernel where that covers it, else with the input-gradient
+        # GEMM (both read dy anyway); a separate reduction over dy only when neither runs
+        b_in_wgrad = need_b and ctx.needs_input_grad[1] and _wgrad_fuses_bias(dy2, x2)
+        if ctx.needs_input_grad[0]:
+            if need_b and not b_in_wgrad:
+                dx, db = _dgrad(dy2, weight, d_pass, x.shape, want_bias_grad=True)
+            else:
+                dx = _dgrad(dy2, weight, d_pass, x.shape)
         if ctx.needs_input_grad[1]:
-            dw, db = _wgrad(dy2, _f32c(x).reshape(-1, K), need_b)
-        elif need_b:
+            dw, db2 = _wgrad(dy2, x2, need_b and db is None)
+            db = db if db is not None else db2
+        elif need_b and db is None:
             db = dy2.sum(0)
         return dx, dw, db, None
 
@@ -536,8 +572,14 @@ class _MlpFn(torch.autograd.Function):
                          tag=(T, Cout, J))
         else:
             dz = _gemm3(dy2, split_weight(w2, transposed=True), J, _f32c(b1), z, _lib.GEMM_GELU_GRAD, *ctx.drop)
-        dw1, db1 = _wgrad(dz, x2, True)
-        dx = _dgrad(dz, w1, d_pass, ctx.xshape) if ctx.needs_input_grad[0] else None
+        dx = db1 = None
+        if ctx.needs_input_grad[0]:
+            if _wgrad_fuses_bias(dz, x2):
+                dx = _dgrad(dz, w1, d_pass, ctx.xshape)
+            else:  # fc1's bias gradient = column sums of dz, taken by the input-gradient GEMM in its pass over dz
+                dx, db1 = _dgrad(dz, w1, d_pass, ctx.xshape, want_bias_grad=True)
+        dw1, db1b = _wgrad(dz, x2, db1 is None)
+        db1 = db1 if db1 is not None else db1b
         return dx, dw1, db1, dw2, None, None, None
 
 

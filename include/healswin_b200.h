@@ -217,6 +217,8 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
  *   mode 1 (add)        d = acc + bias + aux                  aux: (T, N) fp32, e.g. the residual-shortcut gradient
  *   mode 2 (gelu)       d = acc,  d2 = dropout(GELU(acc + bias))      Mlp fc1 + act + drop (:39-41); exact erf GELU
  *   mode 3 (gelu grad)  d = acc * GELU'(aux + bias) * dropmask        aux = the bias-free fc1 output z
+ * colsum: (K) or NULL: colsum[k] += sum_t a[t][k] in the same pass -- when a is the output gradient of a linear (input-
+ * gradient form) this is that linear's bias gradient, so no separate reduction over the activation is needed.
  * bias: (N) or NULL.  drop / seed: the element dropout of modes 2 / 3 (mask = pure function of (seed, row, col), as
  * hs_bias_gelu_fwd).  All of d, d2, aux are (T, N) fp32 row-major.  hs_gemm3_supported: N, K multiples of 4 (TMA row pitch);
  * ragged 32-wide chunks are zero-filled on load and clipped on store by the TMA unit.
@@ -224,7 +226,7 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
 int hs_weight_split(const float* w_dev, int rows, int cols, int ld, int transposed, uint16_t* out_dev, void* stream);
 int hs_gemm3_supported(int64_t T, int N, int K);
 int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
-             float* d2_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream);
+             float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream);
 
 /*
  * Decoder tail, fused: logits = Conv1d_1x1(LayerNorm(x)) (FinalPatchExpand_X4.norm + SwinHPTransformerSys.output,

@@ -36,14 +36,14 @@ def split(w, transposed=False):
     return out
 
 
-def gemm3(a, ws, bias=None, aux=None, mode=0, drop=0.0, seed=0, d=None, d2=None):
+def gemm3(a, ws, bias=None, aux=None, mode=0, drop=0.0, seed=0, d=None, d2=None, colsum=None):
     T, K = a.shape
     N = ws.shape[0]
     if d is None:
         d = torch.empty((T, N), device=a.device, dtype=torch.float32)
     if mode == 2 and d2 is None:
         d2 = torch.empty_like(d)
-    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), T, N, K, mode, C.c_float(drop),
+    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K, mode, C.c_float(drop),
                        C.c_uint64(seed), current_stream()))
     return (d, d2) if mode == 2 else d
 

@@ -78,13 +78,13 @@ def test_argument_validation_happens_before_any_device_work():
     assert rc == 1 and "drop" in _lib.last_error()
     rc = lib.hs_mlp_dgrad_gelu(one, one, one, null, C.c_float(0.0), 0, one, 8192, 384, 1536, 0, null)
     assert rc == 3 and "not covered" in _lib.last_error()
-    rc = lib.hs_gemm3(null, one, null, null, one, null, 8, 32, 32, 0, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(null, one, null, null, one, null, null, 8, 32, 32, 0, C.c_float(0.0), 0, null)
     assert rc == 1 and "bad arguments" in _lib.last_error()
-    rc = lib.hs_gemm3(one, one, null, null, one, null, 8, 32, 32, 1, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 32, 32, 1, C.c_float(0.0), 0, null)
     assert rc == 1 and "aux" in _lib.last_error()
-    rc = lib.hs_gemm3(one, one, null, null, one, null, 8, 32, 32, 2, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 32, 32, 2, C.c_float(0.0), 0, null)
     assert rc == 1 and "second output" in _lib.last_error()
-    rc = lib.hs_gemm3(one, one, null, null, one, null, 8, 30, 32, 0, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 30, 32, 0, C.c_float(0.0), 0, null)
     assert rc == 3 and "not covered" in _lib.last_error()
     rc = lib.hs_weight_split(null, 4, 4, 4, 0, one, null)
     assert rc == 1

@@ -26,13 +26,13 @@ def _split(w, transposed=False):
     return out
 
 
-def _gemm3(a, ws, N, bias=None, aux=None, mode=0, drop=0.0, seed=0):
+def _gemm3(a, ws, N, bias=None, aux=None, mode=0, drop=0.0, seed=0, colsum=None):
     from heal_swin_b200._lib import check, current_stream, lib, ptr
 
     T, K = a.shape
     d = torch.full((T, N), float("nan"), device=a.device)
     d2 = torch.full((T, N), float("nan"), device=a.device) if mode == 2 else None
-    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), T, N, K, mode, C.c_float(drop),
+    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K, mode, C.c_float(drop),
                        C.c_uint64(seed), current_stream()))
     return (d, d2) if mode == 2 else d
 
@@ -95,6 +95,19 @@ def test_gelu_epilogues_match_fp64(T, N, K):
     u = (zz.double() + b.double()).requires_grad_(True)
     torch.nn.functional.gelu(u).sum().backward()
     assert rel_err(got.cpu(), (z_want * u.grad).cpu()) < TOL
+
+
+@pytest.mark.parametrize("T,N,K,mode", [(1000, 96, 288, 0), (4096, 384, 1152, 1), (777, 96, 100, 0), (2048, 768, 3072, 1)])
+def test_column_sums_ride_along(T, N, K, mode):
+    """colsum += column sums of the A operand (the bias gradient of a linear whose output gradient is A), accumulated once
+    although several column-chunk CTAs convert the same A tile; rows beyond T and columns beyond K contribute nothing."""
+    a, w, b = _data(T, N, K, seed=3)
+    aux = torch.randn(T, N, device=a.device) if mode == 1 else None
+    cs = torch.full((K,), 2.0, device=a.device)
+    got = _gemm3(a, _split(w), N, None, aux, mode=mode, colsum=cs)
+    want = a.double() @ w.double().t() + (aux.double() if mode == 1 else 0)
+    assert rel_err(got.cpu(), want.cpu()) < TOL
+    assert rel_err(cs.cpu(), (a.double().sum(0) + 2.0).cpu()) < 1e-5
 
 
 def test_dropout_masks_match_the_bias_gelu_kernels():

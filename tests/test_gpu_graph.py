@@ -1,0 +1,63 @@
+"""GraphedTrainStep (heal_swin_b200/graph.py): the CUDA-graph replay of forward + loss + backward trains exactly like the
+eager step -- in particular the weight-split operands of the bf16x3 GEMMs are refreshed inside the graph after every
+optimizer step -- and refuses configurations whose dropout masks a replay would repeat."""
+import copy
+
+import pytest
+import torch
+
+from tests.util import build_product_model
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(patch_size=4, window_size=64, shift_size=4, shift_strategy="ring_shift", rel_pos_bias="flat", embed_dim=96,
+          depths=[2, 2], num_heads=[3, 6], use_cos_attn=True, use_v2_norm_placement=True, dim_in=8 * 32 * 32, f_in=3,
+          f_out=5, base_pix=8)
+
+
+def _data(dev, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(4, KW["f_in"], KW["dim_in"], generator=g).to(dev)
+    return x, ((x[:, 0] > 0).long() + 2 * (x[:, 1] > 0).long())
+
+
+def test_graph_replay_trains_like_the_eager_step():
+    from heal_swin_b200.graph import GraphedTrainStep
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model_a = build_product_model(KW, None, dev).train()
+    model_b = copy.deepcopy(model_a)
+    loss_fn = torch.nn.CrossEntropyLoss()
+    opt_a = torch.optim.Adam(model_a.parameters(), lr=2e-3, fused=True)
+    opt_b = torch.optim.Adam(model_b.parameters(), lr=2e-3, fused=True)
+    x0, t0 = _data(dev, 0)
+    step = GraphedTrainStep(model_a, loss_fn, opt_a, x0, t0)
+    la, lb = [], []
+    for i in range(6):
+        x, t = _data(dev, i % 2)  # alternate two batches: the static input buffers must be refreshed
+        la.append(float(step(x, t)))
+        opt_b.zero_grad(set_to_none=True)
+        loss = loss_fn(model_b(x), t)
+        loss.backward()
+        opt_b.step()
+        lb.append(float(loss))
+    assert la[-1] < la[0]  # it trains: the replays see the updated weights
+    for a, b in zip(la, lb):
+        assert abs(a - b) <= 2e-3 * abs(b), (la, lb)  # same trajectory up to summation order (atomics in the wgrad kernels)
+    pa, pb = dict(model_a.named_parameters()), dict(model_b.named_parameters())
+    for k in ("layers.0.blocks.1.attn.qkv.weight", "decoder.up.expand.weight", "layers.1.blocks.0.mlp.fc1.bias"):
+        assert float((pa[k] - pb[k]).norm() / pb[k].norm()) < 2e-3, k
+    # the eager form of the same step object gives the same numbers as a replay
+    l_eager = float(step(x0, t0, eager=True))
+    assert abs(l_eager - float(loss_fn(model_a(x0), t0))) < 0.2  # (weights moved by one more step in between)
+
+
+def test_graph_refuses_active_dropout():
+    from heal_swin_b200.graph import GraphedTrainStep
+
+    dev = torch.device("cuda:0")
+    model = build_product_model(dict(KW, drop_rate=0.1), None, dev).train()
+    x0, t0 = _data(dev, 0)
+    with pytest.raises(AssertionError, match="drop probability"):
+        GraphedTrainStep(model, torch.nn.CrossEntropyLoss(), torch.optim.Adam(model.parameters()), x0, t0)

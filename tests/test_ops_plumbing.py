@@ -26,8 +26,10 @@ class FakeLib:
         self.calls = []
         self.splits = 0
 
+    wgrad_cover = 2
+
     def hs_linear_wgrad_supported(self, T, N, K):
-        return 2
+        return self.wgrad_cover
 
     def hs_mlp_dgrad_gelu_supported(self, T, Cc, J):
         return 1
@@ -64,8 +66,10 @@ class FakeLib:
         o[:, :, 32:] = lo.view(rows, nk, 32)
         return 0
 
-    def hs_gemm3(self, a, ws, bias, aux, d, d2, T, N, K, mode, drop, seed, stream):
-        self.calls.append(f"gemm3:{mode}")
+    def hs_gemm3(self, a, ws, bias, aux, d, d2, colsum, T, N, K, mode, drop, seed, stream):
+        self.calls.append(f"gemm3:{mode}" + ("+colsum" if colsum is not None else ""))
+        if colsum is not None:
+            colsum += a.sum(0)
         assert _val(drop) == 0.0 and a.shape == (T, K) and ws.shape[0] == N
         o = ws.view(N, -1, 64).float()
         w = (o[:, :, :32] + o[:, :, 32:]).reshape(N, -1)[:, :K]   # hi + lo: the weight to ~2^-17
@@ -183,8 +187,8 @@ def test_fused_mlp_node_matches_torch_autograd(fake, fork):
     out = ops._MlpFn.apply(x, w1, b1, w2, 0.0, 0, fork)
     y = out[0] + out[1] if fork else out
     y.backward(gy)
-    # fc1 + GELU epilogue, fc2 | wgrad(fc2), fused dgrad + GELU', wgrad(fc1) + bias, dgrad (+ shortcut gradient when forked)
-    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "mlp_dgrad_gelu", "wgrad", "gemm3:1" if fork else "gemm3:0"]
+    # fc1 + GELU epilogue, fc2 | wgrad(fc2), fused dgrad + GELU', dgrad (+ shortcut gradient when forked), wgrad(fc1) + bias
+    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "mlp_dgrad_gelu", "gemm3:1" if fork else "gemm3:0", "wgrad"]
     got = [t.grad.clone() for t in (x, w1, b1, w2)]
     for t in (x, w1, b1, w2):
         t.grad = None
@@ -227,7 +231,7 @@ def test_mlp_node_uses_the_gelu_grad_epilogue_where_the_tf32_kernel_does_not_cov
     b1 = torch.randn(32, generator=g, requires_grad=True)
     w2 = (torch.randn(8, 32, generator=g) / 6).requires_grad_(True)
     ops._MlpFn.apply(x, w1, b1, w2, 0.0, 0, False).sum().backward()
-    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "gemm3:3", "wgrad", "gemm3:0"]
+    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "gemm3:3", "gemm3:0", "wgrad"]
     got = [t.grad.clone() for t in (x, w1, b1, w2)]
     for t in (x, w1, b1, w2):
         t.grad = None
@@ -246,5 +250,36 @@ def test_weight_splits_are_cached_until_the_parameter_changes(fake):
         w.mul_(2.0)  # an optimizer step bumps the version counter
     b = ops.split_weight(w)
     assert fake.splits == 3 and b is a  # same buffer (stable address), new contents
+    # fused optimizers do not bump the version counter: the global optimizer post-step hook starts a new cache epoch
+    opt = torch.optim.Adam([w], lr=0.1, fused=True)
+    w.grad = torch.ones_like(w)
+    v0 = w._version
+    opt.step()
+    assert w._version == v0, "torch changed: fused Adam now bumps versions (the hook is then merely redundant)"
+    assert ops.split_weight(w) is a and fake.splits == 4
+    assert ops.split_weight(w) is a and fake.splits == 4  # cached again until the next step
+    b = ops.split_weight(w)
     hi_lo = b.view(8, 1, 64).float()
     assert _close((hi_lo[:, 0, :32] + hi_lo[:, 0, 32:])[:, :12], w.detach(), 1e-4)
+
+
+def test_bias_gradient_rides_with_the_dgrad_gemm_where_the_wgrad_kernel_cannot_fuse_it(fake):
+    fake.wgrad_cover = 1  # weight gradient covered, bias not (K > 224 in the real kernel)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(9, 8, generator=g, requires_grad=True)
+    w = torch.randn(12, 8, generator=g, requires_grad=True)
+    b = torch.randn(12, generator=g, requires_grad=True)
+    ops._LinearFn.apply(x, w, b, False).square().sum().backward()
+    assert fake.calls == ["gemm3:0", "gemm3:0+colsum", "wgrad"]
+    got = [t.grad.clone() for t in (x, w, b)]
+    for t in (x, w, b):
+        t.grad = None
+    F.linear(x, w, b).square().sum().backward()
+    for a, t in zip(got, (x, w, b)):
+        assert _close(a, t.grad, 1e-4)
+    # no input gradient wanted (first layer): plain reduction
+    fake.calls.clear()
+    x2 = torch.randn(9, 8, generator=g)
+    w.grad = b.grad = None
+    ops._LinearFn.apply(x2, w, b, False).sum().backward()
+    assert fake.calls == ["gemm3:0", "wgrad"] and _close(b.grad, torch.full((12,), 9.0))
