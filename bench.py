@@ -218,14 +218,15 @@ def alg_bytes(name, tag):
         return tag[0] * (2 * tag[1] + tag[2] + 2) * 4
     if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
         return tag[0] * (tag[1] + 2 * tag[2]) * 4
-    if name == "gemm3":            # tag (T, N, K, mode): a (T, K) in, d (T, N) out, + aux in (modes 1, 3) / d2 out (mode 2)
+    if name == "gemm3":            # tag (T, N, K, mode, precision): a (T, K) in, d (T, N) out, + aux in (modes 1, 3) / d2 out (2)
         return tag[0] * (tag[2] + tag[1] * (1 if tag[3] == 0 else 2)) * 4
     return None
 
 
 def gemm3_flops(tag):
-    """bf16 tensor-core flops one hs_gemm3 launch executes: three MMAs per product (hi*hi + lo*hi + hi*lo)."""
-    return 3 * 2.0 * tag[0] * tag[1] * tag[2]
+    """Tensor-core flops one hs_gemm3 launch executes, in bf16-MMA units: three MMAs per product for bf16x3 (hi*hi + lo*hi
+    + hi*lo), one TF32 MMA = two units (half the bf16 rate), one bf16 MMA = one."""
+    return {0: 3, 1: 2, 2: 1}[tag[4] if len(tag) > 4 else 0] * 2.0 * tag[0] * tag[1] * tag[2]
 
 
 def summarize_kernels(kernel_ms, ms_dev, hbm_peak, peak_src, traffic):

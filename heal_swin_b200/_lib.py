@@ -16,6 +16,7 @@ ATTN_COS = 1
 ATTN_NO_TC = 2
 ATTN_NO_TRUNC_COMP = 4
 GEMM_PLAIN, GEMM_ADD, GEMM_GELU, GEMM_GELU_GRAD = 0, 1, 2, 3
+PREC_BF16X3, PREC_TF32, PREC_BF16 = 0, 1, 2
 
 STRATEGY_CODES = {"nest_roll": SHIFT_NEST_ROLL, "nest_grid_shift": SHIFT_NEST_GRID, "ring_shift": SHIFT_RING}
 
@@ -43,9 +44,9 @@ SIGNATURES = {
     "hs_linear_wgrad": [_p, _p, _p, _p, _i64, _i, _i, _u32, _p],
     "hs_mlp_dgrad_gelu_supported": [_i64, _i, _i],
     "hs_mlp_dgrad_gelu": [_p, _p, _p, _p, _f, _u64, _p, _i64, _i, _i, _u32, _p],
-    "hs_weight_split": [_p, _i, _i, _i, _i, _p, _p],
+    "hs_weight_split": [_p, _i, _i, _i, _i, _i, _p, _p],
     "hs_gemm3_supported": [_i64, _i, _i],
-    "hs_gemm3": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _f, _u64, _p],
+    "hs_gemm3": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _f, _u64, _p],
     "hs_ln_head_supported": [_i64, _i, _i],
     "hs_ln_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _f, _p],
     "hs_ln_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],

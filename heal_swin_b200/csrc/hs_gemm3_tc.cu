@@ -55,6 +55,9 @@ constexpr int kASlots = 4;             // ... + 4 A-operand slots of 32 columns 
 constexpr int kACol0 = 2 * kStageCols;
 
 enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3 };
+// operand precision: three bf16 MMAs per product (fp32-class), one TF32 MMA (A straight from the fp32 tile, no conversion;
+// input gradients of the tensor-bound stages), one bf16 MMA ("bf16 operands, fp32 accumulate": BASELINE configs[3])
+enum : int { PREC_BF16X3 = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
 
 struct G3Args {
   const float* bias;  // (N) or null
@@ -63,6 +66,7 @@ struct G3Args {
   int N, K;
   int n_stride, n_box, n_chunks;  // column chunks start every n_stride columns and compute n_box (multiple of 32)
   long long tiles;
+  int prec;     // PREC_*
   int cluster;  // CTAs per cluster (1, 2 or 4): streamed W slices are loaded once per cluster and multicast
   int ring, rw, resident, wring;  // A ring depth, staging regions per epilogue warp, W resident?, W ring depth
   uint32_t drop_thresh;
@@ -74,11 +78,12 @@ struct G3Args {
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                             uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem], TF32 operands (fp32 words, the tensor core reads their top 19 bits)
+__device__ __forceinline__ void umma_tf32_ss_(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -146,7 +151,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&raw_full[i], 1);
-      mbar_init(&slot_empty[i], kCvtWarps);  // released by the converters: the chunk is in their registers
+      // released by the converters once the chunk is in their registers; in TF32 mode by the MMAs that read it (and by the
+      // converters as well when they take the column sums)
+      mbar_init(&slot_empty[i], a.prec == PREC_TF32 ? 1 + ((a.colsum && chunk == 0) ? kCvtWarps : 0) : kCvtWarps);
     }
     for (int i = 0; i < kASlots; ++i) {
       mbar_init(&a_full[i], kCvtWarps);
@@ -218,8 +225,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       const uint32_t idesc = idesc_bf16(128, 32 * S);
       if (a.resident) mbar_wait(&w_full, 0);
       const uint32_t wb = smem_u32(s_w);
-      int as_ = 0, ws = 0;
-      uint32_t aph = 0, wph = 0;
+      const uint32_t idesc32 = umma_idesc_tf32(128, 32 * S, 0, 0);
+      const uint32_t rb = smem_u32(s_ring);
+      int as_ = 0, ws = 0, slot = 0;
+      uint32_t aph = 0, wph = 0, ph = 0;
       long long it = 0;
       for (long long tile = t0; tile < t_end; tile += tstep, ++it) {
         const int st = (int)(it & 1);
@@ -228,20 +237,37 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const uint32_t d = tmem + (uint32_t)st * kStageCols;
         for (int kc = 0; kc < nk; ++kc) {
           if (!a.resident) mbar_wait(&wr_full[ws], wph);
-          mbar_wait(&a_full[as_], aph);
-          tc_fence_after();
-          const uint32_t at = tmem + kACol0 + 32 * as_;
           const uint32_t wk = wb + (a.resident ? kc : ws) * w_slice;
+          if (a.prec == PREC_TF32) {
+            // A: the fp32 chunk as TMA delivered it (K-major, SWIZZLE_128B); W slice: 32 tf32-rounded fp32 per row
+            mbar_wait(&raw_full[slot], ph);
+            tc_fence_after();
+            const uint32_t ab = rb + slot * kChunk;
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint32_t a_hi = at + 8 * ks, a_lo = at + 16 + 8 * ks;
-            const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
-            umma_bf16_ts(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-            umma_bf16_ts(d, a_hi, w_lo, idesc, 1u);
-            umma_bf16_ts(d, a_hi, w_hi, idesc, 1u);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_tf32_ss_(d, umma_desc_at(kDesc, ab + 32 * ks), umma_desc_at(kDesc, wk + 32 * ks), idesc32,
+                            (kc > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&slot_empty[slot]);
+            if (++slot == ring) { slot = 0; ph ^= 1; }
+          } else {
+            mbar_wait(&a_full[as_], aph);
+            tc_fence_after();
+            const uint32_t at = tmem + kACol0 + 32 * as_;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint32_t a_hi = at + 8 * ks, a_lo = at + 16 + 8 * ks;
+              const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
+              if (a.prec == PREC_BF16X3) {
+                umma_bf16_ts(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                umma_bf16_ts(d, a_hi, w_lo, idesc, 1u);
+                umma_bf16_ts(d, a_hi, w_hi, idesc, 1u);
+              } else {
+                umma_bf16_ts(d, a_hi, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(&a_empty[as_]);
+            if (++as_ == kASlots) { as_ = 0; aph ^= 1; }
           }
-          umma_commit(&a_empty[as_]);
-          if (++as_ == kASlots) { as_ = 0; aph ^= 1; }
           if (!a.resident) {
             if (cs > 1) umma_commit_multicast(&wr_empty[ws], cmask);
             else umma_commit(&wr_empty[ws]);
@@ -263,11 +289,13 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     int slot = 0, as_ = 0;
     uint32_t ph = 0, aph = 0;
     const bool do_colsum = a.colsum != nullptr && chunk == 0;
+    const bool convert = a.prec != PREC_TF32;  // TF32: the MMAs read the fp32 chunk directly
     const uint32_t cs_u32 = smem_u32(s_colsum);
     if (do_colsum) {
       for (int i = threadIdx.x - E * 32; i < nk * 32; i += kCvtWarps * 32) s_colsum[i] = 0.f;
       named_bar_sync(1, kCvtWarps * 32);
     }
+    if (convert || do_colsum)
     for (long long tile = t0; tile < t_end; tile += tstep)
       for (int kc = 0; kc < nk; ++kc) {
         mbar_wait(&raw_full[slot], ph);
@@ -308,11 +336,12 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         __syncwarp();  // every lane holds its part of the chunk in registers: the shared-memory slot can be refilled
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
         if (++slot == ring) { slot = 0; ph ^= 1; }
+        if (!convert) continue;
         mbar_wait(&a_empty[as_], aph ^ 1);  // the MMAs that read this tensor-memory slot have completed
         tc_fence_after();
         const uint32_t at = tmem + lane_addr + kACol0 + 32 * as_;
         tmem_st8(at + 8 * half, hi);
-        tmem_st8(at + 16 + 8 * half, lo);
+        if (a.prec == PREC_BF16X3) tmem_st8(at + 16 + 8 * half, lo);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -445,8 +474,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------------------------------
 // W (rows x cols fp32, row stride ld; element (r, c) = w[r * ld + c], or w[c * ld + r] when transposed) ->
 // out (rows, ceil(cols / 32), 64) bf16 = [hi(32) | lo(32)] per 32-wide chunk of the contraction axis (zero padded).
+// format 1: out (rows, ceil(cols / 32), 32) fp32 rounded to the nearest TF32 (the single-MMA TF32 mode; same bytes per row).
 __global__ void weight_split_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int rows, int cols, int ld,
-                                    int transposed) {
+                                    int transposed, int format) {
   __shared__ float tile[32][33];
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
@@ -464,6 +494,12 @@ __global__ void weight_split_kernel(const float* __restrict__ w, uint16_t* __res
   for (int i = ty; i < 32; i += 8) {
     if (r0 + i >= rows) continue;
     const float x = tile[i][tx];
+    if (format == 1) {
+      uint32_t t;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+      reinterpret_cast<uint32_t*>(out)[((long long)(r0 + i) * gridDim.x + blockIdx.x) * 32 + tx] = t;
+      continue;
+    }
     const uint32_t hb = cvt_bf16x2(0.f, x) & 0xffffu;
     const float h = __uint_as_float(hb << 16);
     const uint32_t lb = cvt_bf16x2(0.f, x - h) & 0xffffu;
@@ -525,9 +561,11 @@ int plan(G3Args& a, int mode, int E) {
     a.ring = ring;
     left -= (long long)ring * kChunk;
     a.rw = rw_min + (int)(left / ((long long)E * kRegion));  // (staging_min already holds rw_min regions + the column sums)
-    // streamed W with a long contraction = the tensor-bound shapes, whose limit is L2 -> SM bandwidth: share the W slices
+    // Streamed W slices can be loaded once per cluster of 2 / 4 CTAs and multicast (HEALSWIN_GEMM3_CLUSTER): verified
+    // correct on the B200 and measured to change nothing (profiles/r2i_gemm3_check.log) -- the shapes that stream W are
+    // bound by the tensor pipe at the power-capped clock (81 % of the sustained cuBLAS bf16 rate with three MMAs per
+    // product), not by L2 -> SM traffic -- so the default stays one CTA per cluster.
     a.cluster = 1;
-    if (!resident && box % 64 == 0 && a.tiles >= 2 * 148) a.cluster = 2;
     if (a.rw > rw_max) a.rw = rw_max;
     if (ring >= 4) break;
   }
@@ -600,10 +638,11 @@ int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, floa
 
 extern "C" {
 
-int hs_weight_split(const float* w, int rows, int cols, int ld, int transposed, uint16_t* out, void* stream) {
+int hs_weight_split(const float* w, int rows, int cols, int ld, int transposed, int format, uint16_t* out, void* stream) {
   HS_REQUIRE(w && out && rows > 0 && cols > 0 && ld > 0, "hs_weight_split: bad arguments");
+  HS_REQUIRE(format == 0 || format == 1, "hs_weight_split: unknown format %d", format);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  weight_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, out, rows, cols, ld, transposed);
+  weight_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, out, rows, cols, ld, transposed, format);
   HS_LAUNCH_CHECK();
   return HS_OK;
 }
@@ -613,8 +652,10 @@ int hs_gemm3_supported(int64_t T, int N, int K) {
 }
 
 int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
-             float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream) {
+             float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, int precision, float drop, uint64_t seed,
+             void* stream) {
   HS_REQUIRE(a_dev && wsplit_dev && d_dev && T > 0, "hs_gemm3: bad arguments");
+  HS_REQUIRE(precision >= PREC_BF16X3 && precision <= PREC_BF16, "hs_gemm3: unknown precision %d", precision);
   HS_REQUIRE(mode >= MODE_PLAIN && mode <= MODE_GELU_GRAD, "hs_gemm3: unknown mode %d", mode);
   HS_REQUIRE(drop >= 0.f && drop < 1.f, "hs_gemm3: drop must be in [0, 1), got %f", drop);
   if (!hs_gemm3_supported(T, N, K))
@@ -628,7 +669,7 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
                 reinterpret_cast<uintptr_t>(d_dev) | reinterpret_cast<uintptr_t>(d2_dev)) & 15),
              "hs_gemm3: tensors must be 16-byte aligned");
   G3Args a{};
-  a.bias = bias_dev; a.colsum = colsum_dev; a.T = T; a.N = N; a.K = K;
+  a.bias = bias_dev; a.colsum = colsum_dev; a.T = T; a.N = N; a.K = K; a.prec = precision;
   a.drop_thresh = drop > 0.f ? hs::drop_thresh(drop) : 0u;
   a.drop_scale = 1.0f / (1.0f - drop);
   a.seed = seed;

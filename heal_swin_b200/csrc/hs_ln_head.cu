@@ -363,7 +363,8 @@ constexpr int kRB = 1;  // backward: rows per lane and iteration (2 needs 255 re
   switch (C / 32) {                                                        \
     case 1: HS_LH_DISPATCH_KQ(1, __VA_ARGS__) break;                       \
     case 2: HS_LH_DISPATCH_KQ(2, __VA_ARGS__) break;                       \
-    default: HS_LH_DISPATCH_KQ(3, __VA_ARGS__) break;                      \
+    case 3: HS_LH_DISPATCH_KQ(3, __VA_ARGS__) break;                       \
+    default: HS_LH_DISPATCH_KQ(4, __VA_ARGS__) break;                      \
   }
 
 }  // namespace
@@ -371,7 +372,7 @@ constexpr int kRB = 1;  // backward: rows per lane and iteration (2 needs 255 re
 extern "C" {
 
 int hs_ln_head_supported(int64_t rows, int C, int K) {
-  return (rows > 0 && (C == 32 || C == 64 || C == 96) && K >= 1 && K <= 16) ? 1 : 0;
+  return (rows > 0 && (C == 32 || C == 64 || C == 96 || C == 128) && K >= 1 && K <= 16) ? 1 : 0;
 }
 
 int hs_ln_head_fwd(const float* x, const float* gamma, const float* beta, const float* w, const float* head_bias,
@@ -381,7 +382,7 @@ int hs_ln_head_fwd(const float* x, const float* gamma, const float* beta, const 
   HS_REQUIRE(rows_per_sample > 0 && rows % rows_per_sample == 0, "hs_ln_head_fwd: rows (%lld) is not a multiple of "
              "rows_per_sample (%lld)", (long long)rows, (long long)rows_per_sample);
   if (!hs_ln_head_supported(rows, C, K))
-    return hs::fail(HS_ERR_UNSUPPORTED, "hs_ln_head_fwd: C=%d K=%d is not covered (C in {32, 64, 96}, K <= 16)", C, K);
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_ln_head_fwd: C=%d K=%d is not covered (C in {32, 64, 96, 128}, K <= 16)", C, K);
   HS_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(w), "hs_ln_head_fwd: x, gamma and w must be 16-byte aligned");
   const long long per_block = (kThreadsF / 32) * 4 * kRF;
   long long blocks = (rows + per_block - 1) / per_block;
@@ -401,7 +402,7 @@ int hs_ln_head_bwd(const float* dlogits, const float* x, const float* mean, cons
   HS_REQUIRE(rows_per_sample > 0 && rows % rows_per_sample == 0, "hs_ln_head_bwd: rows (%lld) is not a multiple of "
              "rows_per_sample (%lld)", (long long)rows, (long long)rows_per_sample);
   if (!hs_ln_head_supported(rows, C, K))
-    return hs::fail(HS_ERR_UNSUPPORTED, "hs_ln_head_bwd: C=%d K=%d is not covered (C in {32, 64, 96}, K <= 16)", C, K);
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_ln_head_bwd: C=%d K=%d is not covered (C in {32, 64, 96, 128}, K <= 16)", C, K);
   HS_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(w) && aligned16(dx),
              "hs_ln_head_bwd: x, gamma, w and dx must be 16-byte aligned");
   const long long per_block = (kThreadsB / 32) * 4 * kRB;

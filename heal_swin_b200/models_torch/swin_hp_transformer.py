@@ -438,8 +438,9 @@ class UnetDecoder(nn.Module):
     def forward(self, x, x_downsample):
         for inx, layer_up in enumerate(self.layers_up):
             if inx > 0:
-                x = torch.cat([x, x_downsample[self.num_layers - 1 - inx]], -1)
-                x = ops.linear(x, self.concat_back_dim[inx].weight, self.concat_back_dim[inx].bias)
+                # cat + Linear(2C -> C) (:772-775) as two accumulating GEMMs: the concatenated tensor is never written
+                x = ops.cat_linear(x, x_downsample[self.num_layers - 1 - inx], self.concat_back_dim[inx].weight,
+                                   self.concat_back_dim[inx].bias)
             x = layer_up(x)
         x = self.up.forward_pre_norm(ops.layer_norm(x, self.norm_up))
         # up.norm + Conv1d(kernel 1) over channels in one pass: the normalised (B, N_pix, C) activation is never written,

@@ -357,11 +357,45 @@ _FUSED_MLP = os.environ.get("HEALSWIN_FUSED_MLP", "1") == "1"
 _TF32_MLP_DGRAD = os.environ.get("HEALSWIN_TF32_MLP_DGRAD", "1") == "1"
 
 
+# Operand precision of the hand-written GEMMs.  "fp32" (default): bf16x3 for every forward product and for the HBM-bound
+# input gradients, one TF32 MMA for the tensor-bound input gradients (stages 2-3: gradients are compared at 5e-3, and the
+# weight gradients are TF32 already).  "bf16": one bf16 MMA on the hi terms everywhere -- "bf16 operands, fp32 accumulate",
+# the arithmetic BASELINE configs[3] names (activations stay fp32 in HBM; tolerance stated in tests/test_gpu_bf16.py).
+_GEMM_PRECISION = os.environ.get("HEALSWIN_GEMM_PRECISION", "fp32")
+_TF32_DGRAD = os.environ.get("HEALSWIN_TF32_DGRAD", "1") == "1"
+
+
 def set_gemm_mode(mode: str) -> None:
     """"bf16x3": the hand-written tensor-core GEMMs (default); "library": cuBLAS through torch."""
     global _GEMM_MODE
     assert mode in ("bf16x3", "library"), mode
     _GEMM_MODE = mode
+
+
+def set_gemm_precision(precision: str) -> None:
+    """"fp32": fp32-class products (bf16x3; TF32 for tensor-bound input gradients); "bf16": bf16 operands, fp32 accumulate."""
+    global _GEMM_PRECISION
+    assert precision in ("fp32", "bf16"), precision
+    _GEMM_PRECISION = precision
+
+
+def get_gemm_precision() -> str:
+    return _GEMM_PRECISION
+
+
+def _fwd_prec() -> int:
+    return _lib.PREC_BF16 if _GEMM_PRECISION == "bf16" else _lib.PREC_BF16X3
+
+
+def _dgrad_prec(T, n_out, k_contract) -> int:
+    """Input-gradient GEMM dx (T, n_out) = dy (T, k_contract) @ W: TF32 where three bf16 MMAs per product would make the
+    launch tensor-bound (per output element 6 * k flops at ~1.2 PFLOP/s against 4 * (n + k) / n bytes at ~6 TB/s, i.e.
+    n k / (n + k) > ~130: stages 2-3 of the N_side=256 network), bf16x3 where the launch is HBM-bound anyway."""
+    if _GEMM_PRECISION == "bf16":
+        return _lib.PREC_BF16
+    if _TF32_DGRAD and n_out * k_contract > 130 * (n_out + k_contract):
+        return _lib.PREC_TF32
+    return _lib.PREC_BF16X3
 
 
 def get_gemm_mode() -> str:
@@ -383,16 +417,20 @@ from torch.optim.optimizer import register_optimizer_step_post_hook as _register
 _register_post_step(_on_optimizer_step)
 
 
-def split_weight(weight, transposed=False):
+def split_weight(weight, transposed=False, cols=None, prec=0):
     """The bf16 [hi | lo] operand of ``weight`` (N, K) for hs_gemm3: (N, 2 * ceil32(K)) for the forward, or with
-    ``transposed`` (K, 2 * ceil32(N)) for the input gradient.  Cached per parameter; redone when the parameter's version
-    counter moves (load_state_dict, DDP broadcast, any in-place op), after every torch optimizer step (see above), and on
-    every use inside a CUDA-graph capture (a replay cannot consult the host).  The buffer is reused, so its address is
-    stable.  Call ``invalidate_weight_splits()`` after writing parameters in a way neither mechanism sees (``.data``
-    assignment from a custom optimizer that is not a torch.optim.Optimizer)."""
-    w = weight.detach()
-    N, K = w.shape
-    key = (id(weight), bool(transposed))
+    ``transposed`` (K, 2 * ceil32(N)) for the input gradient.  ``cols = (c0, n)`` takes the column block
+    ``weight[:, c0:c0 + n]`` instead of the whole matrix (the two halves of a skip-concat projection), read in place through
+    the row pitch.  Cached per parameter; redone when the parameter's version counter moves (load_state_dict, DDP
+    broadcast, any in-place op), after every torch optimizer step (see above), and on every use inside a CUDA-graph
+    capture (a replay cannot consult the host).  The buffer is reused, so its address is stable.  Call
+    ``invalidate_weight_splits()`` after writing parameters in a way neither mechanism sees (``.data`` assignment from a
+    custom optimizer that is not a torch.optim.Optimizer)."""
+    w = _f32c(weight.detach())
+    N, ld = w.shape
+    c0, K = (0, ld) if cols is None else cols
+    fmt = 1 if prec == _lib.PREC_TF32 else 0  # TF32 mode: fp32 rounded to the nearest TF32 (same bytes per row)
+    key = (id(weight), bool(transposed), c0, K, fmt)
     ent = _SPLITS.get(key)
     ver = weight._version
     if ent is not None and ent[0]() is weight and ent[2] == w.data_ptr():
@@ -401,10 +439,11 @@ def split_weight(weight, transposed=False):
             return ent[3]
         out = ent[3]
     else:
-        rows, cols = (K, N) if transposed else (N, K)
-        out = torch.empty((rows, 2 * ((cols + 31) // 32 * 32)), device=w.device, dtype=torch.bfloat16)
-    rows, cols = (K, N) if transposed else (N, K)
-    STATS.launch("weight_split", lib.hs_weight_split, ptr(_f32c(w)), rows, cols, K, 1 if transposed else 0, ptr(out),
+        rows, ncols = (K, N) if transposed else (N, K)
+        out = torch.empty((rows, 2 * ((ncols + 31) // 32 * 32)), device=w.device, dtype=torch.bfloat16)
+    rows, ncols = (K, N) if transposed else (N, K)
+    src = w if c0 == 0 else w.reshape(-1)[c0:]  # pointer to element (0, c0); the kernel walks rows with pitch ld
+    STATS.launch("weight_split", lib.hs_weight_split, ptr(src), rows, ncols, ld, 1 if transposed else 0, fmt, ptr(out),
                  current_stream())
     if weight.is_leaf:  # views of a parameter (patch embedding) are new objects every call: not worth caching
         if len(_SPLITS) > 1024:
@@ -434,14 +473,15 @@ def _dgrad_ok(dy2, weight) -> bool:
                 and lib.hs_gemm3_supported(dy2.shape[0], weight.shape[1], weight.shape[0]))
 
 
-def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, seed=0, colsum=None):
+def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, seed=0, colsum=None, prec=None):
     """hs_gemm3 on a (T, K) activation and a split weight; returns d, or (d, d2) for GEMM_GELU.  ``colsum`` (K floats,
     zero or a running sum) receives the column sums of ``a2`` in the same pass."""
     T, K = a2.shape
     d = torch.empty((T, N), device=a2.device, dtype=torch.float32)
     d2 = torch.empty_like(d) if mode == _lib.GEMM_GELU else None
+    prec = _fwd_prec() if prec is None else prec
     STATS.launch("gemm3", lib.hs_gemm3, ptr(a2), ptr(wsplit), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K,
-                 mode, C.c_float(drop), C.c_uint64(seed), current_stream(), tag=(T, N, K, mode))
+                 mode, prec, C.c_float(drop), C.c_uint64(seed), current_stream(), tag=(T, N, K, mode, prec))
     return (d, d2) if mode == _lib.GEMM_GELU else d
 
 
@@ -463,8 +503,9 @@ def _dgrad(dy2, weight, d_pass, xshape, want_bias_grad=False):
     if _dgrad_ok(dy2, weight):
         if want_bias_grad:
             db = torch.zeros((N,), device=dy2.device, dtype=torch.float32)
-        dx = _gemm3(dy2, split_weight(weight, transposed=True), K, None, c,
-                    _lib.GEMM_PLAIN if c is None else _lib.GEMM_ADD, colsum=db)
+        prec = _dgrad_prec(dy2.shape[0], K, N)
+        dx = _gemm3(dy2, split_weight(weight, transposed=True, prec=prec), K, None, c,
+                    _lib.GEMM_PLAIN if c is None else _lib.GEMM_ADD, colsum=db, prec=prec)
     else:
         dx = dy2 @ weight if c is None else torch.addmm(c, dy2, weight)
         if want_bias_grad:
@@ -571,7 +612,9 @@ class _MlpFn(torch.autograd.Function):
                          C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, 0, current_stream(),
                          tag=(T, Cout, J))
         else:
-            dz = _gemm3(dy2, split_weight(w2, transposed=True), J, _f32c(b1), z, _lib.GEMM_GELU_GRAD, *ctx.drop)
+            prec = _dgrad_prec(T, J, Cout)
+            dz = _gemm3(dy2, split_weight(w2, transposed=True, prec=prec), J, _f32c(b1), z, _lib.GEMM_GELU_GRAD, *ctx.drop,
+                        prec=prec)
         dx = db1 = None
         if ctx.needs_input_grad[0]:
             if _wgrad_fuses_bias(dz, x2):
@@ -601,6 +644,64 @@ def mlp_core(x, fc1, fc2, drop=0.0, seed=None, fork=False):
     if drop > 0.0 and seed is None:
         seed = _next_dropout_seed()
     return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0), bool(fork))
+
+
+class _CatLinearFn(torch.autograd.Function):
+    """``F.linear(torch.cat([x1, x2], -1), weight, bias)`` without the concatenation (UnetDecoder skip connections,
+    swin_hp_transformer.py:772-775): two accumulating GEMMs over the two column blocks of the weight -- the second adds the
+    first's result in its epilogue (GEMM_ADD) -- and in the backward two input-gradient GEMMs writing dx1 / dx2 directly
+    (no split copies of a (T, 2C) gradient) and two weight-gradient launches."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, weight, bias):
+        ctx.set_materialize_grads(False)
+        K1, K2 = x1.shape[-1], x2.shape[-1]
+        N = weight.shape[0]
+        a1, a2 = _f32c(x1).reshape(-1, K1), _f32c(x2).reshape(-1, K2)
+        part = _gemm3(a1, split_weight(weight, cols=(0, K1)), N, _f32c(bias))
+        y = _gemm3(a2, split_weight(weight, cols=(K1, K2)), N, None, part, _lib.GEMM_ADD)
+        ctx.save_for_backward(a1, a2, weight)
+        ctx.meta = (x1.shape, x2.shape, bias is not None)
+        return y.view(*x1.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        a1, a2, weight = ctx.saved_tensors
+        s1, s2, has_bias = ctx.meta
+        if dy is None:
+            return None, None, None, None
+        N = weight.shape[0]
+        K1, K2 = a1.shape[1], a2.shape[1]
+        dy2 = _f32c(dy).reshape(-1, N)
+        need_b = has_bias and ctx.needs_input_grad[3]
+        db = torch.zeros((N,), device=dy2.device, dtype=torch.float32) if need_b else None
+        dx1 = dx2 = dw = None
+        if ctx.needs_input_grad[0]:
+            p1 = _dgrad_prec(dy2.shape[0], K1, N)
+            dx1 = _gemm3(dy2, split_weight(weight, transposed=True, cols=(0, K1), prec=p1), K1, colsum=db, prec=p1).view(s1)
+        if ctx.needs_input_grad[1]:
+            p2 = _dgrad_prec(dy2.shape[0], K2, N)
+            dx2 = _gemm3(dy2, split_weight(weight, transposed=True, cols=(K1, K2), prec=p2), K2,
+                         colsum=None if ctx.needs_input_grad[0] else db, prec=p2).view(s2)
+        if need_b and not (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            db = dy2.sum(0)
+        if ctx.needs_input_grad[2]:
+            dw = torch.cat([_wgrad(dy2, a1, False)[0], _wgrad(dy2, a2, False)[0]], dim=1)
+        return dx1, dx2, dw, db
+
+
+def cat_linear(x1, x2, weight, bias=None):
+    """``F.linear(torch.cat([x1, x2], -1), weight, bias)``; the concatenated tensor is never built where the hand-written
+    GEMM covers the shapes."""
+    K1, K2 = x1.shape[-1], x2.shape[-1]
+    T = x1.numel() // K1
+    if (_GEMM_MODE == "bf16x3" and _on_device(x1) and x1.dtype == torch.float32 and x2.dtype == torch.float32
+            and weight.dim() == 2 and weight.is_contiguous() and weight.shape[1] == K1 + K2 and K1 % 4 == 0
+            and x1.shape[:-1] == x2.shape[:-1]
+            and lib.hs_gemm3_supported(T, weight.shape[0], K1) and lib.hs_gemm3_supported(T, weight.shape[0], K2)
+            and lib.hs_gemm3_supported(T, K1, weight.shape[0]) and lib.hs_gemm3_supported(T, K2, weight.shape[0])):
+        return _CatLinearFn.apply(x1, x2, weight, bias)
+    return linear(torch.cat([x1, x2], -1), weight, bias)
 
 
 def linear(x, weight, bias=None, fork=False):

@@ -39,6 +39,11 @@ extern "C" {
 #define HS_SHIFT_NEST_GRID 2  /* hp_shifting.NestGridShift     hp_shifting.py:76-306  */
 #define HS_SHIFT_RING 3       /* hp_shifting.RingShift         hp_shifting.py:309-404 */
 
+/* operand precision of hs_gemm3 */
+#define HS_GEMM_BF16X3 0
+#define HS_GEMM_TF32 1
+#define HS_GEMM_BF16 2
+
 /* flags of the attention kernels */
 #define HS_ATTN_COS 1u /* cosine attention, swin_hp_transformer.py:142-147 */
 #define HS_ATTN_NO_TC 2u /* force the exact-fp32 CUDA-core kernels (cross-check of the tcgen05 TF32 path) */
@@ -217,16 +222,22 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
  *   mode 1 (add)        d = acc + bias + aux                  aux: (T, N) fp32, e.g. the residual-shortcut gradient
  *   mode 2 (gelu)       d = acc,  d2 = dropout(GELU(acc + bias))      Mlp fc1 + act + drop (:39-41); exact erf GELU
  *   mode 3 (gelu grad)  d = acc * GELU'(aux + bias) * dropmask        aux = the bias-free fc1 output z
+ * precision: HS_GEMM_BF16X3 (default: three bf16 MMAs per product, fp32-class) | HS_GEMM_TF32 (one TF32 MMA, A read as fp32
+ * without conversion; wsplit must be hs_weight_split format 1 = fp32 rounded to the nearest TF32, same bytes per row: used
+ * for the input gradients of the tensor-bound stages, where 5e-3 suffices) | HS_GEMM_BF16 (one bf16 MMA on the hi terms:
+ * "bf16 operands, fp32 accumulate", BASELINE configs[3]; wsplit format 0).
  * colsum: (K) or NULL: colsum[k] += sum_t a[t][k] in the same pass -- when a is the output gradient of a linear (input-
  * gradient form) this is that linear's bias gradient, so no separate reduction over the activation is needed.
  * bias: (N) or NULL.  drop / seed: the element dropout of modes 2 / 3 (mask = pure function of (seed, row, col), as
  * hs_bias_gelu_fwd).  All of d, d2, aux are (T, N) fp32 row-major.  hs_gemm3_supported: N, K multiples of 4 (TMA row pitch);
  * ragged 32-wide chunks are zero-filled on load and clipped on store by the TMA unit.
  */
-int hs_weight_split(const float* w_dev, int rows, int cols, int ld, int transposed, uint16_t* out_dev, void* stream);
+int hs_weight_split(const float* w_dev, int rows, int cols, int ld, int transposed, int format, uint16_t* out_dev,
+                    void* stream);
 int hs_gemm3_supported(int64_t T, int N, int K);
 int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
-             float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, float drop, uint64_t seed, void* stream);
+             float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, int precision, float drop, uint64_t seed,
+             void* stream);
 
 /*
  * Decoder tail, fused: logits = Conv1d_1x1(LayerNorm(x)) (FinalPatchExpand_X4.norm + SwinHPTransformerSys.output,
@@ -237,7 +248,7 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
  * Backward writes dx (rows, C) and ACCUMULATES  s_acc[k][c] += sum_rows dlogits[row][k] * xhat[row][c]  (K, C) and
  * g_acc[k] += sum_rows dlogits[row][k]  (K) (zero them first), from which
  *   d(w) = gamma * s_acc + beta * g_acc,  d(gamma) = sum_k w * s_acc,  d(beta) = sum_k w * g_acc,  d(head_bias) = g_acc.
- * hs_ln_head_supported: 1 for C in {32, 64, 96} and 1 <= K <= 16.
+ * hs_ln_head_supported: 1 for C in {32, 64, 96, 128} and 1 <= K <= 16.
  */
 int hs_ln_head_supported(int64_t rows, int C, int K);
 int hs_ln_head_fwd(const float* x_dev, const float* gamma_dev, const float* beta_dev, const float* w_dev,

@@ -27,23 +27,23 @@ def timeit(fn, n=10):
     return a.elapsed_time(b) / n
 
 
-def split(w, transposed=False):
+def split(w, transposed=False, prec=0):
     w = w.contiguous()
     n, k = w.shape
     rows, cols = (k, n) if transposed else (n, k)
     out = torch.empty((rows, 2 * ((cols + 31) // 32 * 32)), device=w.device, dtype=torch.bfloat16)
-    check(lib.hs_weight_split(ptr(w), rows, cols, k, 1 if transposed else 0, ptr(out), current_stream()))
+    check(lib.hs_weight_split(ptr(w), rows, cols, k, 1 if transposed else 0, 1 if prec == 1 else 0, ptr(out), current_stream()))
     return out
 
 
-def gemm3(a, ws, bias=None, aux=None, mode=0, drop=0.0, seed=0, d=None, d2=None, colsum=None):
+def gemm3(a, ws, bias=None, aux=None, mode=0, drop=0.0, seed=0, d=None, d2=None, colsum=None, prec=0):
     T, K = a.shape
     N = ws.shape[0]
     if d is None:
         d = torch.empty((T, N), device=a.device, dtype=torch.float32)
     if mode == 2 and d2 is None:
         d2 = torch.empty_like(d)
-    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K, mode, C.c_float(drop),
+    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K, mode, prec, C.c_float(drop),
                        C.c_uint64(seed), current_stream()))
     return (d, d2) if mode == 2 else d
 

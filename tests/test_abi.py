@@ -56,9 +56,10 @@ def test_shape_predicates_are_host_only():
     assert lib.hs_gemm3_supported(T0, 10, 96) == 0 and lib.hs_gemm3_supported(T0, 96, 50) == 0
     assert lib.hs_bias_gelu_supported(T0, 384) == 1 and lib.hs_bias_gelu_supported(T0, 6144) == 0
     assert lib.hs_bias_gelu_supported(T0, 50) == 0
-    # fused decoder tail: C in {32, 64, 96}, up to 16 output channels
+    # fused decoder tail: C in {32, 64, 96, 128}, up to 16 output channels
     assert lib.hs_ln_head_supported(4 * T0, 96, 10) == 1 and lib.hs_ln_head_supported(4 * T0, 96, 1) == 1
-    assert lib.hs_ln_head_supported(4 * T0, 128, 1) == 0 and lib.hs_ln_head_supported(4 * T0, 96, 17) == 0
+    assert lib.hs_ln_head_supported(4 * T0, 128, 1) == 1 and lib.hs_ln_head_supported(4 * T0, 96, 17) == 0
+    assert lib.hs_ln_head_supported(4 * T0, 160, 1) == 0
 
 
 def test_argument_validation_happens_before_any_device_work():
@@ -78,15 +79,15 @@ def test_argument_validation_happens_before_any_device_work():
     assert rc == 1 and "drop" in _lib.last_error()
     rc = lib.hs_mlp_dgrad_gelu(one, one, one, null, C.c_float(0.0), 0, one, 8192, 384, 1536, 0, null)
     assert rc == 3 and "not covered" in _lib.last_error()
-    rc = lib.hs_gemm3(null, one, null, null, one, null, null, 8, 32, 32, 0, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(null, one, null, null, one, null, null, 8, 32, 32, 0, 0, C.c_float(0.0), 0, null)
     assert rc == 1 and "bad arguments" in _lib.last_error()
-    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 32, 32, 1, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 32, 32, 1, 0, C.c_float(0.0), 0, null)
     assert rc == 1 and "aux" in _lib.last_error()
-    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 32, 32, 2, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 32, 32, 2, 0, C.c_float(0.0), 0, null)
     assert rc == 1 and "second output" in _lib.last_error()
-    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 30, 32, 0, C.c_float(0.0), 0, null)
+    rc = lib.hs_gemm3(one, one, null, null, one, null, null, 8, 30, 32, 0, 0, C.c_float(0.0), 0, null)
     assert rc == 3 and "not covered" in _lib.last_error()
-    rc = lib.hs_weight_split(null, 4, 4, 4, 0, one, null)
+    rc = lib.hs_weight_split(null, 4, 4, 4, 0, 0, one, null)
     assert rc == 1
 
 

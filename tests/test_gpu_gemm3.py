@@ -15,24 +15,24 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-5
 
 
-def _split(w, transposed=False):
+def _split(w, transposed=False, prec=0):
     from heal_swin_b200._lib import check, current_stream, lib, ptr
 
     w = w.contiguous()
     n, k = w.shape
     rows, cols = (k, n) if transposed else (n, k)
     out = torch.empty((rows, 2 * ((cols + 31) // 32 * 32)), device=w.device, dtype=torch.bfloat16)
-    check(lib.hs_weight_split(ptr(w), rows, cols, k, 1 if transposed else 0, ptr(out), current_stream()))
+    check(lib.hs_weight_split(ptr(w), rows, cols, k, 1 if transposed else 0, 1 if prec == 1 else 0, ptr(out), current_stream()))
     return out
 
 
-def _gemm3(a, ws, N, bias=None, aux=None, mode=0, drop=0.0, seed=0, colsum=None):
+def _gemm3(a, ws, N, bias=None, aux=None, mode=0, drop=0.0, seed=0, colsum=None, prec=0):
     from heal_swin_b200._lib import check, current_stream, lib, ptr
 
     T, K = a.shape
     d = torch.full((T, N), float("nan"), device=a.device)
     d2 = torch.full((T, N), float("nan"), device=a.device) if mode == 2 else None
-    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K, mode, C.c_float(drop),
+    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K, mode, prec, C.c_float(drop),
                        C.c_uint64(seed), current_stream()))
     return (d, d2) if mode == 2 else d
 
@@ -144,3 +144,54 @@ def test_linearity_and_exactness_on_bf16_data_at_full_size():
     torch.backends.cuda.matmul.allow_tf32 = False
     want = a @ w.t()  # exact: |sum| <= 96 * 64 < 2^24
     assert torch.equal(got, want)
+
+
+def test_cat_linear_matches_the_concatenated_linear():
+    """ops.cat_linear (skip connections of the decoder, swin_hp_transformer.py:772-775): two accumulating GEMMs over the
+    column blocks of the weight == F.linear(cat(x1, x2)), forward and all gradients."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(11)
+    for T, C in ((4096, 96), (1000, 384)):
+        x1 = torch.randn(2, T // 2, C, generator=g).to(dev).requires_grad_(True)
+        x2 = torch.randn(2, T // 2, C, generator=g).to(dev).requires_grad_(True)
+        lin = torch.nn.Linear(2 * C, C).to(dev)
+        gy = torch.randn(2, T // 2, C, generator=g).to(dev)
+        ops.STATS.reset()
+        y = ops.cat_linear(x1, x2, lin.weight, lin.bias)
+        y.backward(gy)
+        assert ops.STATS.by_name.get("gemm3") == 4  # two forward, two input-gradient GEMMs; no concatenation
+        got = [y.detach().clone()] + [t.grad.clone() for t in (x1, x2, lin.weight, lin.bias)]
+        for t in (x1, x2, lin.weight, lin.bias):
+            t.grad = None
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = torch.nn.functional.linear(torch.cat([x1, x2], -1), lin.weight, lin.bias)
+        ref.backward(gy)
+        want = [ref.detach()] + [t.grad for t in (x1, x2, lin.weight, lin.bias)]
+        # the weight gradient is the TF32 kernel where T >= 4096; the input gradients are TF32 where bf16x3 would make them
+        # tensor-bound (C = 384: ops._dgrad_prec)
+        tols = [2e-5, 1e-3, 1e-3, 2e-3, 2e-5]
+        for a, b, tol in zip(got, want, tols):
+            assert rel_err(a.cpu(), b.cpu()) < tol
+
+
+@pytest.mark.parametrize("T,N,K", [(1000, 384, 1152), (4096, 1536, 384), (512, 96, 100), (2048, 768, 3072)])
+def test_single_mma_precisions(T, N, K):
+    """HS_GEMM_TF32 (one TF32 MMA, A read as fp32 without conversion, weight operand = fp32 rounded to TF32) and
+    HS_GEMM_BF16 (one bf16 MMA on the hi terms).  Tolerances: TF32 truncates A to 10 mantissa bits (relative 2^-11 on
+    average, biased low) -> 1e-3; bf16 operands (2^-9 each) -> 6e-3.  Column sums and the add epilogue ride along."""
+    a, w, b = _data(T, N, K, seed=4)
+    want = a.double() @ w.double().t() + b.double()
+    aux = torch.randn(T, N, device=a.device)
+    cs = torch.zeros(K, device=a.device)
+    got = _gemm3(a, _split(w, prec=1), N, b, aux, mode=1, colsum=cs, prec=1)
+    assert rel_err(got.cpu(), (want + aux.double()).cpu()) < 1e-3
+    assert rel_err(cs.cpu(), a.double().sum(0).cpu()) < 1e-5
+    got = _gemm3(a, _split(w, prec=1), N, b, prec=1)
+    e_tf32 = rel_err(got.cpu(), want.cpu())
+    got = _gemm3(a, _split(w), N, b, prec=2)
+    e_bf16 = rel_err(got.cpu(), want.cpu())
+    got = _gemm3(a, _split(w), N, b)
+    e_x3 = rel_err(got.cpu(), want.cpu())
+    assert e_x3 < TOL < e_tf32 < 1e-3 < e_bf16 < 6e-3, (e_x3, e_tf32, e_bf16)

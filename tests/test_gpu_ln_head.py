@@ -24,7 +24,8 @@ def _reference(x, norm, w, b):
 
 
 @pytest.mark.parametrize("B,P,Cc,K,bias", [(2, 1000, 96, 10, False), (3, 77, 64, 1, True), (1, 5003, 32, 16, True),
-                                           (2, 4096, 96, 3, False), (1, 9, 96, 13, True), (4, 20000, 96, 10, False)])
+                                           (2, 4096, 96, 3, False), (1, 9, 96, 13, True), (4, 20000, 96, 10, False),
+                                           (2, 3000, 128, 1, False), (1, 777, 128, 10, True)])  # C = 128: BASELINE configs[3]
 def test_ln_head_forward_and_gradients_match_torch(B, P, Cc, K, bias):
     from heal_swin_b200 import ops
 

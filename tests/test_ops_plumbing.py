@@ -25,6 +25,7 @@ class FakeLib:
     def __init__(self):
         self.calls = []
         self.splits = 0
+        self.formats = {}
 
     wgrad_cover = 2
 
@@ -50,7 +51,7 @@ class FakeLib:
     def hs_bias_gelu_supported(self, rows, Cc):
         return 1
 
-    def hs_weight_split(self, w, rows, cols, ld, transposed, out, stream):
+    def hs_weight_split(self, w, rows, cols, ld, transposed, fmt, out, stream):
         """[hi(32) | lo(32)] bf16 per 32-wide chunk of the contraction axis, zero padded (include/healswin_b200.h)."""
         self.splits += 1
         m = (w.t() if transposed else w).float()
@@ -58,6 +59,11 @@ class FakeLib:
         nk = (cols + 31) // 32
         pad = torch.zeros(rows, nk * 32)
         pad[:, :cols] = m
+        if fmt == 1:  # fp32 (rounded to TF32 on the device) viewed through the bf16 buffer
+            out.view(torch.float32).copy_(pad)
+            self.formats[id(out)] = 1
+            return 0
+        self.formats[id(out)] = 0
         hi = pad.bfloat16()
         lo = (pad - hi.float()).bfloat16()
         assert out.shape == (rows, 2 * nk * 32) and out.dtype == torch.bfloat16
@@ -66,13 +72,17 @@ class FakeLib:
         o[:, :, 32:] = lo.view(rows, nk, 32)
         return 0
 
-    def hs_gemm3(self, a, ws, bias, aux, d, d2, colsum, T, N, K, mode, drop, seed, stream):
-        self.calls.append(f"gemm3:{mode}" + ("+colsum" if colsum is not None else ""))
+    def hs_gemm3(self, a, ws, bias, aux, d, d2, colsum, T, N, K, mode, prec, drop, seed, stream):
+        self.calls.append(f"gemm3:{mode}" + ("+colsum" if colsum is not None else "") + ("/tf32" if prec == 1 else ""))
+        assert self.formats[id(ws)] == (1 if prec == 1 else 0), "weight operand format does not match the precision"
         if colsum is not None:
             colsum += a.sum(0)
         assert _val(drop) == 0.0 and a.shape == (T, K) and ws.shape[0] == N
-        o = ws.view(N, -1, 64).float()
-        w = (o[:, :, :32] + o[:, :, 32:]).reshape(N, -1)[:, :K]   # hi + lo: the weight to ~2^-17
+        if prec == 1:
+            w = ws.view(torch.float32)[:, :K]
+        else:
+            o = ws.view(N, -1, 64).float()
+            w = (o[:, :, :32] + o[:, :, 32:]).reshape(N, -1)[:, :K]   # hi + lo: the weight to ~2^-17
         acc = a @ w.t()
         b = bias if bias is not None else 0
         if mode == 0:
