@@ -50,9 +50,8 @@ constexpr int kMaxWRing = 4;            // streamed W slices (L2 hits: a short r
 constexpr int kMaxRw = 3;              // staging regions per epilogue warp
 constexpr int kRegion = 32 * 128;      // 4 KB: 32 rows x 32 columns, one warp's part of a slab
 constexpr int kCvtWarps = 8;
-constexpr int kStageCols = 192;        // TMEM columns per accumulator stage (2 stages) ...
-constexpr int kASlots = 4;             // ... + 4 A-operand slots of 32 columns = 512
-constexpr int kACol0 = 2 * kStageCols;
+constexpr int kASlots = 4;             // A-operand slots of 32 TMEM columns behind two 192-column accumulator stages
+constexpr int kACol0 = 2 * 192;
 
 enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3 };
 // operand precision: three bf16 MMAs per product (fp32-class), one TF32 MMA (A straight from the fp32 tile, no conversion;
@@ -67,6 +66,8 @@ struct G3Args {
   int n_stride, n_box, n_chunks;  // column chunks start every n_stride columns and compute n_box (multiple of 32)
   long long tiles;
   int prec;     // PREC_*
+  int ss;       // 1: the A operand stays in shared memory (TF32: as delivered; bf16: split in place), 256-column stages
+  int stage_cols;  // TMEM columns per accumulator stage: 192 (+ 4 A slots of 32 columns) or 256 (ss)
   int cluster;  // CTAs per cluster (1, 2 or 4): streamed W slices are loaded once per cluster and multicast
   int ring, rw, resident, wring;  // A ring depth, staging regions per epilogue warp, W resident?, W ring depth
   uint32_t drop_thresh;
@@ -84,6 +85,15 @@ __device__ __forceinline__ void umma_tf32_ss_(uint32_t d_tmem, uint64_t a_desc, 
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 operands
+__device__ __forceinline__ void umma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -125,7 +135,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   uint8_t* s_ring = s_w + (a.resident ? nk : a.wring) * w_slice;
   uint8_t* s_buf = s_ring + a.ring * kChunk;   // E warps x rw regions of 4 KB
   float* s_colsum = reinterpret_cast<float*>(s_buf + E * a.rw * kRegion);  // nk * 32 floats (chunk-0 CTAs with a.colsum)
-  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], slot_empty[kMaxRing],
+  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], slot_empty[kMaxRing], cvt_full[kMaxRing],
       a_full[kASlots], a_empty[kASlots], acc_full[2], acc_empty[2], aux_full[E * kMaxRw];
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,11 +163,15 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_init(&raw_full[i], 1);
       // released by the converters once the chunk is in their registers; in TF32 mode by the MMAs that read it (and by the
       // converters as well when they take the column sums)
-      mbar_init(&slot_empty[i], a.prec == PREC_TF32 ? 1 + ((a.colsum && chunk == 0) ? kCvtWarps : 0) : kCvtWarps);
+      mbar_init(&slot_empty[i], a.prec == PREC_TF32 ? 1 + ((a.colsum && chunk == 0) ? kCvtWarps : 0)
+                                : (a.ss ? 1 : kCvtWarps));
     }
     for (int i = 0; i < kASlots; ++i) {
       mbar_init(&a_full[i], kCvtWarps);
       mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < kMaxRing; ++i) mbar_init(&cvt_full[i], kCvtWarps);  // ss bf16: the chunk is split in place
+    {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -234,7 +248,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         const int st = (int)(it & 1);
         mbar_wait(&acc_empty[st], (((uint32_t)(it >> 1)) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem + (uint32_t)st * kStageCols;
+        const uint32_t d = tmem + (uint32_t)st * a.stage_cols;
         for (int kc = 0; kc < nk; ++kc) {
           if (!a.resident) mbar_wait(&wr_full[ws], wph);
           const uint32_t wk = wb + (a.resident ? kc : ws) * w_slice;
@@ -247,6 +261,21 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             for (int ks = 0; ks < 4; ++ks)
               umma_tf32_ss_(d, umma_desc_at(kDesc, ab + 32 * ks), umma_desc_at(kDesc, wk + 32 * ks), idesc32,
                             (kc > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&slot_empty[slot]);
+            if (++slot == ring) { slot = 0; ph ^= 1; }
+          } else if (a.ss) {
+            // bf16x3 with the chunk split IN PLACE in shared memory: [hi(32) | lo(32)] bf16 per 128-byte row
+            mbar_wait(&cvt_full[slot], ph);
+            tc_fence_after();
+            const uint32_t ab = rb + slot * kChunk;
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t a_hi = umma_desc_at(kDesc, ab + 32 * ks), a_lo = umma_desc_at(kDesc, ab + 64 + 32 * ks);
+              const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
+              umma_bf16_ss(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+              umma_bf16_ss(d, a_hi, w_lo, idesc, 1u);
+              umma_bf16_ss(d, a_hi, w_hi, idesc, 1u);
+            }
             umma_commit(&slot_empty[slot]);
             if (++slot == ring) { slot = 0; ph ^= 1; }
           } else {
@@ -333,6 +362,21 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
         split2(v[2].z, v[2].w, hi[5], lo[5]);
         split2(v[3].x, v[3].y, hi[6], lo[6]);
         split2(v[3].z, v[3].w, hi[7], lo[7]);
+        if (convert && a.ss) {
+          // in place: this thread's half row (64 B) becomes hi (32 B at chunk 2 half) + lo (32 B at chunk 4 + 2 half); the
+          // two warps of a row half pair exchange nothing, but hi / lo of the OTHER half live in chunks this thread reads
+          // from -- all four warps of the chunk's row quadrant pair must have read before anyone writes
+          named_bar_sync(2 + q, 64);
+          sts_u4(base + (((2 * half + 0) ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+          sts_u4(base + (((2 * half + 1) ^ sw) << 4), make_uint4(hi[4], hi[5], hi[6], hi[7]));
+          sts_u4(base + (((4 + 2 * half + 0) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+          sts_u4(base + (((4 + 2 * half + 1) ^ sw) << 4), make_uint4(lo[4], lo[5], lo[6], lo[7]));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&cvt_full[slot]);
+          if (++slot == ring) { slot = 0; ph ^= 1; }
+          continue;
+        }
         __syncwarp();  // every lane holds its part of the chunk in registers: the shared-memory slot can be refilled
         if (lane == 0) mbar_arrive(&slot_empty[slot]);
         if (++slot == ring) { slot = 0; ph ^= 1; }
@@ -390,7 +434,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
       for (int s = g; s < S; s += NG) {
         uint32_t acc[32];
-        tmem_ld32(tmem + lane_addr + (uint32_t)as * kStageCols + 32 * s, acc);
+        tmem_ld32(tmem + lane_addr + (uint32_t)as * a.stage_cols + 32 * s, acc);
         tmem_wait_ld();
         if (s + NG >= S) {  // this thread's last slab of the tile is in registers
           tc_fence_before();
@@ -531,15 +575,20 @@ int plan(G3Args& a, int mode, int E) {
   const int nk = (a.K + 31) / 32;
   const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
   const int rw_min = aux ? 2 : 1, rw_max = aux ? 3 : 2;
-  int first = (a.N + kStageCols - 1) / kStageCols;     // number of chunks (an accumulator stage has 192 columns)
+  // tensor-bound launches (streamed W, long contraction) keep A in shared memory and use 256-column stages: fewer, wider
+  // MMAs (ncu: 69 % tensor-pipe active against 59 % with 192-column chunks); HBM-bound launches take A through TMEM
+  a.ss = (a.prec == PREC_TF32 || (a.prec == PREC_BF16X3 && (long long)a.N * a.K > 130ll * (a.N + a.K) && a.K >= 256)) ? 1 : 0;
+  if (const char* e = getenv("HEALSWIN_GEMM3_SS")) a.ss = (a.prec == PREC_TF32) ? 1 : (atoi(e) != 0 && a.prec == PREC_BF16X3);
+  a.stage_cols = a.ss ? 256 : 192;
+  int first = (a.N + a.stage_cols - 1) / a.stage_cols;  // number of chunks
   first = (((a.N + first - 1) / first) + 15) / 16 * 16;  // equal chunks, 16-column granularity
   if (const char* e = getenv("HEALSWIN_GEMM3_NTILE")) {  // experiments only
     const int v = atoi(e);
-    if (v >= 32 && v <= kStageCols && v % 16 == 0 && v < first) first = v;
+    if (v >= 32 && v <= a.stage_cols && v % 16 == 0 && v < first) first = v;
   }
-  const int cand[6] = {first, 160, 128, 96, 64, 32};
+  const int cand[7] = {first, 192, 160, 128, 96, 64, 32};
   int best_ring = 0;
-  for (int ci = 0; ci < 6; ++ci) {
+  for (int ci = 0; ci < 7; ++ci) {
     const int stride = cand[ci];
     if (stride > first || (ci > 0 && stride == first)) continue;
     const int box = (stride + 31) / 32 * 32;

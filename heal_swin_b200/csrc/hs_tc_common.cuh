@@ -48,12 +48,13 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // 2-D fp32 tensor (rows x cols, dense) with a (box_cols x box_rows) box
+// (pitch_cols: row pitch in elements when the tensor is a column block of a wider one; 0 = dense)
 inline int make_map(CUtensorMap* m, const float* base, long long rows, int cols, CUtensorMapSwizzle sw,
-                    int box_cols = kD, int box_rows = kWS) {
+                    int box_cols = kD, int box_rows = kWS, long long pitch_cols = 0) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+  cuuint64_t gstr[1] = {(cuuint64_t)(pitch_cols ? pitch_cols : cols) * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,

@@ -170,7 +170,8 @@ extern "C" {
 int hs_linear_wgrad_supported(int64_t T, int N, int K) {
   if (T < 4096 || N < 32 || K < 32 || (N % 4) || (K % 4)) return 0;
   const int q = N < K ? N : K;
-  if (!(q % 32 == 0 && q <= 512)) return 0;
+  if (q > 512) return (q <= 1024 && q % 64 == 0) ? 1 : 0;  // two launches over the column halves of the smaller operand
+  if (q % 32 != 0) return 0;
   return (N >= K && K + 32 <= 256) ? 2 : 1;
 }
 
@@ -179,44 +180,52 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, in
   HS_REQUIRE(dy && x && dw && T > 0 && N > 0 && K > 0, "hs_linear_wgrad: bad arguments");
   if (!hs_linear_wgrad_supported(T, N, K))
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: shape T=%lld N=%d K=%d is not covered (min(N, K) must be a "
-                    "multiple of 32 and <= 512)", (long long)T, N, K);
+                    "multiple of 32 and <= 512, or a multiple of 64 and <= 1024)", (long long)T, N, K);
   HS_REQUIRE(!((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15), "hs_linear_wgrad: unaligned input");
-  // P = operand with more features (rows of D), Q = the other (<= 256 columns)
+  // P = operand with more features (rows of D), Q = the other (<= 512 columns per launch)
   const bool p_is_dy = N >= K;
   const float* P = p_is_dy ? dy : x;
   const float* Q = p_is_dy ? x : dy;
-  WgArgs a{};
-  a.out = dw; a.T = T;
-  a.NP = p_is_dy ? N : K; a.NQ = p_is_dy ? K : N;
-  if (dbias) {
-    if (!(p_is_dy && a.NQ + 32 <= 256))
-      return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: the fused bias gradient needs N >= K and K <= 224 (N=%d K=%d)", N, K);
+  const int NP = p_is_dy ? N : K, NQ_all = p_is_dy ? K : N;
+  // a smaller operand wider than 512 columns (stage 3: 768) does not fit the accumulator: one launch per column half,
+  // each reading its half of Q through the row pitch and writing its column block of dW
+  const int parts = NQ_all > 512 ? 2 : 1;
+  const int NQ = NQ_all / parts;
+  if (dbias && !(p_is_dy && parts == 1 && NQ + 32 <= 256))
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: the fused bias gradient needs N >= K and K <= 224 (N=%d K=%d)", N, K);
+  for (int part = 0; part < parts; ++part) {
+    WgArgs a{};
+    a.T = T;
+    a.NP = NP; a.NQ = NQ;
     a.colsum = dbias;
+    a.ldo_p = p_is_dy ? K : 1; a.ldo_q = p_is_dy ? 1 : K;
+    a.out = dw + (long long)part * NQ * a.ldo_q;
+    a.p_blocks = (a.NP + 127) / 128;
+    a.tt = a.NQ <= 256 ? 64 : 32;
+    const int kTT = a.tt, kSlab = a.tt * 128;
+    const long long tiles = (T + kTT - 1) / kTT;
+    int splits = hs::tc::sm_count() / a.p_blocks;
+    if (splits < 1) splits = 1;
+    if (splits > tiles) splits = (int)tiles;
+    a.splits = splits;
+    const int stage_bytes = (4 + a.NQ / 32 + (dbias ? 1 : 0)) * kSlab;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: stage does not fit");
+    a.stages = stages;
+    a.fix = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix2;
+    a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix1;
+    CUtensorMap map_p, map_q;
+    int rc;
+    if ((rc = hs::tc::make_map(&map_p, P, T, a.NP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT))) return rc;
+    if ((rc = hs::tc::make_map(&map_q, Q + (long long)part * NQ, T, a.NQ, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT,
+                               NQ_all)))
+      return rc;
+    const size_t smem = (size_t)stages * stage_bytes + 1024;
+    HS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    wgrad_tc_kernel<<<a.p_blocks * a.splits, kThreads, smem, (cudaStream_t)stream>>>(map_p, map_q, a);
+    HS_LAUNCH_CHECK();
   }
-  a.ldo_p = p_is_dy ? K : 1; a.ldo_q = p_is_dy ? 1 : K;
-  a.p_blocks = (a.NP + 127) / 128;
-  a.tt = a.NQ <= 256 ? 64 : 32;
-  const int kTT = a.tt, kSlab = a.tt * 128;
-  const long long tiles = (T + kTT - 1) / kTT;
-  int splits = hs::tc::sm_count() / a.p_blocks;
-  if (splits < 1) splits = 1;
-  if (splits > tiles) splits = (int)tiles;
-  a.splits = splits;
-  const int stage_bytes = (4 + a.NQ / 32 + (dbias ? 1 : 0)) * kSlab;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: stage does not fit");
-  a.stages = stages;
-  a.fix = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix2;
-  a.fix1 = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix1;
-  CUtensorMap map_p, map_q;
-  int rc;
-  if ((rc = hs::tc::make_map(&map_p, P, T, a.NP, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT))) return rc;
-  if ((rc = hs::tc::make_map(&map_q, Q, T, a.NQ, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, kTT))) return rc;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
-  HS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  wgrad_tc_kernel<<<a.p_blocks * a.splits, kThreads, smem, (cudaStream_t)stream>>>(map_p, map_q, a);
-  HS_LAUNCH_CHECK();
   return HS_OK;
 }
 

@@ -531,7 +531,16 @@ def _wgrad(dy2, x2, need_bias):
         STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, 0,
                      current_stream(), tag=(T, N, K))
     else:
-        dw = dy2.t() @ x2
+        # shapes outside the kernel (min(N, K) > 512: stage 3; K < 32: patch embedding): the library GEMM, in the same
+        # arithmetic as the kernel (TF32 operands, fp32 accumulation) whatever torch's global switch says -- as fp32
+        # these run as SIMT sgemm kernels, 11 ms per step of the N_side=256 network
+        # (with the kernel switched off -- HEALSWIN_CUSTOM_WGRAD=0, the exact-fp32 tests -- torch's switch decides)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = prev or _CUSTOM_WGRAD
+        try:
+            dw = dy2.t() @ x2
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
     if need_bias and db is None:
         db = dy2.sum(0)
     return dw, db

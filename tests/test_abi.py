@@ -42,10 +42,11 @@ def test_shape_predicates_are_host_only():
     covered, shapes outside the kernels' tiling are not."""
     lib = _lib.lib
     T0 = 8 * 196608
-    # weight gradient: qkv / fc1 (bias fused), fc2 (N < K: no fused bias), stage 3 (min(N, K) = 768: library)
+    # weight gradient: qkv / fc1 (bias fused), fc2 (N < K: no fused bias), stage 3 (min(N, K) = 768: two column halves)
     assert lib.hs_linear_wgrad_supported(T0, 288, 96) == 2 and lib.hs_linear_wgrad_supported(T0, 384, 96) == 2
     assert lib.hs_linear_wgrad_supported(T0, 96, 384) == 1
-    assert lib.hs_linear_wgrad_supported(T0 // 64, 2304, 768) == 0 and lib.hs_linear_wgrad_supported(T0, 10, 96) == 0
+    assert lib.hs_linear_wgrad_supported(T0 // 64, 2304, 768) == 1 and lib.hs_linear_wgrad_supported(T0, 10, 96) == 0
+    assert lib.hs_linear_wgrad_supported(T0 // 64, 3072, 1536) == 0  # min(N, K) > 1024
     assert lib.hs_linear_wgrad_supported(100, 288, 96) == 0
     # fused MLP backward: stages 0-1
     assert lib.hs_mlp_dgrad_gelu_supported(T0, 96, 384) == 1 and lib.hs_mlp_dgrad_gelu_supported(T0 // 4, 192, 768) == 1

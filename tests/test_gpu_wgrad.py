@@ -27,7 +27,9 @@ def _wgrad(dy, x):
                                    (4096 + 37, 192, 768), (8192, 32, 64), (20000, 100, 64), (8192, 1152, 256),
                                    # smaller feature dimension in (256, 512]: 32-token stages, two MMAs per K step
                                    (8192, 1152, 384), (8192, 384, 384), (6000, 384, 1536), (8192, 640, 512),
-                                   (8192, 288, 320)])
+                                   (8192, 288, 320),
+                                   # smaller feature dimension in (512, 1024]: two launches over its column halves (stage 3)
+                                   (24576, 2304, 768), (8192, 768, 768), (6000, 768, 3072), (8192, 1536, 1024)])
 def test_wgrad_matches_fp32_product(T, N, K):
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(T + N + K)
