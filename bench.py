@@ -339,7 +339,7 @@ def run_ours(a):
     loss_fn = torch.nn.CrossEntropyLoss()
     host_loss = torch.zeros((), dtype=torch.float32).pin_memory()
 
-    use_graph = (not a.no_cuda_graph) and a.drop_rate == 0.0
+    use_graph = not a.no_cuda_graph
     if use_graph:
         # the public training-step API of the package: forward + loss + backward replayed as one CUDA graph, one flat
         # NCCL all-reduce of the gradients, fused Adam

@@ -46,10 +46,11 @@ using namespace hs::sm100;
 constexpr int kBM = 128;               // tokens per tile
 constexpr int kChunk = kBM * 128;      // 16 KB: one A chunk, one staging slab
 constexpr int kMaxRing = 10;
-constexpr int kMaxWRing = 4;            // streamed W slices (L2 hits: a short ring is enough)
+constexpr int kMaxWRing = 6;            // streamed W slices (L2 hits: a short ring is enough)
 constexpr int kMaxRw = 3;              // staging regions per epilogue warp
 constexpr int kRegion = 32 * 128;      // 4 KB: 32 rows x 32 columns, one warp's part of a slab
 constexpr int kCvtWarps = 8;
+constexpr int kTeam = 4;               // converter warps per chunk (one per TMEM lane quadrant); two teams alternate
 constexpr int kASlots = 4;             // A-operand slots of 32 TMEM columns behind two 192-column accumulator stages
 constexpr int kACol0 = 2 * 192;
 
@@ -127,6 +128,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   constexpr bool kAux = (MODE == MODE_ADD || MODE == MODE_GELU_GRAD);
   constexpr int NG = E / 4;                    // epilogue groups (4 warps = the 4 TMEM lane quadrants)
   constexpr int kStores = (MODE == MODE_GELU) ? 2 : 1;
+  constexpr bool kColsumOk = (MODE == MODE_PLAIN || MODE == MODE_ADD);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nk = (a.K + 31) / 32;              // K chunks (TMA zero-fills the tail of a ragged last chunk)
@@ -163,14 +165,14 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_init(&raw_full[i], 1);
       // released by the converters once the chunk is in their registers; in TF32 mode by the MMAs that read it (and by the
       // converters as well when they take the column sums)
-      mbar_init(&slot_empty[i], a.prec == PREC_TF32 ? 1 + ((a.colsum && chunk == 0) ? kCvtWarps : 0)
-                                : (a.ss ? 1 : kCvtWarps));
+      mbar_init(&slot_empty[i], a.prec == PREC_TF32 ? 1 + ((kColsumOk && a.colsum && chunk == 0) ? kTeam : 0)
+                                                    : (a.ss ? 1 : kTeam));
     }
     for (int i = 0; i < kASlots; ++i) {
-      mbar_init(&a_full[i], kCvtWarps);
+      mbar_init(&a_full[i], kTeam);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < kMaxRing; ++i) mbar_init(&cvt_full[i], kCvtWarps);  // ss bf16: the chunk is split in place
+    for (int i = 0; i < kMaxRing; ++i) mbar_init(&cvt_full[i], kTeam);  // ss bf16: the chunk is split in place
     {
     }
     for (int i = 0; i < 2; ++i) {
@@ -307,91 +309,103 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
     }
   } else if (warp >= E) {
-    // ================================================================ converters: fp32 chunk (smem) -> hi / lo bf16 (TMEM)
-    // warp cw: TMEM lane quadrant cw & 3 (= warp % 4, the tcgen05.st restriction), K half cw >> 2 (16 of the 32 columns)
+    // ================================================================ converters: fp32 chunk (smem) -> hi / lo bf16
+    // Two TEAMS of four warps (one per TMEM lane quadrant = warp % 4, the tcgen05.st restriction) take alternate chunks,
+    // thread = one full 32-column row: two chunks are in flight, and a thread's row is its own (the in-place variant
+    // needs no cross-warp synchronisation).  hi / lo go to a tensor-memory slot (A from TMEM) or back into the chunk
+    // (ss: A stays in shared memory); in TF32 mode the converters only take the column sums, if those are wanted.
     const int cw = warp - E;
-    const int q = cw & 3, half = cw >> 2;
+    const int q = cw & 3, team = cw >> 2;
     const int row = q * 32 + lane;
     const int sw = row & 7;
     const uint32_t ring_u32 = smem_u32(s_ring);
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    int slot = 0, as_ = 0;
-    uint32_t ph = 0, aph = 0;
-    const bool do_colsum = a.colsum != nullptr && chunk == 0;
+    // (column sums ride with the plain / add modes only: the input-gradient GEMMs; compiled out of the GELU variants, whose
+    // 16 epilogue warps leave 72 registers per thread)
+    constexpr bool kColsumMode = (MODE == MODE_PLAIN || MODE == MODE_ADD);
+    const bool do_colsum = kColsumMode && a.colsum != nullptr && chunk == 0;
     const bool convert = a.prec != PREC_TF32;  // TF32: the MMAs read the fp32 chunk directly
     const uint32_t cs_u32 = smem_u32(s_colsum);
     if (do_colsum) {
       for (int i = threadIdx.x - E * 32; i < nk * 32; i += kCvtWarps * 32) s_colsum[i] = 0.f;
       named_bar_sync(1, kCvtWarps * 32);
     }
-    if (convert || do_colsum)
-    for (long long tile = t0; tile < t_end; tile += tstep)
-      for (int kc = 0; kc < nk; ++kc) {
-        mbar_wait(&raw_full[slot], ph);
-        const uint32_t base = ring_u32 + slot * kChunk + row * 128;
-        float4 v[4];
+    if (convert || do_colsum) {
+      long long c = 0;  // running chunk index of this CTA
+      for (long long tile = t0; tile < t_end; tile += tstep)
+        for (int kc = 0; kc < nk; ++kc, ++c) {
+          // The planner keeps the ring depth EVEN, so a ring slot always belongs to the same team and each of its warps
+          // visits the slot's uses one after the other: a parity wait is then never more than one phase away from its
+          // barrier.  (With an odd ring a slot alternates between the teams and a team can poll it one phase early, TMA
+          // loads completing out of order; making every warp observe every chunk instead deadlocks, because the shared-
+          // memory ring is released before the tensor-memory slot is awaited and a skipping warp can fall a whole ring
+          // cycle behind.  Both were seen on the B200 at full size only.)
+          if ((int)(c & 1) != team) continue;
+          const int slot = (int)(c % ring);
+          const uint32_t ph = (uint32_t)(c / ring) & 1;
+          mbar_wait(&raw_full[slot], ph);
+          const uint32_t base = ring_u32 + slot * kChunk + row * 128;
+          float4 v[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = lds_f4(base + (((4 * half + j) ^ sw) << 4));
-        if (do_colsum) {
-          // column sums of this warp's 32 rows x 16 columns: a reduce-scatter over the lanes (8 + 4 + 2 + 1 + 1 shuffles)
-          // leaves one column per even lane, which adds it to the CTA's running sums
-          const float c[16] = {v[0].x, v[0].y, v[0].z, v[0].w, v[1].x, v[1].y, v[1].z, v[1].w,
-                               v[2].x, v[2].y, v[2].z, v[2].w, v[3].x, v[3].y, v[3].z, v[3].w};
-          const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-          float k8[8], k4[4], k2[2];
+          for (int j = 0; j < 8; ++j) v[j] = lds_f4(base + ((j ^ sw) << 4));
+          if (do_colsum) {
+            // column sums of this warp's 32 rows x 32 columns: a reduce-scatter over the lanes (16 + 8 + 4 + 2 + 1
+            // shuffles) leaves one column per lane, which adds it to the CTA's running sums
+            const float* cc = reinterpret_cast<const float*>(v);
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+            float k16[16], k8[8], k4[4], k2[2];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            k8[i] = (b4 ? c[i + 8] : c[i]) + __shfl_xor_sync(0xffffffffu, b4 ? c[i] : c[i + 8], 16);
+            for (int i = 0; i < 16; ++i)
+              k16[i] = (b4 ? cc[i + 16] : cc[i]) + __shfl_xor_sync(0xffffffffu, b4 ? cc[i] : cc[i + 16], 16);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            k4[i] = (b3 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k8[i] : k8[i + 4], 8);
+            for (int i = 0; i < 8; ++i)
+              k8[i] = (b3 ? k16[i + 8] : k16[i]) + __shfl_xor_sync(0xffffffffu, b3 ? k16[i] : k16[i + 8], 8);
 #pragma unroll
-          for (int i = 0; i < 2; ++i)
-            k2[i] = (b2 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, b2 ? k4[i] : k4[i + 2], 4);
-          float k1 = (b1 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b1 ? k2[0] : k2[1], 2);
-          k1 += __shfl_xor_sync(0xffffffffu, k1, 1);
-          const int col = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
-          if (!(lane & 1)) red_add_shared_f32(cs_u32 + 4 * (32 * kc + 16 * half + col), k1);
-        }
-        uint32_t hi[8], lo[8];
-        split2(v[0].x, v[0].y, hi[0], lo[0]);
-        split2(v[0].z, v[0].w, hi[1], lo[1]);
-        split2(v[1].x, v[1].y, hi[2], lo[2]);
-        split2(v[1].z, v[1].w, hi[3], lo[3]);
-        split2(v[2].x, v[2].y, hi[4], lo[4]);
-        split2(v[2].z, v[2].w, hi[5], lo[5]);
-        split2(v[3].x, v[3].y, hi[6], lo[6]);
-        split2(v[3].z, v[3].w, hi[7], lo[7]);
-        if (convert && a.ss) {
-          // in place: this thread's half row (64 B) becomes hi (32 B at chunk 2 half) + lo (32 B at chunk 4 + 2 half); the
-          // two warps of a row half pair exchange nothing, but hi / lo of the OTHER half live in chunks this thread reads
-          // from -- all four warps of the chunk's row quadrant pair must have read before anyone writes
-          named_bar_sync(2 + q, 64);
-          sts_u4(base + (((2 * half + 0) ^ sw) << 4), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-          sts_u4(base + (((2 * half + 1) ^ sw) << 4), make_uint4(hi[4], hi[5], hi[6], hi[7]));
-          sts_u4(base + (((4 + 2 * half + 0) ^ sw) << 4), make_uint4(lo[0], lo[1], lo[2], lo[3]));
-          sts_u4(base + (((4 + 2 * half + 1) ^ sw) << 4), make_uint4(lo[4], lo[5], lo[6], lo[7]));
-          fence_proxy_async_smem();
+            for (int i = 0; i < 4; ++i)
+              k4[i] = (b2 ? k8[i + 4] : k8[i]) + __shfl_xor_sync(0xffffffffu, b2 ? k8[i] : k8[i + 4], 4);
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+              k2[i] = (b1 ? k4[i + 2] : k4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? k4[i] : k4[i + 2], 2);
+            const float k1 = (b0 ? k2[1] : k2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? k2[0] : k2[1], 1);
+            const int col = (b4 ? 16 : 0) + (b3 ? 8 : 0) + (b2 ? 4 : 0) + (b1 ? 2 : 0) + (b0 ? 1 : 0);
+            red_add_shared_f32(cs_u32 + 4 * (32 * kc + col), k1);
+          }
+          if (!convert) {  // TF32 + column sums: the slot is released by the MMAs and by this team
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&slot_empty[slot]);
+            continue;
+          }
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            split2(v[j].x, v[j].y, hi[2 * j], lo[2 * j]);
+            split2(v[j].z, v[j].w, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          if (a.ss) {  // in place: hi -> 16-byte chunks 0-3 of my row, lo -> chunks 4-7 (all eight are in my registers)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              sts_u4(base + ((j ^ sw) << 4), make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]));
+              sts_u4(base + (((4 + j) ^ sw) << 4), make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&cvt_full[slot]);
+            continue;
+          }
+          __syncwarp();  // every lane holds its row in registers: the shared-memory slot can be refilled
+          if (lane == 0) mbar_arrive(&slot_empty[slot]);
+          const int as_ = (int)(c % kASlots);
+          mbar_wait(&a_empty[as_], (((uint32_t)(c / kASlots)) & 1) ^ 1);  // the MMAs that read this slot have completed
+          tc_fence_after();
+          const uint32_t at = tmem + lane_addr + kACol0 + 32 * as_;
+          tmem_st16(at, hi);
+          if (a.prec == PREC_BF16X3) tmem_st16(at + 16, lo);
+          tmem_wait_st();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&cvt_full[slot]);
-          if (++slot == ring) { slot = 0; ph ^= 1; }
-          continue;
+          if (lane == 0) mbar_arrive(&a_full[as_]);
         }
-        __syncwarp();  // every lane holds its part of the chunk in registers: the shared-memory slot can be refilled
-        if (lane == 0) mbar_arrive(&slot_empty[slot]);
-        if (++slot == ring) { slot = 0; ph ^= 1; }
-        if (!convert) continue;
-        mbar_wait(&a_empty[as_], aph ^ 1);  // the MMAs that read this tensor-memory slot have completed
-        tc_fence_after();
-        const uint32_t at = tmem + lane_addr + kACol0 + 32 * as_;
-        tmem_st8(at + 8 * half, hi);
-        if (a.prec == PREC_BF16X3) tmem_st8(at + 16 + 8 * half, lo);
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[as_]);
-        if (++as_ == kASlots) { as_ = 0; aph ^= 1; }
-      }
+    }
     if (do_colsum) {
       named_bar_sync(1, kCvtWarps * 32);
       for (int i = threadIdx.x - E * 32; i < a.K; i += kCvtWarps * 32) atomicAdd(a.colsum + i, s_colsum[i]);
@@ -595,11 +609,16 @@ int plan(G3Args& a, int mode, int E) {
     const int w_slice = box * 128;
     const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0);
     const int resident = ((long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
-    const int wring = nk < 3 ? nk : 3;
+    int wring = nk < 3 ? nk : 3;
+    if (const char* e = getenv("HEALSWIN_GEMM3_WRING")) {  // experiments only
+      const int v = atoi(e);
+      if (v >= 2 && v <= kMaxWRing && v <= nk) wring = v;
+    }
     const long long w_bytes = (long long)(resident ? nk : wring) * w_slice;
     long long left = kSmemAvail - w_bytes - staging_min;
     int ring = left > 0 ? (int)(left / kChunk) : 0;
     if (ring > kMaxRing) ring = kMaxRing;
+    ring &= ~1;  // even: chunk c and chunk c + ring are converted by the same team
     if (ring <= best_ring) continue;
     best_ring = ring;
     a.n_stride = stride;
@@ -713,6 +732,7 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
   const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
   HS_REQUIRE(!aux || aux_dev, "hs_gemm3: mode %d needs the aux tensor", mode);
   HS_REQUIRE(mode != MODE_GELU || d2_dev, "hs_gemm3: MODE_GELU needs the second output");
+  HS_REQUIRE(!colsum_dev || mode == MODE_PLAIN || mode == MODE_ADD, "hs_gemm3: column sums ride with modes 0 and 1 only");
   HS_REQUIRE(!((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(wsplit_dev) |
                 reinterpret_cast<uintptr_t>(bias_dev) | reinterpret_cast<uintptr_t>(aux_dev) |
                 reinterpret_cast<uintptr_t>(d_dev) | reinterpret_cast<uintptr_t>(d2_dev)) & 15),

@@ -14,8 +14,10 @@ Data parallelism: the captured part is rank-local.  Gradients live in ONE flat b
 exchange step after the replay is a single NCCL all-reduce over NVLink, followed by the (eager, fused) optimizer step.
 The reference gets the same semantics from Lightning's DDP plugin (heal_swin/train.py:187).
 
-Limits: dropout / stochastic depth draw their mask seeds on the host, so a replay would repeat the captured masks --
-models with a non-zero drop probability in training mode are refused (use the eager path for those).
+Dropout: the element / attention-probability masks of this library are pure functions of (seed, position).  Inside a
+capture ``ops._next_dropout_seed`` hands out INDIRECT seeds that refer to a device-side counter (csrc/hs_common.h:
+``resolve_seed``); the captured step increments that counter first, so every replay draws fresh masks while forward and
+backward of one replay agree.  Stochastic depth uses torch's own graph-safe CUDA generator.
 """
 import torch
 import torch.distributed as dist
@@ -43,10 +45,9 @@ class GraphedTrainStep:
     models_lightning/segmentation/model_lightning_swin_hp.py:61 -- runs inside the captured graph."""
 
     def __init__(self, model, loss_fn, optimizer, example_x, example_t, warmup=3, preprocess=None):
-        p = _active_drop_probability(model)
-        assert p == 0.0, (f"the model has an active drop probability of {p}: a graph replay would repeat the captured "
-                          "dropout masks; train such configurations eagerly")
         self.model, self.loss_fn, self.optimizer = model, loss_fn, optimizer
+        self.has_dropout = _active_drop_probability(model) > 0.0
+        self.seed_counter = ops.seed_counter(example_x.device)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.params = [q for q in model.parameters() if q.requires_grad]
         total = sum(q.numel() for q in self.params)
@@ -80,6 +81,7 @@ class GraphedTrainStep:
         ops.STATS.timing = was_timing
 
     def _fwd_bwd(self):
+        self.seed_counter.add_(1)  # (captured: every replay advances the counter behind the indirect dropout seeds)
         self.flat_grad.zero_()
         x, t = (self.x, self.t) if self.preprocess is None else self.preprocess(self.x, self.t)
         loss = self.loss_fn(self.model(x), t)

@@ -95,12 +95,42 @@ class GatherRows(torch.autograd.Function):
         return out, None, None
 
 
+_SEED_COUNTERS = {}   # device -> int64 tensor [1]: the replay counter indirect seeds refer to
+_SEED_CALL_ID = [0]
+
+
+def seed_counter(device):
+    """The device-side counter behind indirect dropout seeds (csrc/hs_common.h: resolve_seed).  A captured training step
+    increments it once per replay (heal_swin_b200/graph.py), which gives every replay fresh masks."""
+    dev = torch.device(device)
+    t = _SEED_COUNTERS.get(dev)
+    if t is None:
+        base = int(torch.randint(0, 2**31, (1,)).item()) + (int(os.environ.get("RANK", "0")) << 32)
+        t = _SEED_COUNTERS[dev] = torch.tensor([base], device=dev, dtype=torch.int64)
+    return t
+
+
 def _next_dropout_seed() -> int:
-    """64-bit seed of one attention-dropout mask, drawn from torch's default CPU generator: reproducible under
+    """64-bit seed of one dropout mask.  Eagerly: drawn from torch's default CPU generator -- reproducible under
     torch.manual_seed, replayed identically when torch.utils.checkpoint re-runs the forward (it restores the RNG state),
-    no device sync.  The rank is mixed in so that data-parallel shards do not share masks."""
+    no device sync; the rank is mixed in so that data-parallel shards do not share masks.  Inside a CUDA-graph capture a
+    host integer would be baked into the graph and every replay would repeat the mask: there the seed is INDIRECT (bit
+    63 set, a call id in bits 48-62, the address of the device-side replay counter in bits 0-47)."""
+    if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        _SEED_CALL_ID[0] = (_SEED_CALL_ID[0] + 1) & 0x7FFF
+        ptr_ = seed_counter(torch.device("cuda", torch.cuda.current_device())).data_ptr()
+        assert ptr_ < (1 << 48)
+        return (1 << 63) | (_SEED_CALL_ID[0] << 48) | ptr_
     x = int(torch.randint(0, 2**62, (1,)).item()) ^ (int(os.environ.get("RANK", "0")) * 0xD1B54A32D192ED03)
-    return x & 0xFFFFFFFFFFFFFFFF
+    return x & 0x7FFFFFFFFFFFFFFF
+
+
+def _pick_seed(seed, p):
+    """A fresh seed when dropout is active and none was given; a caller's seed is a plain VALUE (bit 63 is reserved for
+    the indirect seeds of graph captures and is cleared)."""
+    if seed is None:
+        return _next_dropout_seed() if p > 0.0 else 0
+    return int(seed) & 0x7FFFFFFFFFFFFFFF
 
 
 class WindowAttnCore(torch.autograd.Function):
@@ -176,8 +206,7 @@ def window_attention_core(qkv, bias_table, logit_scale, src, groups, dense_mask,
     """``attn_drop`` > 0 applies dropout to the attention probabilities inside the kernel (training mode of
     ``nn.Dropout(attn_drop)``, swin_hp_transformer.py:167-169); ``seed`` fixes the mask (default: a fresh one)."""
     attn_drop = float(attn_drop)
-    if attn_drop > 0.0 and seed is None:
-        seed = _next_dropout_seed()
+    seed = _pick_seed(seed, attn_drop)
     return WindowAttnCore.apply(qkv, bias_table, logit_scale, src, groups, dense_mask, rel_index_i32,
                                 float(scale), num_heads, window_size, bool(use_cos), attn_drop, int(seed or 0))
 
@@ -242,8 +271,7 @@ def layer_norm(x, norm, residual=None, pre_bias=None, row_scale=None, in_drop=0.
     Any other norm layer is applied as the module it is."""
     in_drop = float(in_drop)
     if _fusable_norm(norm, x):
-        if in_drop > 0.0 and seed is None:
-            seed = _next_dropout_seed()
+        seed = _pick_seed(seed, in_drop)
         return LayerNormFn.apply(x, norm.weight, norm.bias, residual, pre_bias, float(norm.eps), row_scale, in_drop,
                                  int(seed or 0))
     h = x if pre_bias is None else x + pre_bias
@@ -338,8 +366,7 @@ def bias_gelu(z, bias, drop=0.0, seed=None):
     if not (z.is_cuda and lib.hs_bias_gelu_supported(z.numel() // z.shape[-1], z.shape[-1])):
         h = torch.nn.functional.gelu(z if bias is None else z + bias)
         return torch.nn.functional.dropout(h, drop, True) if drop > 0.0 else h
-    if drop > 0.0 and seed is None:
-        seed = _next_dropout_seed()
+    seed = _pick_seed(seed, drop)
     return BiasGeluFn.apply(z, bias, drop, int(seed or 0))
 
 
@@ -650,8 +677,7 @@ def mlp_core(x, fc1, fc2, drop=0.0, seed=None, fork=False):
     """``F.linear(dropout(GELU(fc1(x))), fc2.weight)`` (no fc2 bias) through the fused node; check ``mlp_supported``.
     ``fork``: also return the input as the residual shortcut (see ``linear``)."""
     drop = float(drop)
-    if drop > 0.0 and seed is None:
-        seed = _next_dropout_seed()
+    seed = _pick_seed(seed, drop)
     return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0), bool(fork))
 
 

@@ -18,6 +18,10 @@
  *     caches: the driver entry point for TMA descriptors, the SM count) and are
  *     re-entrant (forward runs on the main thread, backward on the autograd thread).
  *   - tensors are dense row-major fp32 unless said otherwise.
+ *   - dropout `seed` arguments: a plain 63-bit value, or -- bit 63 set -- an INDIRECT seed: bits 0-47 = address of a
+ *     uint64 counter in device memory, bits 48-62 = a call id; the kernels mix the counter's current value with the id.
+ *     A captured CUDA graph that increments the counter once per replay thereby draws fresh masks on every replay while
+ *     the forward and the backward of one replay agree (heal_swin_b200/graph.py).
  */
 #ifndef HEALSWIN_B200_H
 #define HEALSWIN_B200_H

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One training step (forward + CE + backward) of every BASELINE.json configuration that fits one GPU, on the B200
 kernels: config 1 (tiny, window 16 / head_dim 16: exact-fp32 CUDA-core attention path), config 2 (the benchmark model),
-config 4 (depth head, C=128 -- run in fp32/TF32: this engine has no bf16 path), config 5 (flat SWIN-UNet 640x640,
+config 4 (depth head, C=128: fp32-class GEMMs and the bf16-operand mode), config 5 (flat SWIN-UNet 640x640,
 window 8).  Prints ms per step (CUDA events, 3 steps after 2 warm-ups) and checks that outputs and gradients are finite."""
 import os
 import sys
@@ -14,7 +14,6 @@ from heal_swin_b200.models_torch import swin_hp_transformer as HP  # noqa: E402
 from heal_swin_b200.models_torch import swin_transformer as FL  # noqa: E402
 
 dev = torch.device("cuda:0")
-torch.backends.cuda.matmul.allow_tf32 = True
 
 
 def run(name, model, x, target_fn):
@@ -83,8 +82,14 @@ cfg = HP.SwinHPTransformerConfig(patch_size=4, window_size=64, shift_size=4, shi
                                  embed_dim=128, depths=[2, 2, 6, 2], num_heads=[4, 8, 16, 32], use_cos_attn=True,
                                  use_v2_norm_placement=True, drop_path_rate=0.0)
 d = torch.randn(8, 1, n, generator=g).to(dev)
-run("config 4 (depth head, C=128, f_out=1, B=8, TF32 not bf16)", HP.SwinHPTransformerSys(cfg, DataSpec(n, 3, 1, 12)), x,
+run("config 4 (depth head, C=128, f_out=1, B=8, fp32-class GEMMs)", HP.SwinHPTransformerSys(cfg, DataSpec(n, 3, 1, 12)), x,
     lambda y: (y - d).square().mean())
+from heal_swin_b200 import ops  # noqa: E402
+
+ops.set_gemm_precision("bf16")  # "bf16 operands, fp32 accumulate": the arithmetic BASELINE configs[3] names
+run("config 4 (depth head, C=128, f_out=1, B=8, bf16 operands)", HP.SwinHPTransformerSys(cfg, DataSpec(n, 3, 1, 12)), x,
+    lambda y: (y - d).square().mean())
+ops.set_gemm_precision("fp32")
 del x, t, d
 
 # config 5: flat SWIN-UNet 640x640, patch 2, window 8, shift 2, C=96, batch 8

@@ -70,6 +70,10 @@ def main():
             ("s3 qkv", T3, 2304, 768), ("s3 fc1", T3, 3072, 768), ("s3 fc2", T3, 768, 3072),
             ("merge0", T1, 192, 384), ("expand3", T3, 1536, 768), ("final expand", T0, 384, 96), ("concat1", T1, 192, 384),
         ]
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    if only:
+        shapes = [sh for sh in shapes if any(o in sh[0] for o in only)]
+    dprec = 1 if "--tf32-dgrad" in sys.argv else 0  # time the dgrad + aux column in the single-MMA TF32 mode
     ok = True
     for label, T, N, K in shapes:
         a = torch.randn(T, K, device=dev)
@@ -123,7 +127,8 @@ def main():
             tlt = timeit(lambda: torch.nn.functional.linear(a, w, bias, out=None))
             z2, h2 = torch.empty_like(d), torch.empty_like(d)
             tg = timeit(lambda: gemm3(a, ws, bias, mode=2, d=z2, d2=h2))
-            ta = timeit(lambda: gemm3(dy, wst, None, aux, mode=1, d=dx1))
+            wst_t = split(w, transposed=True, prec=dprec) if dprec else wst
+            ta = timeit(lambda: gemm3(dy, wst_t, None, aux, mode=1, d=dx1, prec=dprec))
             tgg = timeit(lambda: gemm3(a, ws, bias, zz, mode=3, d=g3))
             gb = T * (N + K) * 4 / 1e9
             fl = 2.0 * T * N * K / 1e12

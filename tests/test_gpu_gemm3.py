@@ -195,3 +195,28 @@ def test_single_mma_precisions(T, N, K):
     got = _gemm3(a, _split(w), N, b)
     e_x3 = rel_err(got.cpu(), want.cpu())
     assert e_x3 < TOL < e_tf32 < 1e-3 < e_bf16 < 6e-3, (e_x3, e_tf32, e_bf16)
+
+
+@pytest.mark.parametrize("T,N,K,prec", [
+    (8 * 196608, 96, 288, 0),    # stage-0 qkv input gradient: 9 K chunks per tile, resident W (the shape that exposed the
+                                 # converter-team parity hazard: it needs a long persistent loop to show)
+    (8 * 196608, 96, 384, 0),    # stage-0 fc2: streamed W
+    (8 * 49152, 768, 192, 0),    # stage-1 fc1: four column chunks
+    (8 * 12288, 1536, 384, 0),   # stage-2 fc1: tensor-bound, A split in place in shared memory, 256-column stages
+    (8 * 12288, 384, 1536, 1),   # stage-2 fc1 input gradient: single TF32 MMA
+    (8 * 3072, 768, 3072, 0),    # stage-3 fc2
+    (8 * 12288, 384, 1152, 2),   # bf16-operand mode
+])
+def test_full_size_launches_are_exact_on_small_integer_data(T, N, K, prec):
+    """BASELINE configs[1] shapes at their full token counts (long persistent loops, every pipeline barrier cycling
+    thousands of times): on small-integer data every product and every partial sum is exact in all three precisions, so
+    the result must be BIT-EXACT on every tile -- any protocol slip (a stale or half-converted chunk) shows."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(T % 1000 + N + K)
+    a = torch.randint(-4, 5, (T, K), generator=g, device=dev).float()
+    w = torch.randint(-4, 5, (N, K), generator=g, device=dev).float()
+    for _ in range(3):
+        got = _gemm3(a, _split(w, prec=prec), N, prec=prec)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = a @ w.t()  # exact: |sum| <= 3072 * 16 < 2^24
+    assert torch.equal(got, want)

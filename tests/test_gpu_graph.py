@@ -1,6 +1,6 @@
 """GraphedTrainStep (heal_swin_b200/graph.py): the CUDA-graph replay of forward + loss + backward trains exactly like the
 eager step -- in particular the weight-split operands of the bf16x3 GEMMs are refreshed inside the graph after every
-optimizer step -- and refuses configurations whose dropout masks a replay would repeat."""
+optimizer step -- and draws fresh dropout masks on every replay (indirect seeds, csrc/hs_common.h: resolve_seed)."""
 import copy
 
 import pytest
@@ -53,11 +53,29 @@ def test_graph_replay_trains_like_the_eager_step():
     assert abs(l_eager - float(loss_fn(model_a(x0), t0))) < 0.2  # (weights moved by one more step in between)
 
 
-def test_graph_refuses_active_dropout():
+def test_graph_replays_draw_fresh_dropout_masks():
+    """With dropout active the captured step uses INDIRECT seeds (a device-side counter the graph bumps per replay): with
+    frozen weights (lr = 0) consecutive replays of the SAME batch give different losses -- different masks -- whose mean
+    agrees with the eager step's, and with a real optimizer the replayed step trains."""
     from heal_swin_b200.graph import GraphedTrainStep
 
     dev = torch.device("cuda:0")
-    model = build_product_model(dict(KW, drop_rate=0.1), None, dev).train()
+    torch.manual_seed(0)
+    kw = dict(KW, drop_rate=0.2, attn_drop_rate=0.2, drop_path_rate=0.1)
+    model = build_product_model(kw, None, dev).train()
+    loss_fn = torch.nn.CrossEntropyLoss()
     x0, t0 = _data(dev, 0)
-    with pytest.raises(AssertionError, match="drop probability"):
-        GraphedTrainStep(model, torch.nn.CrossEntropyLoss(), torch.optim.Adam(model.parameters()), x0, t0)
+    frozen = torch.optim.SGD(model.parameters(), lr=0.0)
+    step = GraphedTrainStep(model, loss_fn, frozen, x0, t0)
+    assert step.has_dropout
+    replayed = [float(step(x0, t0)) for _ in range(8)]
+    assert len({round(v, 6) for v in replayed}) >= 7, replayed          # fresh masks on (practically) every replay
+    eager = [float(step(x0, t0, eager=True)) for _ in range(8)]
+    assert len({round(v, 6) for v in eager}) >= 7, eager
+    m_r, m_e = sum(replayed) / 8, sum(eager) / 8
+    assert abs(m_r - m_e) < 0.05 * m_e, (replayed, eager)
+    # and it trains
+    opt = torch.optim.Adam(model.parameters(), lr=2e-3, fused=True)
+    step2 = GraphedTrainStep(model, loss_fn, opt, x0, t0)
+    losses = [float(step2(x0, t0)) for _ in range(40)]
+    assert all(v == v for v in losses) and min(losses[-8:]) < 0.85 * losses[0], losses[::5]

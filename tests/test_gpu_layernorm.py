@@ -157,7 +157,7 @@ def test_layernorm_fused_dropout_droppath_matches_torch_with_the_same_mask(C):
     from heal_swin_b200 import ops
 
     dev = torch.device("cuda:0")
-    B, n, p, seed = 4, 150, 0.2, 0xABCDEF0123456789
+    B, n, p, seed = 4, 150, 0.2, 0x2BCDEF0123456789
     rows = B * n
     g = torch.Generator().manual_seed(C)
     x = torch.randn(B, n, C, generator=g).to(dev).requires_grad_(True)
