@@ -50,6 +50,8 @@ SIGNATURES = {
     "hs_ln_head_supported": [_i64, _i, _i],
     "hs_ln_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _f, _p],
     "hs_ln_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],
+    "hs_cross_entropy_supported": [_i],
+    "hs_cross_entropy": [_p, _p, _i, _p, _p, _i, _i, _i64, _i64, _p],
     "hs_bias_gelu_supported": [_i64, _i],
     "hs_bias_gelu_fwd": [_p, _p, _f, _u64, _p, _i64, _i, _p],
     "hs_bias_gelu_bwd": [_p, _p, _p, _f, _u64, _p, _p, _i64, _i, _p],

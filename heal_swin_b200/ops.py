@@ -259,6 +259,51 @@ class LayerNormFn(torch.autograd.Function):
         return dx.view(ctx.shape), dw, db, dres, dpb, None, None, None, None
 
 
+class _CrossEntropyFn(torch.autograd.Function):
+    """Mean cross-entropy over (B, K, P) logits and (B, P) class ids with the gradient produced in the same pass
+    (csrc/hs_cross_entropy.cu): the backward is one scaling of the saved gradient."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        require_cuda(logits, target)
+        x = _f32c(logits)
+        B, K = x.shape[0], x.shape[1]
+        P = x.numel() // (B * K)
+        t = target.contiguous()
+        assert t.numel() == B * P and t.dtype in (torch.uint8, torch.int64), "targets: (B, P) uint8 or int64"
+        dl = torch.empty_like(x)
+        acc = torch.zeros(2, device=x.device, dtype=torch.float32)
+        STATS.launch("cross_entropy", lib.hs_cross_entropy, ptr(x), ptr(t), t.element_size(), ptr(dl), ptr(acc), B, K, P,
+                     int(ignore_index), current_stream(), tag=(B * P, K))
+        ctx.save_for_backward(dl, acc)
+        return acc[0] / acc[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        dl, acc = ctx.saved_tensors
+        return dl.mul_(g / acc[1]), None, None  # (the saved gradient is consumed: one backward per forward)
+
+
+def cross_entropy(logits, target, ignore_index=-100):
+    """``F.cross_entropy(logits, target)`` (mean reduction, no class weights, no label smoothing) for the network output
+    (B, K, *spatial) and class ids (B, *spatial); uint8 targets are accepted as they come from the data pipeline."""
+    if (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() >= 3 and target.dtype in (torch.uint8, torch.int64)
+            and lib.hs_cross_entropy_supported(logits.shape[1])):
+        return _CrossEntropyFn.apply(logits, target, ignore_index)
+    return torch.nn.functional.cross_entropy(logits, target.long(), ignore_index=ignore_index)
+
+
+class CrossEntropyLoss(torch.nn.Module):
+    """Drop-in for ``nn.CrossEntropyLoss()`` with default arguments (model_lightning_swin_hp.py:45)."""
+
+    def __init__(self, ignore_index=-100):
+        super().__init__()
+        self.ignore_index = ignore_index
+
+    def forward(self, logits, target):
+        return cross_entropy(logits, target, self.ignore_index)
+
+
 def _fusable_norm(norm, x):
     return (isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine and norm.bias is not None
             and len(norm.normalized_shape) == 1 and norm.normalized_shape[0] == x.shape[-1])

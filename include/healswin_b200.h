@@ -263,6 +263,19 @@ int hs_ln_head_bwd(const float* dlogits_dev, const float* x_dev, const float* me
                    const float* gamma_dev, const float* w_dev, float* dx_dev, float* s_acc_dev, float* g_acc_dev,
                    int64_t rows, int64_t rows_per_sample, int C, int K, void* stream);
 
+/*
+ * Cross-entropy over the network output, forward and gradient in one pass (nn.CrossEntropyLoss,
+ * heal_swin/models_lightning/segmentation/model_lightning_swin_hp.py:45, 109):
+ *   logits, dlogits: (B, K, P) fp32 (class planes of P pixels, the layout of the network output); target: (B, P) uint8 or
+ *   int64 (target_bytes = 1 | 8); pixels whose target equals ignore_index (or lies outside [0, K)) are not counted.
+ *   dlogits = softmax(logits) - onehot(target) (0 for uncounted pixels) -- UNSCALED; acc[0] += sum of -log softmax[target],
+ *   acc[1] += number of counted pixels (zero acc first).  mean loss = acc[0] / acc[1]; d(mean loss) = dlogits / acc[1].
+ * hs_cross_entropy_supported: 1 <= K <= 32.
+ */
+int hs_cross_entropy_supported(int K);
+int hs_cross_entropy(const float* logits_dev, const void* target_dev, int target_bytes, float* dlogits_dev, float* acc_dev,
+                     int B, int K, int64_t P, int64_t ignore_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
