@@ -379,13 +379,13 @@ int pick_grid_x(long long total, int H, int num_sms, int ctas_per_sm) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return cached ? cached : 148;
+  // per device (a process may drive several GPUs): an immutable cache, filled on first use
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev] ? cached[dev] : 148;
 }
 
 }  // namespace

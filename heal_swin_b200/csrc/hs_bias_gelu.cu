@@ -89,13 +89,13 @@ int pick_block(int C4) {  // a multiple of C4, as close to 512 threads as possib
 }
 
 int num_sms() {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return cached ? cached : 148;
+  // per device (a process may drive several GPUs): an immutable cache, filled on first use
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) cudaDeviceGetAttribute(&cached[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cached[dev] ? cached[dev] : 148;
 }
 
 bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

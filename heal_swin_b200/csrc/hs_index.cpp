@@ -366,8 +366,8 @@ int hs_shift_tables(int strategy, int64_t nside, int base_pix, int ws, int shift
 }
 
 int hs_attn_mask_from_groups(const int8_t* groups, int64_t N, int ws, float* mask) {
+  // any window size: the flat (lat-lon) twin takes rectangular windows such as 4 x 6; only the HEALPix tables above need 2^k
   HS_REQUIRE(groups && mask && ws > 0 && N % ws == 0, "hs_attn_mask_from_groups: bad arguments");
-  HS_REQUIRE(is_pow2(ws), "window_size must be a power of 2 (got %d)", ws);
   for (int64_t w = 0; w < N / ws; ++w)
     for (int i = 0; i < ws; ++i)
       for (int j = 0; j < ws; ++j)

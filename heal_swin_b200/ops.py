@@ -590,6 +590,13 @@ def _wgrad_fuses_bias(dy2, x2) -> bool:
                 and lib.hs_linear_wgrad_supported(dy2.shape[0], dy2.shape[1], x2.shape[1]) == 2)
 
 
+def _tc_flags() -> int:
+    """Flags for the TF32 kernels: HEALSWIN_NO_TRUNC_COMP=1 switches the statistical truncation compensation off in ALL of
+    them (attention, weight gradient, stage-0/1 MLP gradient) -- for operands that are exactly representable in TF32 the
+    compensation is a +3.5e-4 .. 7e-4 bias rather than a correction."""
+    return _lib.ATTN_NO_TRUNC_COMP if os.environ.get("HEALSWIN_NO_TRUNC_COMP") == "1" else 0
+
+
 def _wgrad(dy2, x2, need_bias):
     """(dW, db or None) of a linear: the token-split tensor-core kernel where it covers the shape, else the library."""
     T, N = dy2.shape
@@ -600,7 +607,7 @@ def _wgrad(dy2, x2, need_bias):
         dw = torch.zeros((N, K), device=x2.device, dtype=torch.float32)
         if need_bias and cover == 2:  # bias gradient in the same pass over dy
             db = torch.zeros((N,), device=x2.device, dtype=torch.float32)
-        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, 0,
+        STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, _tc_flags(),
                      current_stream(), tag=(T, N, K))
     else:
         # shapes outside the kernel (min(N, K) > 512: stage 3; K < 32: patch embedding): the library GEMM, in the same
@@ -690,7 +697,7 @@ class _MlpFn(torch.autograd.Function):
         if _TF32_MLP_DGRAD and lib.hs_mlp_dgrad_gelu_supported(T, Cout, J):
             dz = torch.empty_like(z)
             STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1),
-                         C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, 0, current_stream(),
+                         C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, _tc_flags(), current_stream(),
                          tag=(T, Cout, J))
         else:
             prec = _dgrad_prec(T, J, Cout)

@@ -30,6 +30,9 @@ FLAT_CASES = {
     "nomask_norel": (dict(patch_size=[2, 2], window_size=[8, 8], shift_size=[4, 4], embed_dim=32, depths=[2, 2],
                           num_heads=[1, 2], use_masking=False, use_rel_pos_bias=False, dim_in=(32, 32),
                           f_in=2, f_out=2), 2),
+    # non-power-of-two window (4 x 6 = 24 tokens) and a deepest stage that collapses to a single window (no shift)
+    "v1_ws4x6": (dict(patch_size=[2, 2], window_size=[4, 6], shift_size=[2, 3], embed_dim=16, depths=[2, 2, 2],
+                      num_heads=[1, 2, 4], dim_in=(32, 48), f_in=2, f_out=4), 2),
 }
 
 FLAT_GRAD_KEYS = (
