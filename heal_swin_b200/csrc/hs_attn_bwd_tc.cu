@@ -35,10 +35,24 @@ namespace {
 using namespace hs::sm100;
 using namespace hs::tc;
 
-constexpr int kSlots = 3;
+constexpr int kKS = 2;  // ring of K-major input tiles (live from the load to the end of the score MMAs)
+constexpr int kMS = 4;  // ring of MN-major input tiles (live until the TMA store of the outputs staged in them has been read)
 constexpr int kStageCols = 256;  // D1 (128) + D2 (128)
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
+constexpr int kEwThreads = 256;  // two elementwise warpgroups
+// How the two elementwise warpgroups share the work.  true: both sweep every unit, 32 columns each.  false: warpgroup g
+// sweeps all 64 columns of the units with (n & 1) == g.
+#ifndef HS_BWD_COOP
+#define HS_BWD_COOP 0
+#endif
+constexpr bool kCoop = HS_BWD_COOP != 0;
+#ifndef HS_BWD_PREFETCH
+#define HS_BWD_PREFETCH 0
+#endif
+constexpr bool kL2Prefetch = HS_BWD_PREFETCH != 0;  // L2 prefetch of the next unit's tiles by the producer
+constexpr int kSweepCols = kCoop ? kWS / 2 : kWS;  // columns swept by one thread
+constexpr int kSweepers = kCoop ? 2 : 1;           // threads per row
 constexpr int kDbtPitch = 64;   // floats; 16-byte chunk c4 of row r is stored at chunk (c4 ^ (r & 15)): conflict-free float4 RMW
 // Output path of the epilogue.  true: every thread writes its 128-byte output row(s) straight from registers (full
 // cache lines); the slot is released immediately.  false: stage the tiles in the slot and TMA-store them (the slot then
@@ -53,25 +67,28 @@ struct SlotMeta {
   int pad[3];
 };
 
-struct Slot {
+struct KSlot {
   uint8_t qk[2 * kTile];   // [Q;K]  K-major, SWIZZLE_128B
   uint8_t dov[2 * kTile];  // [dO;V] K-major, SWIZZLE_128B
+};
+struct Slot {
   uint8_t q_mn[kTile];     // MN-major (SWIZZLE_128B_ATOM_32B); reused as dQ staging
   uint8_t k_mn[kTile];     //   "                                reused as dK staging
   uint8_t do_mn[kTile];    //   "                                reused as dV staging
 };
 
 struct Smem {
-  Slot slot[kSlots];
+  KSlot kslot[kKS];
+  Slot slot[kMS];
   float bias[kWS * kBiasPitch];     // bias[i][j] * log2(e); query rows read it row-wise (LDS.128), key rows column-wise
-  SlotMeta meta[kSlots];
-  float inv[kSlots][2 * kWS];  // per slot (statistics warps, from the forward): [0,64) 1/max(|q_i|,eps), [64,128) 1/max(|k_j|,eps)
-  float lse[kSlots][kWS];    // per slot (written by the statistics warp): log2-domain log-sum-exp of every query row
-  float delta[kSlots][kWS];  // per slot: rowsum(P o dP) = dO_i . O_i
-  float4 lse4[2][kWS];       // per warpgroup: my row's value replicated 4x (what a query-row thread reads along its columns)
-  float4 delta4[2][kWS];
+  SlotMeta meta[kMS];
+  float inv[kMS][2 * kWS];  // per slot (statistics warps, from the forward): [0,64) 1/max(|q_i|,eps), [64,128) 1/max(|k_j|,eps)
+  float nlse[kMS][kWS];    // per slot (written by the statistics warp): MINUS the log2-domain log-sum-exp of every query row
+  float ndelta[kMS][kWS];  // per slot: MINUS rowsum(P o dP) = -dO_i . O_i
+  float4 part[2][2][2 * kWS];  // per TMEM stage and warpgroup: every row's partial sums (ds_sweep), elementwise -> epilogue warps
   float dbt[2][kWS * kDbtPitch];  // per warpgroup: dbt[i][j] = sum over its units of dS[i][j] (query-row thread i owns row i)
-  uint64_t full[kSlots], empty[kSlots], meta_ready[kSlots], stats_ready[kSlots];
+  uint64_t kfull[kKS], kempty[kKS];
+  uint64_t full[kMS], empty[kMS], meta_ready[kMS], stats_ready[kMS];
   uint64_t s_ready[2], dsn_ready[2], dst_ready[2], o_ready[2], stage_free[2];
   uint32_t tmem_base;
 };
@@ -100,7 +117,7 @@ struct BwdArgs {
 
 #ifdef HS_BWD_TRACE
 // Diagnostics build only (tools/trace_bwd.cu): per-phase clock64 stamps of CTA (0, 0), role x unit x point.
-constexpr int kTraceUnits = 48, kTracePoints = 8, kTraceRoles = 6;  // roles: wg0 nat, wg0 tr, wg1 nat, wg1 tr, mma, producer
+constexpr int kTraceUnits = 48, kTracePoints = 8, kTraceRoles = 8;  // roles: wg0 nat, wg0 tr, wg1 nat, wg1 tr, mma, producer, epilogue nat, epilogue tr
 __device__ long long g_trace[kTraceRoles * kTraceUnits * kTracePoints];
 #define HS_TRACE(role, n, k)                                                               \
   do {                                                                                     \
@@ -113,183 +130,200 @@ __device__ long long g_trace[kTraceRoles * kTraceUnits * kTracePoints];
 
 
 // ---------------------------------------------------------------------------------------------------------------
-// Elementwise stage of one unit.  Written as ROLLED loops over 8-column chunks with everything recomputed from TMEM
-// (no per-row register arrays): the whole hot path is a few hundred instructions and stays resident in the
-// instruction cache -- the fully unrolled first version (4000 instructions, 64 KB) spent half of its issue slots
-// waiting for instruction fetches (profiles/r1d_attn_bwd_tc_*).  TMEM loads are double-buffered: the next chunk is in
-// flight while the current one is used.
+// Elementwise stage of one unit.  A ROLLED loop over 8-column chunks with everything recomputed from TMEM (no per-row
+// register arrays): the fully unrolled first version (4000 instructions, 64 KB) spent half of its issue slots waiting
+// for instruction fetches (profiles/r1d_attn_bwd_tc_*).  TMEM loads are double-buffered: the next chunk is in flight
+// while the current one is used.  The sweep is specialised at compile time on the thread's orientation (query row /
+// key row) and on the attention variant (cos, bias), and does its fp32 arithmetic two columns at a time with the
+// packed FMUL2 / FFMA2 / FADD2 instructions of sm_100: the first version (run-time flags, scalar math) issued 29
+// instructions per element and was bound by the issue slots of the two elementwise warps per scheduler
+// (profiles/r1l_attn_bwd_full_summary.txt: 0.48 IPC, tensor pipe 19 %).
 struct RowCtx {
   uint32_t s_src, dp_src;  // my 64-column block of D1 (S or S^T) and D2 (dP or dP^T), lane field included
+  uint32_t p_dst, ds_dst;  // where P^T (key rows only) and dS / dS^T go (TMEM, lane field included)
   uint32_t oinv, brow;     // shared-memory addresses: normalisation of the other index (cos), my bias row / column
-  uint32_t bstep;          // byte step between consecutive bias entries along my columns (4: row, 4 * pitch: column)
+  uint32_t nlse_v, ndelta_v;  // key rows: shared addresses of the (negated) statistics vectors over the query index
   uint32_t groups;         // shared-memory address of the unit's 64 group ids
+  uint32_t dbt_row;        // query rows: shared address of my row of the dbias tile (0 = none)
+  int dbt_xor;             //   16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 15))
   float row_scale;         // log2(e) * scale (* my 1/|row| for cos) * truncation fix
+  float nlse, ndelta;      // query rows: minus my log-sum-exp / minus my rowsum(P o dP)
+  float fix2;
   int my_group;
-  bool cos, has_bias, masked;
+  bool masked;
   // attention dropout: element (i, j) of the unit; my row is index `drop_r`, columns run over the other index
   uint32_t drop_key, drop_thresh;  // thresh 0 = off
   float drop_scale;
   int drop_r;
-  bool drop_row_is_query;  // query-row thread: (i, j) = (drop_r, c); key-row thread: (i, j) = (c, drop_r); also set without dropout
 };
 
 constexpr int kCW = 8;  // columns per chunk of the elementwise loops (16 was measured slower: 1.44 vs 1.27 ms)
 
-__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[kCW]) {
-  if constexpr (kCW == 8) tmem_ld8(taddr, r); else tmem_ld16(taddr, r);
-}
-__device__ __forceinline__ void tmem_st_chunk(uint32_t taddr, const uint32_t (&r)[kCW]) {
-  if constexpr (kCW == 8) tmem_st8(taddr, r); else tmem_st16(taddr, r);
-}
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2u(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 
-// log2-domain logits of columns [c0, c0 + kCW) from the raw tensor-core products; ov = normalisation of the other index
-__device__ __forceinline__ void logits_chunk(const RowCtx& R, const uint32_t (&raw)[kCW], int c0, float (&x)[kCW],
-                                             float (&ov)[kCW]) {
-  float bv[kCW];
-#pragma unroll
-  for (int q = 0; q < kCW / 4; ++q) {
-    float4 o4 = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (R.cos) o4 = lds_f4(R.oinv + 4 * (c0 + 4 * q));
-    ov[4 * q + 0] = o4.x; ov[4 * q + 1] = o4.y; ov[4 * q + 2] = o4.z; ov[4 * q + 3] = o4.w;
-  }
-  if (R.has_bias) {
-    if (R.bstep == 4) {
-#pragma unroll
-      for (int q = 0; q < kCW / 4; ++q) {
-        const float4 b4 = lds_f4(R.brow + 4 * (c0 + 4 * q));
-        bv[4 * q + 0] = b4.x; bv[4 * q + 1] = b4.y; bv[4 * q + 2] = b4.z; bv[4 * q + 3] = b4.w;
-      }
-    } else {  // key rows: bias[c][r] walks down a column; consecutive lanes hit consecutive banks
-#pragma unroll
-      for (int e = 0; e < kCW; ++e) bv[e] = lds_f1(R.brow + R.bstep * (c0 + e));
-    }
-  } else {
-#pragma unroll
-    for (int e = 0; e < kCW; ++e) bv[e] = 0.f;
-  }
-#pragma unroll
-  for (int e = 0; e < kCW; ++e) x[e] = fmaf(__uint_as_float(raw[e]) * R.row_scale, ov[e], bv[e]);
-  if (R.masked) {
-#pragma unroll
-    for (int q = 0; q < kCW / 4; ++q) {
-      uint32_t g4;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(g4) : "r"(R.groups + c0 + 4 * q) : "memory");
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if ((int)((g4 >> (8 * e)) & 0xff) != R.my_group) x[4 * q + e] += kMaskFill * kLog2e;
-    }
-  }
-}
-
-// all threads: p = exp2(logit - lse), dS = p (dP - delta); P and dS (scaled by the other index' 1/norm for cos) go back
-// to TMEM as TF32 A operands; query-row threads also accumulate dS into their warpgroup's dbias tile.
-// lse_v / delta_v: shared addresses of the statistics seen along my columns, `vstep` = 1 (vectors over the query index,
-// key-row threads) or 0 (my own row's 4-fold copy, query-row threads).  Returns sum_c dS_c * raw_c (for cos).
-// dbt_row: shared address of my row of the dbias tile (0 = none); 16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 15)).
-template <bool kDrop>
-__device__ __forceinline__ float ds_sweep(const RowCtx& R, float fix2, uint32_t lse_v, uint32_t delta_v, uint32_t vstep,
-                                          uint32_t p_dst, uint32_t ds_dst, uint32_t dbt_row, int dbt_xor) {
+// all threads: p = exp2(logit - lse), dS = p (dP - delta); dS (scaled by the other index' 1/norm for cos) goes back to
+// TMEM as the TF32 A operand of dQ (query rows, over S) / dK (key rows, over dP^T); key rows also write P^T (over S^T)
+// for dV; query rows accumulate dS into their warpgroup's dbias tile.  Returns sum_c dS_c * raw_c, centred (cos only).
+template <bool kNat, bool kCos, bool kBias, bool kDrop>
+__device__ __forceinline__ float4 ds_sweep(const RowCtx& R, const int cb) {
   // rs = sum_c dS_c * w_c with w = raw * (1/norm of the other index) (the cos logit up to my row's scale).  In exact
   // arithmetic sum_c dS_c = 0 along a query row, so any constant may be subtracted from w: the P-weighted mean of w is
   // subtracted (sds * pw) so that an error of the row's delta (it now comes from the forward output) is not amplified.
-  float rs[4] = {0.f, 0.f, 0.f, 0.f}, sds[2] = {0.f, 0.f}, pw[2] = {0.f, 0.f};
+  float2 rs[2] = {f2(0.f, 0.f), f2(0.f, 0.f)}, sds = f2(0.f, 0.f), pw = f2(0.f, 0.f);
+  const float2 rsc = f2(R.row_scale, R.row_scale), fx2 = f2(R.fix2, R.fix2);
+  const float2 nl_own = f2(R.nlse, R.nlse), nd_own = f2(R.ndelta, R.ndelta);
   auto chunk = [&](const uint32_t (&sraw)[kCW], const uint32_t (&dpr)[kCW], int c0) {
-    float x[kCW], ov[kCW], lv[kCW], dv[kCW], ds[kCW];
-    logits_chunk(R, sraw, c0, x, ov);
+    float2 raw[4], x[4], ov[4], nl[4], nd[4];
 #pragma unroll
-    for (int q = 0; q < kCW / 4; ++q) {
-      const float4 l4 = lds_f4(lse_v + vstep * (4 * (c0 + 4 * q)));
-      const float4 d4 = lds_f4(delta_v + vstep * (4 * (c0 + 4 * q)));
-      lv[4 * q + 0] = l4.x; lv[4 * q + 1] = l4.y; lv[4 * q + 2] = l4.z; lv[4 * q + 3] = l4.w;
-      dv[4 * q + 0] = d4.x; dv[4 * q + 1] = d4.y; dv[4 * q + 2] = d4.z; dv[4 * q + 3] = d4.w;
+    for (int p = 0; p < 4; ++p) raw[p] = f2u(sraw[2 * p], sraw[2 * p + 1]);
+    if (kCos) {
+      const float4 a4 = lds_f4(R.oinv + 4 * c0), b4 = lds_f4(R.oinv + 4 * c0 + 16);
+      ov[0] = f2(a4.x, a4.y); ov[1] = f2(a4.z, a4.w); ov[2] = f2(b4.x, b4.y); ov[3] = f2(b4.z, b4.w);
     }
-    float4 acc[kCW / 4];
-    if (dbt_row) {  // issue the tile loads early; the row is owned by this thread alone (plain read-modify-write)
+    if (kNat) {
 #pragma unroll
-      for (int q = 0; q < kCW / 4; ++q) acc[q] = lds_f4(dbt_row + 16 * (((c0 >> 2) + q) ^ dbt_xor));
+      for (int p = 0; p < 4; ++p) { nl[p] = nl_own; nd[p] = nd_own; }
+    } else {
+      const float4 a4 = lds_f4(R.nlse_v + 4 * c0), b4 = lds_f4(R.nlse_v + 4 * c0 + 16);
+      const float4 c4 = lds_f4(R.ndelta_v + 4 * c0), d4 = lds_f4(R.ndelta_v + 4 * c0 + 16);
+      nl[0] = f2(a4.x, a4.y); nl[1] = f2(a4.z, a4.w); nl[2] = f2(b4.x, b4.y); nl[3] = f2(b4.z, b4.w);
+      nd[0] = f2(c4.x, c4.y); nd[1] = f2(c4.z, c4.w); nd[2] = f2(d4.x, d4.y); nd[3] = f2(d4.z, d4.w);
+    }
+    // log2-domain logits
+#pragma unroll
+    for (int p = 0; p < 4; ++p) x[p] = __fmul2_rn(raw[p], rsc);
+    if (kBias) {
+      float2 bv[4];
+      if (kNat) {
+        const float4 a4 = lds_f4(R.brow + 4 * c0), b4 = lds_f4(R.brow + 4 * c0 + 16);
+        bv[0] = f2(a4.x, a4.y); bv[1] = f2(a4.z, a4.w); bv[2] = f2(b4.x, b4.y); bv[3] = f2(b4.z, b4.w);
+      } else {  // key rows: bias[c][r] walks down a column; consecutive lanes hit consecutive banks
+        const uint32_t bp = R.brow + 4 * kBiasPitch * c0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          bv[p] = f2(lds_f1(bp + 4 * kBiasPitch * (2 * p)), lds_f1(bp + 4 * kBiasPitch * (2 * p + 1)));
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) x[p] = kCos ? __ffma2_rn(x[p], ov[p], bv[p]) : __fadd2_rn(x[p], bv[p]);
+    } else if (kCos) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) x[p] = __fmul2_rn(x[p], ov[p]);
+    }
+    if (R.masked) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t g4;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(g4) : "r"(R.groups + c0 + 4 * q) : "memory");
+        if ((int)(g4 & 0xff) != R.my_group) x[2 * q].x += kMaskFill * kLog2e;
+        if ((int)((g4 >> 8) & 0xff) != R.my_group) x[2 * q].y += kMaskFill * kLog2e;
+        if ((int)((g4 >> 16) & 0xff) != R.my_group) x[2 * q + 1].x += kMaskFill * kLog2e;
+        if ((int)((g4 >> 24) & 0xff) != R.my_group) x[2 * q + 1].y += kMaskFill * kLog2e;
+      }
+    }
+    float4 acc[2];
+    if (kNat && R.dbt_row) {  // issue the tile loads early; the row is owned by this thread alone (plain read-modify-write)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) acc[q] = lds_f4(R.dbt_row + 16 * (((c0 >> 2) + q) ^ R.dbt_xor));
     }
     uint32_t pa[kCW], ua[kCW];
+    float2 ds[4];
 #pragma unroll
-    for (int e = 0; e < kCW; ++e) {
-      const float pv = ex2_approx(x[e] - lv[e]);
-      float dpe = __uint_as_float(dpr[e]) * fix2, pd = pv;
+    for (int p = 0; p < 4; ++p) {
+      const float2 arg = __fadd2_rn(x[p], nl[p]);
+      const float2 pv = f2(ex2_approx(arg.x), ex2_approx(arg.y));
+      float2 dpe = f2u(dpr[2 * p], dpr[2 * p + 1]);
+      float2 pd = pv;
       if (kDrop) {  // O = dropout(P) V:  dP -> dP o m,  the P fed to dV is P o m   (m = 0 or 1 / (1 - p))
-        const int c = c0 + e;
-        const bool keep = R.drop_row_is_query ? hs::drop_keep(R.drop_key, R.drop_r, c, kWS, R.drop_thresh)
-                                              : hs::drop_keep(R.drop_key, c, R.drop_r, kWS, R.drop_thresh);
-        const float mk = keep ? R.drop_scale : 0.f;
-        dpe *= mk;
-        pd *= mk;
+        const int c = c0 + 2 * p;
+        const bool k0 = kNat ? hs::drop_keep(R.drop_key, R.drop_r, c, kWS, R.drop_thresh)
+                             : hs::drop_keep(R.drop_key, c, R.drop_r, kWS, R.drop_thresh);
+        const bool k1 = kNat ? hs::drop_keep(R.drop_key, R.drop_r, c + 1, kWS, R.drop_thresh)
+                             : hs::drop_keep(R.drop_key, c + 1, R.drop_r, kWS, R.drop_thresh);
+        const float2 mk = f2(k0 ? R.drop_scale : 0.f, k1 ? R.drop_scale : 0.f);
+        dpe = __fmul2_rn(dpe, mk);
+        pd = __fmul2_rn(pd, mk);
       }
-      ds[e] = pv * (dpe - dv[e]);
-      const float u = ds[e] * ov[e];
-      rs[e & 3] = fmaf(u, __uint_as_float(sraw[e]), rs[e & 3]);
-      if (R.cos) {
-        sds[e & 1] += ds[e];
-        pw[e & 1] = fmaf(pv * ov[e], __uint_as_float(sraw[e]), pw[e & 1]);
+      dpe = __ffma2_rn(dpe, fx2, nd[p]);
+      ds[p] = __fmul2_rn(pv, dpe);
+      const float2 u = kCos ? __fmul2_rn(ds[p], ov[p]) : ds[p];
+      if (kCos) {
+        rs[p & 1] = __ffma2_rn(u, raw[p], rs[p & 1]);
+        if (kNat) {
+          sds = __fadd2_rn(sds, ds[p]);
+          pw = __ffma2_rn(__fmul2_rn(pv, ov[p]), raw[p], pw);
+        }
       }
-      pa[e] = __float_as_uint(tf32_rna(pd));
-      ua[e] = __float_as_uint(tf32_rna(u));
+      if (!kNat) {
+        pa[2 * p] = __float_as_uint(tf32_rna(pd.x));
+        pa[2 * p + 1] = __float_as_uint(tf32_rna(pd.y));
+      }
+      ua[2 * p] = __float_as_uint(tf32_rna(u.x));
+      ua[2 * p + 1] = __float_as_uint(tf32_rna(u.y));
     }
     // the chunk of S / dP at these columns has been consumed: overwrite in place
-    tmem_st_chunk(p_dst + c0, pa);
-    tmem_st_chunk(ds_dst + c0, ua);
-    if (dbt_row) {
+    if (!kNat) tmem_st8(R.p_dst + c0, pa);
+    tmem_st8(R.ds_dst + c0, ua);
+    if (kNat && R.dbt_row) {
 #pragma unroll
-      for (int q = 0; q < kCW / 4; ++q) {
-        acc[q].x += ds[4 * q + 0]; acc[q].y += ds[4 * q + 1]; acc[q].z += ds[4 * q + 2]; acc[q].w += ds[4 * q + 3];
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dbt_row + 16 * (((c0 >> 2) + q) ^ dbt_xor)),
-                     "f"(acc[q].x), "f"(acc[q].y), "f"(acc[q].z), "f"(acc[q].w)
+      for (int q = 0; q < 2; ++q) {
+        const float2 lo = __fadd2_rn(f2(acc[q].x, acc[q].y), ds[2 * q]), hi = __fadd2_rn(f2(acc[q].z, acc[q].w), ds[2 * q + 1]);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(R.dbt_row + 16 * (((c0 >> 2) + q) ^ R.dbt_xor)),
+                     "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y)
                      : "memory");
       }
     }
   };
   uint32_t sa[kCW], da[kCW], sb[kCW], db[kCW];
-  tmem_ld_chunk(R.s_src, sa);
-  tmem_ld_chunk(R.dp_src, da);
+  tmem_ld8(R.s_src + cb, sa);
+  tmem_ld8(R.dp_src + cb, da);
 #pragma unroll 1
-  for (int c0 = 0; c0 < kWS; c0 += 2 * kCW) {
+  for (int c0 = cb; c0 < cb + kSweepCols; c0 += 2 * kCW) {  // my warpgroup's share of the columns
     tmem_wait_ld();
-    tmem_ld_chunk(R.s_src + c0 + kCW, sb);
-    tmem_ld_chunk(R.dp_src + c0 + kCW, db);
+    tmem_ld8(R.s_src + c0 + kCW, sb);
+    tmem_ld8(R.dp_src + c0 + kCW, db);
     chunk(sa, da, c0);
     tmem_wait_ld();
-    if (c0 + 2 * kCW < kWS) {
-      tmem_ld_chunk(R.s_src + c0 + 2 * kCW, sa);
-      tmem_ld_chunk(R.dp_src + c0 + 2 * kCW, da);
+    if (c0 + 2 * kCW < cb + kSweepCols) {
+      tmem_ld8(R.s_src + c0 + 2 * kCW, sa);
+      tmem_ld8(R.dp_src + c0 + 2 * kCW, da);
     }
     chunk(sb, db, c0 + kCW);
   }
   tmem_wait_st();
-  // (only along a query row: the column sums of dS seen by the key-row threads do not vanish)
-  const float centre = R.drop_row_is_query ? (sds[0] + sds[1]) * (pw[0] + pw[1]) : 0.f;
-  return (rs[0] + rs[1]) + (rs[2] + rs[3]) - centre;
+  // partial sums over my columns: (sum dS w, sum dS, sum P w); the epilogue adds the two halves of the row and centres
+  return make_float4((rs[0].x + rs[0].y) + (rs[1].x + rs[1].y), sds.x + sds.y, pw.x + pw.y, 0.f);
 }
 
-template <bool kDrop>
+template <bool kDrop, bool kCos, bool kBias>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_constant__ CUtensorMap map_qkv_mn,
                    const __grid_constant__ CUtensorMap map_do_k, const __grid_constant__ CUtensorMap map_do_mn,
-                   const __grid_constant__ CUtensorMap map_dqkv, const BwdArgs a) {
+                   const __grid_constant__ CUtensorMap map_dqkv, const __grid_constant__ CUtensorMap map_out,
+                   const BwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y;
-  const bool has_bias = a.bias != nullptr;
+  constexpr bool has_bias = kBias;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) {
+    for (int i = 0; i < kKS; ++i) {
+      mbar_init(&S.kfull[i], 2);
+      mbar_init(&S.kempty[i], 128 * kSweepers);  // the unit's elementwise threads: scores done, statistics done
+    }
+    for (int i = 0; i < kMS; ++i) {
       mbar_init(&S.full[i], 2);
-      mbar_init(&S.empty[i], 128);
+      mbar_init(&S.empty[i], 128);  // the epilogue threads
       mbar_init(&S.meta_ready[i], 1);
       mbar_init(&S.stats_ready[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&S.s_ready[i], 1);
-      mbar_init(&S.dsn_ready[i], 64);  // dS of the 64 query rows is in TMEM   -> dQ
-      mbar_init(&S.dst_ready[i], 64);  // P^T, dS^T of the 64 key rows           -> dV, dK
+      mbar_init(&S.dsn_ready[i], 64 * kSweepers);  // dS of the 64 query rows is in TMEM   -> dQ
+      mbar_init(&S.dst_ready[i], 64 * kSweepers);  // P^T, dS^T of the 64 key rows           -> dV, dK
       mbar_init(&S.o_ready[i], 1);
-      mbar_init(&S.stage_free[i], 128);
+      mbar_init(&S.stage_free[i], 128);  // the epilogue threads, once the outputs are in their registers
     }
     mbar_fence_init();
   }
@@ -300,6 +334,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     tma_prefetch_desc(&map_do_k);
     tma_prefetch_desc(&map_do_mn);
     tma_prefetch_desc(&map_dqkv);
+    tma_prefetch_desc(&map_out);
   }
   for (int idx = threadIdx.x; idx < 2 * kWS * kDbtPitch; idx += kThreads) (&S.dbt[0][0])[idx] = 0.f;
   if (has_bias) {
@@ -315,21 +350,146 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
 
-  if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 168;");
+  // register file: 2 x 128 x 152 (elementwise) + 128 x 104 (producer / MMA / statistics) + 128 x 104 (epilogue) = 64 K
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ================================================================= epilogue warps: one TMEM lane quadrant each (warps 12, 13:
+    // query rows -> dQ; warps 14, 15: key rows -> dK, dV), every unit of both TMEM stages.  The elementwise warpgroups
+    // never wait for the output MMAs: they hand the row sums over through S.rs and go on with their next unit.
+    const int q4 = warp - 12;
+    const int L = q4 * 32 + lane;  // TMEM lane
+    const bool nat = L < kWS;
+    const int r = L & 63;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int half_bar = nat ? 5 : 6;  // named barrier of the 64 threads of this half
+    const float eff = kCos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale;
+    bool store_pending = false;
+    float racc = 0.f;  // running sum of dS o (logits without bias / mask): d logit_scale
+    int n = 0;
+    for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
+      const int slot = n % kMS, t = n & 1;
+      const uint32_t ph = (uint32_t)(n >> 1) & 1;
+      [[maybe_unused]] const int trole = nat ? 6 : 7;  // trace role (diagnostics build only)
+      if (r == 0) HS_TRACE(trole, n, 0);
+      mbar_wait(&S.full[slot], (uint32_t)(n / kMS) & 1);  // (long complete: makes the row table visible)
+      const SlotMeta& M = S.meta[slot];
+      Slot& T = S.slot[slot];
+      const int flags = M.flags;
+      const int my_row = M.rows[r];
+      const uint32_t D1 = tmem + (uint32_t)t * kStageCols + lane_addr, D2 = D1 + 128;
+      mbar_wait(nat ? &S.dsn_ready[t] : &S.dst_ready[t], ph);  // my half's sweep is done: S.rs is valid
+      const float my_inv = S.inv[slot][L];
+      float rs = 0.f;  // sum_c dS[r][c] * (eff * cos(r, c))   (cos attention only)
+      if (kCos) {
+        const float4 p0 = S.part[t][0][L], p1 = kCoop ? S.part[t][1][L] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // (the centring applies along a query row only: the column sums of dS seen by the key rows do not vanish)
+        const float centre = nat ? (p0.y + p1.y) * (p0.z + p1.z) : 0.f;
+        rs = ((p0.x + p1.x) - centre) * (eff * my_inv * a.fix2);
+        if (nat) racc += rs;
+      }
+      mbar_wait(&S.o_ready[t], ph);
+      if (r == 0) HS_TRACE(trole, n, 1);
+      tc_fence_after();
+      uint32_t acc0[kD], acc1[kD];
+      if (nat) {
+        tmem_ld32(D2 + 64, acc0);  // dQ
+      } else {
+        tmem_ld32(D1 + 64, acc0);  // dK
+        tmem_ld32(D2 + 96, acc1);  // dV
+      }
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&S.stage_free[t]);
+      if (r == 0) HS_TRACE(trole, n, 2);
+
+      // through the scaling / F.normalize:  d row = g * acc - row * corr
+      const float g = eff * my_inv * a.fix1;  // dS (rounded) x k / q (truncated)
+      const bool clamped = my_inv >= 1.0f / kNormEps;
+      const float corr = (kCos && !clamped) ? my_inv * my_inv * rs : 0.f;
+      const int row0 = M.rows[0];
+      const bool contig = !kDirectStore && (flags & kFlagContig) != 0;
+      uint8_t* st0 = (nat ? T.q_mn : T.k_mn) + r * 128;
+      uint8_t* st1 = T.do_mn + r * 128;
+      float* g0 = a.dqkv + (long long)my_row * 3 * a.C + (nat ? 0 : a.C) + h * kD;
+      const float2 g2 = f2(g, g), nc2 = f2(-corr, -corr), f12 = f2(a.fix1, a.fix1);
+      if (kCos) {
+        // my own row of q / k comes from the MN-major copy (the K-major tiles are long recycled); the staged output row
+        // goes to the same 128 bytes in another chunk order: read the whole row before the first write
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 x4 = *reinterpret_cast<const float4*>(st0 - r * 128 + sw128b32_off(r, c));
+          const float2 lo = __ffma2_rn(f2(x4.x, x4.y), nc2, __fmul2_rn(f2u(acc0[4 * c + 0], acc0[4 * c + 1]), g2));
+          const float2 hi = __ffma2_rn(f2(x4.z, x4.w), nc2, __fmul2_rn(f2u(acc0[4 * c + 2], acc0[4 * c + 3]), g2));
+          acc0[4 * c + 0] = __float_as_uint(lo.x); acc0[4 * c + 1] = __float_as_uint(lo.y);
+          acc0[4 * c + 2] = __float_as_uint(hi.x); acc0[4 * c + 3] = __float_as_uint(hi.y);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float2 lo = __fmul2_rn(f2u(acc0[4 * c + 0], acc0[4 * c + 1]), g2);
+          const float2 hi = __fmul2_rn(f2u(acc0[4 * c + 2], acc0[4 * c + 3]), g2);
+          acc0[4 * c + 0] = __float_as_uint(lo.x); acc0[4 * c + 1] = __float_as_uint(lo.y);
+          acc0[4 * c + 2] = __float_as_uint(hi.x); acc0[4 * c + 3] = __float_as_uint(hi.y);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 v4 = make_float4(__uint_as_float(acc0[4 * c + 0]), __uint_as_float(acc0[4 * c + 1]),
+                                      __uint_as_float(acc0[4 * c + 2]), __uint_as_float(acc0[4 * c + 3]));
+        if (contig)
+          *reinterpret_cast<float4*>(st0 + ((c ^ (r & 7)) << 4)) = v4;
+        else
+          reinterpret_cast<float4*>(g0)[c] = v4;
+      }
+      if (!nat) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float2 lo = __fmul2_rn(f2u(acc1[4 * c + 0], acc1[4 * c + 1]), f12);  // P^T (rounded) x dO (truncated)
+          const float2 hi = __fmul2_rn(f2u(acc1[4 * c + 2], acc1[4 * c + 3]), f12);
+          const float4 v4 = make_float4(lo.x, lo.y, hi.x, hi.y);
+          if (contig)
+            *reinterpret_cast<float4*>(st1 + ((c ^ (r & 7)) << 4)) = v4;
+          else
+            reinterpret_cast<float4*>(g0 + a.C)[c] = v4;
+        }
+      }
+      if (contig) {
+        fence_proxy_async_smem();
+        named_bar_sync(half_bar, 64);
+        if (r == 0) {
+          if (nat) {
+            tma_store_2d(&map_dqkv, T.q_mn, h * kD, row0);
+          } else {
+            tma_store_2d(&map_dqkv, T.k_mn, a.C + h * kD, row0);
+            tma_store_2d(&map_dqkv, T.do_mn, 2 * a.C + h * kD, row0);
+          }
+          tma_store_commit();
+          store_pending = true;
+          if (r == 0) HS_TRACE(trole, n, 3);
+          tma_store_wait_read<0>();  // the staging tiles live in the slot: it is free once the TMA engine has read them
+        }
+      }
+      mbar_arrive(&S.empty[slot]);
+      if (r == 0) HS_TRACE(trole, n, 4);
+    }
+    if (store_pending) tma_store_wait<0>();
+    if (nat && kCos && a.dlogit) {
+      // d logit_scale = sum dS o logits_cos, zero where the clamp is active (torch.clamp backward)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
+      if (lane == 0 && __ldg(a.logit_scale + h) <= kLogitScaleMax) atomicAdd(a.dlogit + h, racc);
+    }
+  } else if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
     if (warp == 8) {
       // ================================================================= load producer
-      int n = 0;
-      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
-        const int slot = n % kSlots;
-        const uint32_t use = (uint32_t)(n / kSlots);
-        mbar_wait(&S.empty[slot], (use & 1) ^ 1);
-        if (lane == 0) HS_TRACE(5, n, 0);
-        SlotMeta& M = S.meta[slot];
-        Slot& T = S.slot[slot];
-        const int b = unit / a.nW, w = unit - b * a.nW;
+      // The row table of a unit (two global loads per lane) is fetched one unit ahead, and as soon as it is known the
+      // unit's tiles are prefetched into L2: the TMA loads proper are issued only when ring entries free up, two units
+      // ahead of their use, which alone does not cover the HBM latency under load (profiles/r2z_attn_bwd_*).
+      auto fetch_rows = [&](int u, int& r0, int& r1, int& g0, int& g1) {
+        const int w = u % a.nW;
         const long long s0 = (long long)w * kWS;
-        int r0, r1, g0 = 0, g1 = 0;
+        g0 = g1 = 0;
         if (a.src) {
           r0 = a.src[s0 + lane];
           r1 = a.src[s0 + 32 + lane];
@@ -341,6 +501,33 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           g0 = a.groups[s0 + lane];
           g1 = a.groups[s0 + 32 + lane];
         }
+      };
+      int nr0 = 0, nr1 = 0, ng0 = 0, ng1 = 0;
+      if ((int)blockIdx.x < a.total) fetch_rows(blockIdx.x, nr0, nr1, ng0, ng1);
+      int n = 0;
+      for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
+        const int slot = n % kMS, ks = n % kKS;
+        const int r0 = nr0, r1 = nr1, g0 = ng0, g1 = ng1;
+        const int unit_next = unit + (int)gridDim.x;
+        if (unit_next < a.total) {
+          fetch_rows(unit_next, nr0, nr1, ng0, ng1);
+          const int nb = __shfl_sync(0xffffffffu, nr0, 0);
+          if (kL2Prefetch && __all_sync(0xffffffffu, (nr0 == nb + lane) && (nr1 == nb + 32 + lane)) && elect_one()) {
+            const int row = (int)((long long)(unit_next / a.nW) * a.N) + nb;
+            tma_prefetch_l2_2d(&map_qkv_k, h * kD, row);
+            tma_prefetch_l2_2d(&map_qkv_k, a.C + h * kD, row);
+            tma_prefetch_l2_2d(&map_qkv_k, 2 * a.C + h * kD, row);
+            tma_prefetch_l2_2d(&map_do_k, h * kD, row);
+            tma_prefetch_l2_2d(&map_out, h * kD, row);
+          }
+        }
+        mbar_wait(&S.kempty[ks], ((uint32_t)(n / kKS) & 1) ^ 1);
+        mbar_wait(&S.empty[slot], ((uint32_t)(n / kMS) & 1) ^ 1);
+        if (lane == 0) HS_TRACE(5, n, 0);
+        SlotMeta& M = S.meta[slot];
+        Slot& T = S.slot[slot];
+        KSlot& TK = S.kslot[ks];
+        const int b = unit / a.nW;
         const int rbase = __shfl_sync(0xffffffffu, r0, 0);
         const int gbase = __shfl_sync(0xffffffffu, g0, 0);
         const bool contig = __all_sync(0xffffffffu, (r0 == rbase + lane) && (r1 == rbase + 32 + lane));
@@ -354,13 +541,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.meta_ready[slot]);  // the statistics warps can start (they read rows[] only)
         if (elect_one()) {
-          mbar_arrive_expect_tx(&S.full[slot], contig ? 7u * kTile : 0u);
+          mbar_arrive_expect_tx(&S.kfull[ks], contig ? 4u * kTile : 0u);
+          mbar_arrive_expect_tx(&S.full[slot], contig ? 3u * kTile : 0u);
           if (contig) {
             const int row = goff + rbase;
-            tma_load_2d(T.qk, &map_qkv_k, &S.full[slot], h * kD, row);
-            tma_load_2d(T.qk + kTile, &map_qkv_k, &S.full[slot], a.C + h * kD, row);
-            tma_load_2d(T.dov, &map_do_k, &S.full[slot], h * kD, row);
-            tma_load_2d(T.dov + kTile, &map_qkv_k, &S.full[slot], 2 * a.C + h * kD, row);
+            tma_load_2d(TK.qk, &map_qkv_k, &S.kfull[ks], h * kD, row);
+            tma_load_2d(TK.qk + kTile, &map_qkv_k, &S.kfull[ks], a.C + h * kD, row);
+            tma_load_2d(TK.dov, &map_do_k, &S.kfull[ks], h * kD, row);
+            tma_load_2d(TK.dov + kTile, &map_qkv_k, &S.kfull[ks], 2 * a.C + h * kD, row);
             tma_load_2d(T.q_mn, &map_qkv_mn, &S.full[slot], h * kD, row);
             tma_load_2d(T.k_mn, &map_qkv_mn, &S.full[slot], a.C + h * kD, row);
             tma_load_2d(T.do_mn, &map_do_mn, &S.full[slot], h * kD, row);
@@ -376,10 +564,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
             const float* g = a.qkv + grow * 3 * a.C + h * kD + c16 * 4;
             const float* gd = a.dout + grow * a.C + h * kD + c16 * 4;
             const uint32_t ok = sw128_off(r, c16), om = sw128b32_off(r, c16);
-            cp_async16(T.qk + ok, g);
-            cp_async16(T.qk + kTile + ok, g + a.C);
-            cp_async16(T.dov + ok, gd);
-            cp_async16(T.dov + kTile + ok, g + 2 * a.C);
+            cp_async16(TK.qk + ok, g);
+            cp_async16(TK.qk + kTile + ok, g + a.C);
+            cp_async16(TK.dov + ok, gd);
+            cp_async16(TK.dov + kTile + ok, g + 2 * a.C);
             cp_async16(T.q_mn + om, g);
             cp_async16(T.k_mn + om, g + a.C);
             cp_async16(T.do_mn + om, gd);
@@ -388,7 +576,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           fence_proxy_async_smem();
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&S.full[slot]);  // arrival 2 of 2 (publishes the metadata too)
+        if (lane == 0) {  // arrival 2 of 2 (publishes the metadata too)
+          mbar_arrive(&S.kfull[ks]);
+          mbar_arrive(&S.full[slot]);
+        }
         if (lane == 0) HS_TRACE(5, n, 1);
       }
     } else if (warp == 9 && elect_one()) {
@@ -408,13 +599,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       while (no < units) {
         bool progressed = false;
         if (ns < units) {
-          const int slot = ns % kSlots, t = ns & 1;
-          if (mbar_test_wait(&S.full[slot], (uint32_t)(ns / kSlots) & 1) &&
+          const int ks = ns % kKS, t = ns & 1;
+          if (mbar_test_wait(&S.kfull[ks], (uint32_t)(ns / kKS) & 1) &&
               mbar_test_wait(&S.stage_free[t], ((uint32_t)(ns >> 1) & 1) ^ 1)) {
             HS_TRACE(4, ns, 0);
             tc_fence_after();
             const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
-            const uint32_t qk = smem_u32(S.slot[slot].qk), dov = smem_u32(S.slot[slot].dov);
+            const uint32_t qk = smem_u32(S.kslot[ks].qk), dov = smem_u32(S.kslot[ks].dov);
 #pragma unroll
             for (int s = 0; s < 4; ++s)  // [Q;K] [Q;K]^T : lanes 0-63 x cols 64-127 = S, lanes 64-127 x cols 0-63 = S^T
               umma_tf32_ss(D1, umma_desc_at(kDescK, qk + s * 32), umma_desc_at(kDescK, qk + s * 32), kIdescS, s > 0);
@@ -428,11 +619,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           }
         }
         if (no < ns) {
-          const int t = no & 1, slot = no % kSlots;
+          const int t = no & 1, slot = no % kMS;
           const uint32_t ph = (uint32_t)(no >> 1) & 1;
           const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
           const Slot& T = S.slot[slot];
-          if (ophase == 0 && mbar_test_wait(&S.dsn_ready[t], ph)) {
+          if (ophase == 0 && mbar_test_wait(&S.dsn_ready[t], ph) && mbar_test_wait(&S.full[slot], (uint32_t)(no / kMS) & 1)) {
             HS_TRACE(4, no, 2);
             tc_fence_after();
             const uint32_t kb = smem_u32(T.k_mn);
@@ -476,219 +667,116 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       int n = 0;
       for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
         if ((n & 1) != (warp & 1)) continue;
-        const int slot = n % kSlots;
-        mbar_wait(&S.meta_ready[slot], (uint32_t)(n / kSlots) & 1);
+        const int slot = n % kMS, ks = n % kKS;
+        mbar_wait(&S.meta_ready[slot], (uint32_t)(n / kMS) & 1);
         const SlotMeta& M = S.meta[slot];
-        float4 o[2][8], d[2][8];
+        float4 o[2][8];
         float lse[2], qi[2] = {1.f, 1.f}, ki[2] = {1.f, 1.f};
         const long long plane = (long long)a.H * ((long long)a.B * a.N);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const long long row = M.rows[lane + 32 * k];
           const float4* orow = reinterpret_cast<const float4*>(a.out + row * a.C + h * kD);
-          const float4* drow = reinterpret_cast<const float4*>(a.dout + row * a.C + h * kD);
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            o[k][c] = __ldg(orow + c);
-            d[k][c] = __ldg(drow + c);
-          }
+          for (int c = 0; c < 8; ++c) o[k][c] = __ldg(orow + c);
           lse[k] = __ldg(a.lse + (long long)h * ((long long)a.B * a.N) + row);
-          if (a.cos) {
+          if (kCos) {
             qi[k] = __ldg(a.lse + plane + (long long)h * ((long long)a.B * a.N) + row);
             ki[k] = __ldg(a.lse + 2 * plane + (long long)h * ((long long)a.B * a.N) + row);
           }
         }
+        // dO comes from the slot's K-major tile (rows 0-63 of [dO;V]) once the loads have landed
+        mbar_wait(&S.kfull[ks], (uint32_t)(n / kKS) & 1);
+        const uint8_t* dtile = S.kslot[ks].dov;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          float dot = 0.f;
+          const int rr = lane + 32 * k;
+          float2 dot = f2(0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            dot += (o[k][c].x * d[k][c].x + o[k][c].y * d[k][c].y) + (o[k][c].z * d[k][c].z + o[k][c].w * d[k][c].w);
-          S.lse[slot][lane + 32 * k] = lse[k];
-          S.delta[slot][lane + 32 * k] = dot;
-          S.inv[slot][lane + 32 * k] = qi[k];
-          S.inv[slot][kWS + lane + 32 * k] = ki[k];
+          for (int c = 0; c < 8; ++c) {
+            const float4 d4 = *reinterpret_cast<const float4*>(dtile + sw128_off(rr, c));
+            dot = __ffma2_rn(f2(o[k][c].x, o[k][c].y), f2(d4.x, d4.y), dot);
+            dot = __ffma2_rn(f2(o[k][c].z, o[k][c].w), f2(d4.z, d4.w), dot);
+          }
+          S.nlse[slot][rr] = -lse[k];
+          S.ndelta[slot][rr] = -(dot.x + dot.y);
+          S.inv[slot][rr] = qi[k];
+          S.inv[slot][kWS + rr] = ki[k];
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.stats_ready[slot]);
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    // ================================================================= elementwise + epilogue warpgroups
-    const int wg = warp >> 2;              // handles units n with (n & 1) == wg, TMEM stage wg
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+    // ================================================================= elementwise warpgroups
+    const int wg = warp >> 2;              // see kCoop
     const int L = (warp & 3) * 32 + lane;  // TMEM lane
     const bool nat = L < kWS;              // warps 0,1: query rows; warps 2,3: key rows
     const int r = L & 63;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t D1 = tmem + (uint32_t)wg * kStageCols + lane_addr, D2 = D1 + 128;
-    const int half_bar = 5 + wg * 2 + (nat ? 0 : 1);  // named barrier of the 64 threads of this half
-
-    float racc = 0.f;  // running sum of dS o (logits without bias / mask): d logit_scale
-    const float eff = a.cos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale;
-    bool store_pending = false;
-    int pending_slot = -1;  // store-issuing threads (r == 0): slot whose staging tiles a TMA store may still be reading
-
+    const float eff = kCos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale;
     int n = 0;
     for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
-      if ((n & 1) != wg) continue;
-      const int slot = n % kSlots;
+      if (!kCoop && (n & 1) != wg) continue;
+      const int slot = n % kMS, ks = n % kKS, t = n & 1;
       const uint32_t it = (uint32_t)(n >> 1) & 1;
-      if (pending_slot >= 0) {  // the staging tiles of my previous unit live in its slot: free it once they are read
-        tma_store_wait_read<0>();
-        mbar_arrive(&S.empty[pending_slot]);
-        pending_slot = -1;
-      }
-      mbar_wait(&S.full[slot], (uint32_t)(n / kSlots) & 1);
+      const uint32_t D1 = tmem + (uint32_t)t * kStageCols + lane_addr, D2 = D1 + 128;
+      mbar_wait(&S.kfull[ks], (uint32_t)(n / kKS) & 1);  // (makes the unit's metadata visible as well)
       [[maybe_unused]] const int trole = wg * 2 + (nat ? 0 : 1);  // trace role (diagnostics build only)
       if (r == 0) HS_TRACE(trole, n, 0);
 
       const SlotMeta& M = S.meta[slot];
-      Slot& T = S.slot[slot];
       const int flags = M.flags;
-      const uint8_t* myrow = T.qk + L * 128;  // row L of [Q;K]: q_r for the query half, k_r for the key half
-
-      const int my_row = M.rows[r];
       if (r == 0) HS_TRACE(trole, n, 6);
-      mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kSlots) & 1);  // lse / delta / norms of this unit (statistics warps)
+      mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kMS) & 1);  // lse / delta / norms of this unit (statistics warps)
       if (r == 0) HS_TRACE(trole, n, 7);
       const float my_inv = S.inv[slot][L];  // 1/|q_r| (query rows) or 1/|k_r| (key rows); 1 without cos attention
-      if (nat) {
-        const float lse = S.lse[slot][r], dl = S.delta[slot][r];
-        S.lse4[wg][r] = make_float4(lse, lse, lse, lse);
-        S.delta4[wg][r] = make_float4(dl, dl, dl, dl);
-      }
       const float row_scale = eff * kLog2e * my_inv * a.fix2;  // S = q k^T has two truncated operands
 
-      mbar_wait(&S.s_ready[wg], it);
+      mbar_wait(&S.s_ready[t], it);
+      mbar_arrive(&S.kempty[ks]);  // score MMAs and statistics are done with the K-major tiles
       if (r == 0) HS_TRACE(trole, n, 1);
       tc_fence_after();
       RowCtx R;
       R.s_src = D1 + (nat ? 64u : 0u);   // S (query rows) / S^T (key rows)
       R.dp_src = D2 + (nat ? 64u : 0u);  // dP / dP^T
+      R.p_dst = D1;                      // P^T over S^T (key rows)
+      R.ds_dst = nat ? D1 + 64 : D2;     // dS over S / dS^T over dP^T
       R.oinv = smem_u32(S.inv[slot] + (nat ? kWS : 0));
       R.brow = smem_u32(S.bias + (nat ? r * kBiasPitch : r));
-      R.bstep = nat ? 4u : 4u * kBiasPitch;
+      R.nlse_v = smem_u32(S.nlse[slot]);
+      R.ndelta_v = smem_u32(S.ndelta[slot]);
+      R.nlse = S.nlse[slot][r];
+      R.ndelta = S.ndelta[slot][r];
       R.groups = smem_u32(M.groups);
+      R.dbt_row = (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u;
+      R.dbt_xor = r & 15;
       R.row_scale = row_scale;
+      R.fix2 = a.fix2;
       R.my_group = M.groups[r];
-      R.cos = a.cos != 0;
-      R.has_bias = has_bias;
       R.masked = !(flags & kFlagUniform);
       R.drop_thresh = a.drop_thresh;
       R.drop_scale = a.drop_scale;
       R.drop_key = a.drop_thresh ? hs::drop_unit_key(a.seed, unit, h, a.H) : 0u;
       R.drop_r = r;
-      R.drop_row_is_query = nat;
-      const uint32_t lse_v = smem_u32(nat ? (const void*)&S.lse4[wg][r] : (const void*)S.lse[slot]);
-      const uint32_t delta_v = smem_u32(nat ? (const void*)&S.delta4[wg][r] : (const void*)S.delta[slot]);
-      const uint32_t vstep = nat ? 0u : 1u;
-      // P^T over S^T for the key rows (the query rows write P into a dead block); dS over S / dS^T over dP^T
-      float rs = ds_sweep<kDrop>(R, a.fix2, lse_v, delta_v, vstep, D1, nat ? D1 + 64 : D2,
-                          (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u, r & 15);
-      rs *= row_scale;  // sum_c dS[r][c] * log2(e) * (eff * cos(r, c))
+      const int cb = kCoop ? 32 * wg : 0;
+      const float4 part = nat ? ds_sweep<true, kCos, kBias, kDrop>(R, cb) : ds_sweep<false, kCos, kBias, kDrop>(R, cb);
+      if (kCos) S.part[t][kCoop ? wg : 0][L] = part;  // for the epilogue warps (ordered by the arrive below)
       tc_fence_before();
-      mbar_arrive(nat ? &S.dsn_ready[wg] : &S.dst_ready[wg]);
+      mbar_arrive(nat ? &S.dsn_ready[t] : &S.dst_ready[t]);
       if (r == 0) HS_TRACE(trole, n, 2);
-      rs *= (1.0f / kLog2e);  // sum_c dS[r][c] * (eff * cos(r, c))   (meaningful for cos attention only)
-      if (nat) racc += rs;
-
-      mbar_wait(&S.o_ready[wg], it);
-      if (r == 0) HS_TRACE(trole, n, 3);
-      tc_fence_after();
-      uint32_t acc0[kD], acc1[kD];
-      if (nat) {
-        tmem_ld32(D2 + 64, acc0);  // dQ
-      } else {
-        tmem_ld32(D1 + 64, acc0);  // dK
-        tmem_ld32(D2 + 96, acc1);  // dV
-      }
-      tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(&S.stage_free[wg]);
-      if (r == 0) HS_TRACE(trole, n, 4);
-
-      // through the scaling / F.normalize:  d row = g * acc - row * corr
-      const float g = eff * my_inv * a.fix1;  // dS (rounded) x k / q (truncated)
-      const bool clamped = my_inv >= 1.0f / kNormEps;
-      const float corr = (a.cos && !clamped) ? my_inv * my_inv * rs : 0.f;
-      const int row0 = M.rows[0];
-      const bool contig = !kDirectStore && (flags & kFlagContig) != 0;
-      uint8_t* st0 = (nat ? T.q_mn : T.k_mn) + r * 128;
-      uint8_t* st1 = T.do_mn + r * 128;
-      float* g0 = a.dqkv + (long long)my_row * 3 * a.C + (nat ? 0 : a.C) + h * kD;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 v4;
-        v4.x = __uint_as_float(acc0[4 * c + 0]) * g;
-        v4.y = __uint_as_float(acc0[4 * c + 1]) * g;
-        v4.z = __uint_as_float(acc0[4 * c + 2]) * g;
-        v4.w = __uint_as_float(acc0[4 * c + 3]) * g;
-        if (a.cos) {
-          const float4 x4 = *reinterpret_cast<const float4*>(myrow + ((c ^ (r & 7)) << 4));
-          v4.x = fmaf(-x4.x, corr, v4.x);
-          v4.y = fmaf(-x4.y, corr, v4.y);
-          v4.z = fmaf(-x4.z, corr, v4.z);
-          v4.w = fmaf(-x4.w, corr, v4.w);
-        }
-        if (contig)
-          *reinterpret_cast<float4*>(st0 + ((c ^ (r & 7)) << 4)) = v4;
-        else
-          reinterpret_cast<float4*>(g0)[c] = v4;
-      }
-      if (!nat) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 v4;
-          v4.x = __uint_as_float(acc1[4 * c + 0]) * a.fix1;  // P^T (rounded) x dO (truncated)
-          v4.y = __uint_as_float(acc1[4 * c + 1]) * a.fix1;
-          v4.z = __uint_as_float(acc1[4 * c + 2]) * a.fix1;
-          v4.w = __uint_as_float(acc1[4 * c + 3]) * a.fix1;
-          if (contig)
-            *reinterpret_cast<float4*>(st1 + ((c ^ (r & 7)) << 4)) = v4;
-          else
-            reinterpret_cast<float4*>(g0 + a.C)[c] = v4;
-        }
-      }
-      if (contig) {
-        fence_proxy_async_smem();
-        named_bar_sync(half_bar, 64);
-        if (r == 0) {
-          if (nat) {
-            tma_store_2d(&map_dqkv, T.q_mn, h * kD, row0);
-          } else {
-            tma_store_2d(&map_dqkv, T.k_mn, a.C + h * kD, row0);
-            tma_store_2d(&map_dqkv, T.do_mn, 2 * a.C + h * kD, row0);
-          }
-          tma_store_commit();
-          store_pending = true;
-          pending_slot = slot;  // released at the top of this thread's next unit, once the TMA engine has read it
-        }
-      }
-      if (pending_slot != slot) mbar_arrive(&S.empty[slot]);
-      if (r == 0) HS_TRACE(trole, n, 5);
     }
-    if (pending_slot >= 0) {
-      tma_store_wait_read<0>();
-      mbar_arrive(&S.empty[pending_slot]);
-    }
-    if (store_pending) tma_store_wait<0>();
 
     if (a.dbias) {
       // both warpgroups accumulated into the same tile: wait for all 8 elementwise warps, then one atomic per entry
-      named_bar_sync(9, 256);
+      named_bar_sync(9, kEwThreads);
       float* gb = a.dbias + (long long)h * kWS * kWS;
-      for (int idx = threadIdx.x; idx < kWS * kWS; idx += 256) {
+      for (int idx = threadIdx.x; idx < kWS * kWS; idx += kEwThreads) {
         const int i = idx >> 6, j = idx & 63;
         const int pos = i * kDbtPitch + 4 * ((j >> 2) ^ (i & 15)) + (j & 3);
         atomicAdd(gb + idx, S.dbt[0][pos] + S.dbt[1][pos]);
       }
-    }
-    if (nat && a.cos && a.dlogit) {
-      // d logit_scale = sum dS o logits_cos, zero where the clamp is active (torch.clamp backward)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
-      if (lane == 0 && __ldg(a.logit_scale + h) <= kLogitScaleMax) atomicAdd(a.dlogit + h, racc);
     }
   }
 
@@ -707,7 +795,7 @@ int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, con
                        cudaStream_t stream) {
   HS_REQUIRE(qkv && dout && dqkv && out && lse, "hs_window_attn_bwd: null qkv/out/lse/dout/dqkv");
   HS_REQUIRE(!(flags & HS_ATTN_COS) || logit_scale, "hs_window_attn_bwd: cos attention needs logit_scale");
-  CUtensorMap map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv;
+  CUtensorMap map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, map_out;
   const long long rows = (long long)B * N;
   int rc;
   if ((rc = make_map(&map_qkv_k, qkv, rows, 3 * C, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
@@ -715,6 +803,7 @@ int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, con
   if ((rc = make_map(&map_do_k, dout, rows, C, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_map(&map_do_mn, dout, rows, C, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))) return rc;
   if ((rc = make_map(&map_dqkv, dqkv, rows, 3 * C, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_map(&map_out, out, rows, C, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;  // (L2 prefetch only)
   BwdArgs a{};
   a.qkv = qkv; a.out = out; a.lse = lse; a.dout = dout; a.dqkv = dqkv; a.src = src; a.groups = groups; a.bias = bias;
   a.logit_scale = logit_scale; a.dbias = dbias; a.dlogit = dlogit; a.scale = scale;
@@ -726,20 +815,25 @@ int window_attn_bwd_tc(const float* qkv, const float* out, const float* lse, con
   a.drop_scale = 1.0f / (1.0f - drop.p);
   a.seed = drop.seed;
   const size_t smem = sizeof(Smem) + 1024;
-  static bool attr_done = false;  // benign race: the attribute is idempotent
-  if (!attr_done) {
-    HS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HS_CUDA(cudaFuncSetAttribute(attn_bwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
   int gx = sm_count() / H;
   if (gx < 1) gx = 1;
   if (gx > a.total) gx = a.total;
-  dim3 grid(gx, H);
-  if (a.drop_thresh)
-    attn_bwd_tc_kernel<true><<<grid, kThreads, smem, stream>>>(map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, a);
-  else
-    attn_bwd_tc_kernel<false><<<grid, kThreads, smem, stream>>>(map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, a);
+  const dim3 grid(gx, H);
+  // one instantiation per (dropout, cos, bias): the variant flags are compile-time constants of the elementwise sweep
+  using Kernel = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                          const CUtensorMap, const BwdArgs);
+  static const Kernel table[8] = {
+      attn_bwd_tc_kernel<false, false, false>, attn_bwd_tc_kernel<false, false, true>,
+      attn_bwd_tc_kernel<false, true, false>,  attn_bwd_tc_kernel<false, true, true>,
+      attn_bwd_tc_kernel<true, false, false>,  attn_bwd_tc_kernel<true, false, true>,
+      attn_bwd_tc_kernel<true, true, false>,   attn_bwd_tc_kernel<true, true, true>};
+  static bool attr_done = false;  // benign race: the attribute is idempotent (and per function, not per device)
+  if (!attr_done) {
+    for (Kernel k : table) HS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const Kernel kern = table[(a.drop_thresh ? 4 : 0) + (a.cos ? 2 : 0) + (bias ? 1 : 0)];
+  kern<<<grid, kThreads, smem, stream>>>(map_qkv_k, map_qkv_mn, map_do_k, map_do_mn, map_dqkv, map_out, a);
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

@@ -35,44 +35,53 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     printf("run %d rc=%d err=%s %.3f ms\n", it, rc, cudaGetErrorString(err), ms);
   }
+#ifdef HS_BWD_TRACE
   static long long tr[kTraceRoles * kTraceUnits * kTracePoints];
   cudaMemcpyFromSymbol(tr, g_trace, sizeof(tr));
   auto at = [&](int role, int n, int k) { return tr[(role * kTraceUnits + n) * kTracePoints + k]; };
   const long long t0 = at(5, 0, 0);
-  const char* names[6] = {"wg0.nat", "wg0.tr ", "wg1.nat", "wg1.tr ", "mma    ", "prod   "};
-  printf("cycles relative to the producer's first stamp; softmax points: full, s_ready, ds_arrive, o_ready, tmem_ld(stage_free), done\n");
+  const char* names[8] = {"wg0.nat", "wg0.tr ", "wg1.nat", "wg1.tr ", "mma    ", "prod   ", "epi.nat", "epi.tr "};
+  printf("cycles relative to the producer's first stamp; elementwise points: full, s_ready, ds_arrive\n");
   printf("mma points: [0] waits done, [1] scores issued, [2] ds_ready(n), [3] x_ready(n), [4] dK issued; prod: [0] slot free, [1] issued\n");
+  printf("epilogue points: loop top, o_ready, tmem_ld done (stage_free), store issued, slot released\n");
   for (int n = 16; n < 28; ++n) {
-    for (int role = 0; role < 6; ++role) {
-      if (role < 4 && (n & 1) != (role >> 1)) continue;
+    for (int role = 0; role < 8; ++role) {
+      if (!kCoop && role < 4 && (n & 1) != (role >> 1)) continue;
       printf("unit %2d %s:", n, names[role]);
-      const int np = role < 4 ? 6 : (role == 4 ? 5 : 2);
+      const int np = role < 4 ? 3 : (role == 4 ? 5 : (role == 5 ? 2 : 5));
       for (int k = 0; k < np; ++k) printf(" %8lld", at(role, n, k) - t0);
       printf("\n");
     }
   }
   // average per-phase durations over units 8..47
-  double d[6][8] = {};
-  int cnt[6] = {};
-  for (int n = 8; n < kTraceUnits; ++n)
-    for (int role = 0; role < 4; ++role) {
-      if ((n & 1) != (role >> 1)) continue;
-      for (int k = 0; k < 5; ++k) d[role][k] += (double)(at(role, n, k + 1) - at(role, n, k));
-      if (n + 2 < kTraceUnits) d[role][5] += (double)(at(role, n + 2, 0) - at(role, n, 5));
-      cnt[role]++;
-    }
-  for (int role = 0; role < 4; ++role)
-    printf("%s avg cycles: wait_s %.0f | elementwise %.0f | wait_o %.0f | tmem_ld %.0f | epilogue %.0f | to next full %.0f\n", names[role],
-           d[role][0] / cnt[role], d[role][1] / cnt[role], d[role][2] / cnt[role], d[role][3] / cnt[role], d[role][4] / cnt[role], d[role][5] / cnt[role]);
   {
-    double w6 = 0, w7 = 0, w1 = 0; int c = 0;
-    for (int n = 8; n < kTraceUnits; ++n) {
-      const int role = (n & 1) * 2;  // query-row thread 0 of the unit's warpgroup
-      w6 += (double)(at(role, n, 6) - at(role, n, 0)); w7 += (double)(at(role, n, 7) - at(role, n, 6));
-      w1 += (double)(at(role, n, 1) - at(role, n, 7)); ++c;
-    }
-    printf("wait_s split (query rows): norms+barrier %.0f | stats_ready wait %.0f | s_ready wait %.0f\n", w6 / c, w7 / c, w1 / c);
+    double d[4][4] = {};
+    int cnt[4] = {};
+    const int step = kCoop ? 1 : 2;
+    for (int n = 8; n + step < kTraceUnits; ++n)
+      for (int role = 0; role < 4; ++role) {
+        if (!kCoop && (n & 1) != (role >> 1)) continue;
+        d[role][0] += (double)(at(role, n, 7) - at(role, n, 0));      // statistics wait
+        d[role][1] += (double)(at(role, n, 1) - at(role, n, 7));      // s_ready wait
+        d[role][2] += (double)(at(role, n, 2) - at(role, n, 1));      // sweep
+        d[role][3] += (double)(at(role, n + step, 0) - at(role, n, 2));  // to the next unit's full
+        cnt[role]++;
+      }
+    for (int role = 0; role < 4; ++role)
+      printf("%s avg cycles: stats wait %.0f | s_ready wait %.0f | sweep %.0f | to next full %.0f\n", names[role],
+             d[role][0] / cnt[role], d[role][1] / cnt[role], d[role][2] / cnt[role], d[role][3] / cnt[role]);
+    double e[2][5] = {};
+    int c = 0;
+    for (int n = 8; n + 1 < kTraceUnits; ++n, ++c)
+      for (int role = 6; role < 8; ++role) {
+        for (int k = 0; k < 4; ++k) e[role - 6][k] += (double)(at(role, n, k + 1) - at(role, n, k));
+        e[role - 6][4] += (double)(at(role, n + 1, 0) - at(role, n, 4));
+      }
+    for (int role = 0; role < 2; ++role)
+      printf("%s avg cycles: wait o_ready %.0f | tmem_ld %.0f | math+stage+store %.0f | store read %.0f | loop %.0f\n", names[6 + role],
+             e[role][0] / c, e[role][1] / c, e[role][2] / c, e[role][3] / c, e[role][4] / c);
   }
-  printf("unit period (cycles): %.0f\n", (double)(at(0, 46, 0) - at(0, 8, 0)) / 38.0);
+  printf("unit period (cycles): %.0f\n", (double)(at(6, 46, 0) - at(6, 8, 0)) / 38.0);
+#endif
   return 0;
 }
