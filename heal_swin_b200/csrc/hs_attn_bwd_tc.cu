@@ -18,11 +18,23 @@
 // MN-major B tiles (K, dO, Q) produce dQ, dV, dK into dead column blocks (see the MMA issuer for the exact map).
 //
 // Every input tile is needed K-major (scores) and, except V, MN-major (outputs): they are fetched twice by TMA with the
-// two swizzles (the second fetch hits L2).  HBM traffic per unit: q, k, v, dO in; dq, dk, dv out = 7 x 8 KB.
+// two swizzles (the second fetch hits L2).  HBM traffic per unit: q, k, v, dO in; dq, dk, dv out = 7 x 8 KB (+ the 8 KB
+// of the forward output read by the statistics warps).
 //
-// Warp roles (384 threads): warps 0-3 / 4-7 = two elementwise warpgroups (unit n -> group n & 1, TMEM stage n & 1),
-// warp 8 = load producer, warp 9 = MMA issuer, warps 10-11 = row statistics (from the forward's lse and output).  3 shared-memory slots of 56 KB; the output tiles are staged in the
-// slot's (dead) MN-major tiles and written back by TMA.
+// Warp roles (512 threads, register file split with setmaxnreg 152 / 104 / 104):
+//   warps 0-3 / 4-7   two elementwise warpgroups: unit n -> group n & 1, TMEM stage n & 1.  They only sweep: wait for the
+//                     scores, write dS / P^T / dS^T back to TMEM, hand the row sums to the epilogue warps (S.part) and go
+//                     on with their next unit.
+//   warp 8            load producer (row table one unit ahead; TMA loads, or cp.async gathers for shifted windows)
+//   warp 9            MMA issuer (one elected thread, polling)
+//   warps 10-11       row statistics (-lse from the forward, -delta = -dO . O with dO read from the K-major tile)
+//   warps 12-15       epilogue: one TMEM lane quadrant each; scale / F.normalize correction, staging in the unit's (dead)
+//                     MN-major tiles, TMA store, slot release.
+// Shared memory: a ring of 2 K-major entries (32 KB: [Q;K], [dO;V]; dead as soon as the score MMAs are done) and a ring of 4
+// MN-major entries (24 KB: q, k, dO; B operands of the output MMAs, then output staging until the TMA store has read
+// them).  With one ring of 3 x 56 KB the long-lived MN tiles limited the units in flight to 3 and the whole chain
+// load -> scores -> sweep -> output MMAs -> epilogue -> store ran at one unit per 4.3 k cycles; see DESIGN.md section 3
+// for the measurements that led here (profiles/r2z_attn_bwd_*).
 #include <cfloat>
 
 #include "hs_common.h"
@@ -51,6 +63,11 @@ constexpr bool kCoop = HS_BWD_COOP != 0;
 #define HS_BWD_PREFETCH 0
 #endif
 constexpr bool kL2Prefetch = HS_BWD_PREFETCH != 0;  // L2 prefetch of the next unit's tiles by the producer
+// Which half accumulates the dbias tile.  With cos attention the query-row sweep is the heavier one (row sums for the
+// F.normalize / logit_scale terms), so the key-row threads take the tile (held transposed, dbt[j][i]); without, the
+// query-row threads do (measured on one box, stage 0: cos 1.47 -> 1.40 ms, plain 1.01 -> 1.05 ms the other way round;
+// splitting the tile between the halves by 32 x 32 quadrant was slower than either: 1.54 / 1.08 ms).
+__host__ __device__ constexpr bool dbt_on_key_rows(bool cos) { return cos; }
 constexpr int kSweepCols = kCoop ? kWS / 2 : kWS;  // columns swept by one thread
 constexpr int kSweepers = kCoop ? 2 : 1;           // threads per row
 constexpr int kDbtPitch = 64;   // floats; 16-byte chunk c4 of row r is stored at chunk (c4 ^ (r & 15)): conflict-free float4 RMW
@@ -144,7 +161,7 @@ struct RowCtx {
   uint32_t oinv, brow;     // shared-memory addresses: normalisation of the other index (cos), my bias row / column
   uint32_t nlse_v, ndelta_v;  // key rows: shared addresses of the (negated) statistics vectors over the query index
   uint32_t groups;         // shared-memory address of the unit's 64 group ids
-  uint32_t dbt_row;        // query rows: shared address of my row of the dbias tile (0 = none)
+  uint32_t dbt_row;        // shared address of my row of the dbias tile (0 = none / the other half accumulates it)
   int dbt_xor;             //   16-byte chunk c4 of row r lives at chunk (c4 ^ (r & 15))
   float row_scale;         // log2(e) * scale (* my 1/|row| for cos) * truncation fix
   float nlse, ndelta;      // query rows: minus my log-sum-exp / minus my rowsum(P o dP)
@@ -222,7 +239,7 @@ __device__ __forceinline__ float4 ds_sweep(const RowCtx& R, const int cb) {
       }
     }
     float4 acc[2];
-    if (kNat && R.dbt_row) {  // issue the tile loads early; the row is owned by this thread alone (plain read-modify-write)
+    if (kNat != dbt_on_key_rows(kCos) && R.dbt_row) {  // issue the tile loads early; the row is owned by this thread alone (plain read-modify-write)
 #pragma unroll
       for (int q = 0; q < 2; ++q) acc[q] = lds_f4(R.dbt_row + 16 * (((c0 >> 2) + q) ^ R.dbt_xor));
     }
@@ -264,7 +281,7 @@ __device__ __forceinline__ float4 ds_sweep(const RowCtx& R, const int cb) {
     // the chunk of S / dP at these columns has been consumed: overwrite in place
     if (!kNat) tmem_st8(R.p_dst + c0, pa);
     tmem_st8(R.ds_dst + c0, ua);
-    if (kNat && R.dbt_row) {
+    if (kNat != dbt_on_key_rows(kCos) && R.dbt_row) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         const float2 lo = __fadd2_rn(f2(acc[q].x, acc[q].y), ds[2 * q]), hi = __fadd2_rn(f2(acc[q].z, acc[q].w), ds[2 * q + 1]);
@@ -750,7 +767,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       R.nlse = S.nlse[slot][r];
       R.ndelta = S.ndelta[slot][r];
       R.groups = smem_u32(M.groups);
-      R.dbt_row = (nat && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u;
+      R.dbt_row = (nat != dbt_on_key_rows(kCos) && a.dbias) ? smem_u32(S.dbt[wg] + r * kDbtPitch) : 0u;
       R.dbt_xor = r & 15;
       R.row_scale = row_scale;
       R.fix2 = a.fix2;
@@ -774,7 +791,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       float* gb = a.dbias + (long long)h * kWS * kWS;
       for (int idx = threadIdx.x; idx < kWS * kWS; idx += kEwThreads) {
         const int i = idx >> 6, j = idx & 63;
-        const int pos = i * kDbtPitch + 4 * ((j >> 2) ^ (i & 15)) + (j & 3);
+        const int tr = dbt_on_key_rows(kCos) ? j : i, tc = dbt_on_key_rows(kCos) ? i : j;  // tile row (owner thread) / column
+        const int pos = tr * kDbtPitch + 4 * ((tc >> 2) ^ (tr & 15)) + (tc & 3);
         atomicAdd(gb + idx, S.dbt[0][pos] + S.dbt[1][pos]);
       }
     }
