@@ -68,6 +68,14 @@ constexpr bool kL2Prefetch = HS_BWD_PREFETCH != 0;  // L2 prefetch of the next u
 // query-row threads do (measured on one box, stage 0: cos 1.47 -> 1.40 ms, plain 1.01 -> 1.05 ms the other way round;
 // splitting the tile between the halves by 32 x 32 quadrant was slower than either: 1.54 / 1.08 ms).
 __host__ __device__ constexpr bool dbt_on_key_rows(bool cos) { return cos; }
+// Mirrored stacking on TMEM stage 1: its units are computed as [K;Q] [K;Q]^T and [V;dO] [V;dO]^T, so the key-row
+// orientation sits on lanes 0-63 and the query rows on lanes 64-127 -- every TMEM column offset of the unmirrored map
+// XOR 64.  A TMEM lane quadrant is tied to a warp (id % 4) and thereby to a scheduler; without the mirror the two
+// heavier roles (key-row sweep, dK + dV epilogue) always ran on schedulers 2-3.
+#ifndef HS_BWD_MIRROR
+#define HS_BWD_MIRROR 1
+#endif
+constexpr bool kMirror = !kCoop && HS_BWD_MIRROR != 0;
 constexpr int kSweepCols = kCoop ? kWS / 2 : kWS;  // columns swept by one thread
 constexpr int kSweepers = kCoop ? 2 : 1;           // threads per row
 constexpr int kDbtPitch = 64;   // floats; 16-byte chunk c4 of row r is stored at chunk (c4 ^ (r & 15)): conflict-free float4 RMW
@@ -375,10 +383,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     // never wait for the output MMAs: they hand the row sums over through S.rs and go on with their next unit.
     const int q4 = warp - 12;
     const int L = q4 * 32 + lane;  // TMEM lane
-    const bool nat = L < kWS;
+    const bool lower = L < kWS;
     const int r = L & 63;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    const int half_bar = nat ? 5 : 6;  // named barrier of the 64 threads of this half
     const float eff = kCos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale;
     bool store_pending = false;
     float racc = 0.f;  // running sum of dS o (logits without bias / mask): d logit_scale
@@ -386,6 +393,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     for (int unit = blockIdx.x; unit < a.total; unit += gridDim.x, ++n) {
       const int slot = n % kMS, t = n & 1;
       const uint32_t ph = (uint32_t)(n >> 1) & 1;
+      const bool mirror = kMirror && t == 1;
+      const uint32_t sx = mirror ? 64u : 0u;  // XOR of the TMEM column offsets
+      const bool nat = lower != mirror;       // query rows (-> dQ) or key rows (-> dK, dV)
+      const int half_bar = nat ? 5 : 6;       // named barrier of the 64 threads of this half
       [[maybe_unused]] const int trole = nat ? 6 : 7;  // trace role (diagnostics build only)
       if (r == 0) HS_TRACE(trole, n, 0);
       mbar_wait(&S.full[slot], (uint32_t)(n / kMS) & 1);  // (long complete: makes the row table visible)
@@ -395,7 +406,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       const int my_row = M.rows[r];
       const uint32_t D1 = tmem + (uint32_t)t * kStageCols + lane_addr, D2 = D1 + 128;
       mbar_wait(nat ? &S.dsn_ready[t] : &S.dst_ready[t], ph);  // my half's sweep is done: S.rs is valid
-      const float my_inv = S.inv[slot][L];
+      const float my_inv = S.inv[slot][nat ? r : kWS + r];
       float rs = 0.f;  // sum_c dS[r][c] * (eff * cos(r, c))   (cos attention only)
       if (kCos) {
         const float4 p0 = S.part[t][0][L], p1 = kCoop ? S.part[t][1][L] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -409,10 +420,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       tc_fence_after();
       uint32_t acc0[kD], acc1[kD];
       if (nat) {
-        tmem_ld32(D2 + 64, acc0);  // dQ
+        tmem_ld32(D2 + (64u ^ sx), acc0);  // dQ
       } else {
-        tmem_ld32(D1 + 64, acc0);  // dK
-        tmem_ld32(D2 + 96, acc1);  // dV
+        tmem_ld32(D1 + (64u ^ sx), acc0);  // dK
+        tmem_ld32(D2 + (96u ^ sx), acc1);  // dV
       }
       tmem_wait_ld();
       tc_fence_before();
@@ -490,7 +501,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       if (r == 0) HS_TRACE(trole, n, 4);
     }
     if (store_pending) tma_store_wait<0>();
-    if (nat && kCos && a.dlogit) {
+    if (kCos && a.dlogit) {  // (every epilogue thread owned query rows in some units)
       // d logit_scale = sum dS o logits_cos, zero where the clamp is active (torch.clamp backward)
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) racc += __shfl_xor_sync(0xffffffffu, racc, o);
@@ -544,6 +555,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         SlotMeta& M = S.meta[slot];
         Slot& T = S.slot[slot];
         KSlot& TK = S.kslot[ks];
+        const int qoff = (kMirror && (n & 1)) ? kTile : 0, koff = kTile - qoff;  // [Q;K], [dO;V] or mirrored [K;Q], [V;dO]
         const int b = unit / a.nW;
         const int rbase = __shfl_sync(0xffffffffu, r0, 0);
         const int gbase = __shfl_sync(0xffffffffu, g0, 0);
@@ -562,10 +574,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           mbar_arrive_expect_tx(&S.full[slot], contig ? 3u * kTile : 0u);
           if (contig) {
             const int row = goff + rbase;
-            tma_load_2d(TK.qk, &map_qkv_k, &S.kfull[ks], h * kD, row);
-            tma_load_2d(TK.qk + kTile, &map_qkv_k, &S.kfull[ks], a.C + h * kD, row);
-            tma_load_2d(TK.dov, &map_do_k, &S.kfull[ks], h * kD, row);
-            tma_load_2d(TK.dov + kTile, &map_qkv_k, &S.kfull[ks], 2 * a.C + h * kD, row);
+            tma_load_2d(TK.qk + qoff, &map_qkv_k, &S.kfull[ks], h * kD, row);
+            tma_load_2d(TK.qk + koff, &map_qkv_k, &S.kfull[ks], a.C + h * kD, row);
+            tma_load_2d(TK.dov + qoff, &map_do_k, &S.kfull[ks], h * kD, row);
+            tma_load_2d(TK.dov + koff, &map_qkv_k, &S.kfull[ks], 2 * a.C + h * kD, row);
             tma_load_2d(T.q_mn, &map_qkv_mn, &S.full[slot], h * kD, row);
             tma_load_2d(T.k_mn, &map_qkv_mn, &S.full[slot], a.C + h * kD, row);
             tma_load_2d(T.do_mn, &map_do_mn, &S.full[slot], h * kD, row);
@@ -581,10 +593,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
             const float* g = a.qkv + grow * 3 * a.C + h * kD + c16 * 4;
             const float* gd = a.dout + grow * a.C + h * kD + c16 * 4;
             const uint32_t ok = sw128_off(r, c16), om = sw128b32_off(r, c16);
-            cp_async16(TK.qk + ok, g);
-            cp_async16(TK.qk + kTile + ok, g + a.C);
-            cp_async16(TK.dov + ok, gd);
-            cp_async16(TK.dov + kTile + ok, g + 2 * a.C);
+            cp_async16(TK.qk + qoff + ok, g);
+            cp_async16(TK.qk + koff + ok, g + a.C);
+            cp_async16(TK.dov + qoff + ok, gd);
+            cp_async16(TK.dov + koff + ok, g + 2 * a.C);
             cp_async16(T.q_mn + om, g);
             cp_async16(T.k_mn + om, g + a.C);
             cp_async16(T.do_mn + om, gd);
@@ -640,13 +652,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
           const uint32_t ph = (uint32_t)(no >> 1) & 1;
           const uint32_t D1 = tmem + (uint32_t)t * kStageCols, D2 = D1 + 128;
           const Slot& T = S.slot[slot];
+          const uint32_t sx = (kMirror && t == 1) ? 64u : 0u;  // mirrored stage: every column offset XOR 64
           if (ophase == 0 && mbar_test_wait(&S.dsn_ready[t], ph) && mbar_test_wait(&S.full[slot], (uint32_t)(no / kMS) & 1)) {
             HS_TRACE(4, no, 2);
             tc_fence_after();
             const uint32_t kb = smem_u32(T.k_mn);
 #pragma unroll
             for (int s = 0; s < 8; ++s)  // dQ = dS k            A: D1[:, 64:128)  ->  D2[:, 64:96)
-              umma_tf32_ts(D2 + 64, D1 + 64 + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
+              umma_tf32_ts(D2 + (64u ^ sx), D1 + (64u ^ sx) + s * 8, umma_desc_at(kDescMN, kb + s * 1024), kIdescO, s > 0);
             ophase = 1;
             progressed = true;
           }
@@ -655,12 +668,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
             const uint32_t db = smem_u32(T.do_mn), qb = smem_u32(T.q_mn);
 #pragma unroll
             for (int s = 0; s < 8; ++s)  // dV = P^T dO          A: D1[:, 0:64)    ->  D2[:, 96:128)
-              umma_tf32_ts(D2 + 96, D1 + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
+              umma_tf32_ts(D2 + (96u ^ sx), D1 + sx + s * 8, umma_desc_at(kDescMN, db + s * 1024), kIdescO, s > 0);
             HS_TRACE(4, no, 3);
             // dK overwrites the dS block that dQ has read: tcgen05.mma instructions of one thread execute in issue order
 #pragma unroll
             for (int s = 0; s < 8; ++s)  // dK = dS^T q          A: D2[:, 0:64)    ->  D1[:, 64:96)
-              umma_tf32_ts(D1 + 64, D2 + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
+              umma_tf32_ts(D1 + (64u ^ sx), D2 + sx + s * 8, umma_desc_at(kDescMN, qb + s * 1024), kIdescO, s > 0);
             umma_commit(&S.o_ready[t]);
             HS_TRACE(4, no, 4);
             ophase = 0;
@@ -704,7 +717,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
         }
         // dO comes from the slot's K-major tile (rows 0-63 of [dO;V]) once the loads have landed
         mbar_wait(&S.kfull[ks], (uint32_t)(n / kKS) & 1);
-        const uint8_t* dtile = S.kslot[ks].dov;
+        const uint8_t* dtile = S.kslot[ks].dov + ((kMirror && (n & 1)) ? kTile : 0);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int rr = lane + 32 * k;
@@ -729,7 +742,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
     // ================================================================= elementwise warpgroups
     const int wg = warp >> 2;              // see kCoop
     const int L = (warp & 3) * 32 + lane;  // TMEM lane
-    const bool nat = L < kWS;              // warps 0,1: query rows; warps 2,3: key rows
+    const bool lower = L < kWS;
+    const bool nat = lower != (kMirror && wg == 1);  // query rows or key rows (mirrored on stage 1 = warpgroup 1)
     const int r = L & 63;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const float eff = kCos ? __expf(fminf(__ldg(a.logit_scale + h), kLogitScaleMax)) : a.scale;
@@ -748,7 +762,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       if (r == 0) HS_TRACE(trole, n, 6);
       mbar_wait(&S.stats_ready[slot], (uint32_t)(n / kMS) & 1);  // lse / delta / norms of this unit (statistics warps)
       if (r == 0) HS_TRACE(trole, n, 7);
-      const float my_inv = S.inv[slot][L];  // 1/|q_r| (query rows) or 1/|k_r| (key rows); 1 without cos attention
+      const float my_inv = S.inv[slot][nat ? r : kWS + r];  // 1/|q_r| (query rows) or 1/|k_r| (key rows); 1 without cos attention
       const float row_scale = eff * kLog2e * my_inv * a.fix2;  // S = q k^T has two truncated operands
 
       mbar_wait(&S.s_ready[t], it);
@@ -756,10 +770,10 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       if (r == 0) HS_TRACE(trole, n, 1);
       tc_fence_after();
       RowCtx R;
-      R.s_src = D1 + (nat ? 64u : 0u);   // S (query rows) / S^T (key rows)
-      R.dp_src = D2 + (nat ? 64u : 0u);  // dP / dP^T
-      R.p_dst = D1;                      // P^T over S^T (key rows)
-      R.ds_dst = nat ? D1 + 64 : D2;     // dS over S / dS^T over dP^T
+      R.s_src = D1 + (lower ? 64u : 0u);   // S (query rows) / S^T (key rows): lanes 0-63 x cols 64-127, lanes 64-127 x cols 0-63
+      R.dp_src = D2 + (lower ? 64u : 0u);  // dP / dP^T
+      R.p_dst = R.s_src;                   // P^T over S^T (key rows)
+      R.ds_dst = nat ? R.s_src : R.dp_src; // dS over S / dS^T over dP^T
       R.oinv = smem_u32(S.inv[slot] + (nat ? kWS : 0));
       R.brow = smem_u32(S.bias + (nat ? r * kBiasPitch : r));
       R.nlse_v = smem_u32(S.nlse[slot]);
