@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhealswin_b200.so")
+# (HEALSWIN_B200_LIB: another build of the same library, for same-box A/B runs of build variants)
+LIB_PATH = os.environ.get("HEALSWIN_B200_LIB") or os.path.join(_HERE, "libhealswin_b200.so")
 
 HS_OK, HS_ERR_ARG, HS_ERR_CUDA, HS_ERR_UNSUPPORTED = 0, 1, 2, 3
 SHIFT_NONE, SHIFT_NEST_ROLL, SHIFT_NEST_GRID, SHIFT_RING = 0, 1, 2, 3

@@ -71,9 +71,12 @@ __host__ __device__ constexpr bool dbt_on_key_rows(bool cos) { return cos; }
 // Mirrored stacking on TMEM stage 1: its units are computed as [K;Q] [K;Q]^T and [V;dO] [V;dO]^T, so the key-row
 // orientation sits on lanes 0-63 and the query rows on lanes 64-127 -- every TMEM column offset of the unmirrored map
 // XOR 64.  A TMEM lane quadrant is tied to a warp (id % 4) and thereby to a scheduler; without the mirror the two
-// heavier roles (key-row sweep, dK + dV epilogue) always ran on schedulers 2-3.
+// heavier roles (key-row sweep, dK + dV epilogue) always run on schedulers 2-3.  Stand-alone (random data, stage 0) the
+// mirror is 2-4 % faster; inside the training step (22 launches, four stage shapes, shifted blocks with gathered and
+// masked windows) it measured 15.2-15.5 ms against 14.0-14.2 ms without, same box, alternating runs
+// (profiles/r2z_attn_bwd_variants.log) -- so it is off.
 #ifndef HS_BWD_MIRROR
-#define HS_BWD_MIRROR 1
+#define HS_BWD_MIRROR 0
 #endif
 constexpr bool kMirror = !kCoop && HS_BWD_MIRROR != 0;
 constexpr int kSweepCols = kCoop ? kWS / 2 : kWS;  // columns swept by one thread
@@ -396,7 +399,9 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap map_qkv_k, const __grid_c
       const bool mirror = kMirror && t == 1;
       const uint32_t sx = mirror ? 64u : 0u;  // XOR of the TMEM column offsets
       const bool nat = lower != mirror;       // query rows (-> dQ) or key rows (-> dK, dV)
-      const int half_bar = nat ? 5 : 6;       // named barrier of the 64 threads of this half
+      // named barrier of the 64 threads of this half: by LANE half, not by role -- with the mirror the roles alternate per
+      // unit, and a barrier id per role would pair a warp of one unit with a warp of the next
+      const int half_bar = lower ? 5 : 6;
       [[maybe_unused]] const int trole = nat ? 6 : 7;  // trace role (diagnostics build only)
       if (r == 0) HS_TRACE(trole, n, 0);
       mbar_wait(&S.full[slot], (uint32_t)(n / kMS) & 1);  // (long complete: makes the row table visible)

@@ -70,6 +70,7 @@ struct G3Args {
   int ss;       // 1: the A operand stays in shared memory (TF32: as delivered; bf16: split in place), 256-column stages
   int stage_cols;  // TMEM columns per accumulator stage: 192 (+ 4 A slots of 32 columns) or 256 (ss)
   int cluster;  // CTAs per cluster (1, 2 or 4): streamed W slices are loaded once per cluster and multicast
+  int pair;     // 1: the two CTAs of a cluster run cta_group::2 MMAs (M = 256; each holds half of the W slice); ss modes only
   int ring, rw, resident, wring;  // A ring depth, staging regions per epilogue warp, W resident?, W ring depth
   uint32_t drop_thresh;
   float drop_scale;
@@ -120,8 +121,12 @@ __device__ __forceinline__ void split2(float e0, float e1, uint32_t& hi, uint32_
   lo = cvt_bf16x2(e1 - h1, e0 - h0);
 }
 
-template <int E, int MODE>
-__global__ void __launch_bounds__((E + kCvtWarps + 3) * 32, 1)
+// threads per CTA: E epilogue warps, 8 converters, A producer, MMA issuer, W producer (+ the W forwarder of a pair)
+template <int E, bool PAIR>
+constexpr int block_threads() { return (E + kCvtWarps + 3 + (PAIR ? 1 : 0)) * 32; }
+
+template <int E, int MODE, bool PAIR>
+__global__ void __launch_bounds__(block_threads<E, PAIR>(), 1)
 gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
              const __grid_constant__ CUtensorMap map_aux, const __grid_constant__ CUtensorMap map_d,
              const __grid_constant__ CUtensorMap map_d2, const G3Args a) {
@@ -132,12 +137,13 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int nk = (a.K + 31) / 32;              // K chunks (TMA zero-fills the tail of a ragged last chunk)
-  const int w_slice = a.n_box * 128;           // bytes of one K slice of the W chunk
+  constexpr bool pair = PAIR;  // (a kernel that contains cta_group::2 instructions can only be launched as a cluster)
+  const int w_slice = (pair ? a.n_box / 2 : a.n_box) * 128;  // bytes of one K slice of the W chunk (pair: this CTA's half)
   uint8_t* s_w = sm;                           // resident: nk slices; streamed: a ring of wring slices
   uint8_t* s_ring = s_w + (a.resident ? nk : a.wring) * w_slice;
   uint8_t* s_buf = s_ring + a.ring * kChunk;   // E warps x rw regions of 4 KB
   float* s_colsum = reinterpret_cast<float*>(s_buf + E * a.rw * kRegion);  // nk * 32 floats (chunk-0 CTAs with a.colsum)
-  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], slot_empty[kMaxRing], cvt_full[kMaxRing],
+  __shared__ uint64_t w_full, wr_full[kMaxWRing], wr_full2[kMaxWRing], wr_empty[kMaxWRing], raw_full[kMaxRing], slot_empty[kMaxRing], cvt_full[kMaxRing],
       a_full[kASlots], a_empty[kASlots], acc_full[2], acc_empty[2], aux_full[E * kMaxRw];
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -159,7 +165,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     mbar_init(&w_full, 1);
     for (int i = 0; i < kMaxWRing; ++i) {
       mbar_init(&wr_full[i], 1);
-      mbar_init(&wr_empty[i], cs);  // released by the MMA issuers of all CTAs of the cluster (multicast commit)
+      mbar_init(&wr_full2[i], 1);   // pair, leader: the peer's half of the slice has landed (remote arrive)
+      // released by the MMA issuers of all CTAs of the cluster (multicast commit); pair: by the leader's commit alone
+      mbar_init(&wr_empty[i], pair ? 1 : cs);
     }
     for (int i = 0; i < kMaxRing; ++i) {
       mbar_init(&raw_full[i], 1);
@@ -172,17 +180,21 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       mbar_init(&a_full[i], kTeam);
       mbar_init(&a_empty[i], 1);
     }
-    for (int i = 0; i < kMaxRing; ++i) mbar_init(&cvt_full[i], kTeam);  // ss bf16: the chunk is split in place
+    // ss bf16: the chunk is split in place.  pair: the LEADER's barrier collects both CTAs' chunks (TF32: one forwarder each)
+    for (int i = 0; i < kMaxRing; ++i) mbar_init(&cvt_full[i], pair ? 2 * (a.prec == PREC_TF32 ? 1 : kTeam) : kTeam);
     {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], E * 32);
+      mbar_init(&acc_empty[i], pair ? 2 * E : E * 32);  // pair: one arrive per epilogue warp of both CTAs, on the leader
     }
     for (int i = 0; i < E * kMaxRw; ++i) mbar_init(&aux_full[i], 1);
     mbar_fence_init();
   }
-  if (warp == E + kCvtWarps + 1) tmem_alloc(&tmem_base, 512);
+  if (warp == E + kCvtWarps + 1) {
+    if (pair) tmem_alloc_pair(&tmem_base, 512);
+    else tmem_alloc(&tmem_base, 512);
+  }
   if (warp == E + kCvtWarps && lane == 0) tma_prefetch_desc(&map_a);
   if (warp == E + kCvtWarps + 2 && lane == 0) tma_prefetch_desc(&map_w);
   if (warp == 0 && lane == 0) {
@@ -225,7 +237,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           for (int kc = 0; kc < nk; ++kc) {
             mbar_wait(&wr_empty[ws], wph ^ 1);
             mbar_arrive_expect_tx(&wr_full[ws], (uint32_t)w_slice);
-            if (cs > 1)
+            if (pair)  // my half of the rows the MMA uses: [crank, crank + 1) * 16 S
+              tma_load_2d(s_w + ws * w_slice, &map_w, &wr_full[ws], 64 * kc, n0 + crank * 16 * S);
+            else if (cs > 1)
               tma_load_2d_multicast(s_w + ws * w_slice + crank * part_rows * 128, &map_w, &wr_full[ws], 64 * kc,
                                     n0 + crank * part_rows, cmask);
             else
@@ -234,51 +248,78 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           }
       }
     }
+  } else if (pair && warp == E + kCvtWarps + 3) {
+    // ================================================================ pair, peer CTA: tell the leader that this CTA's half of
+    // each W slice has landed (the leader's MMA issuer can only wait on its own CTA's barriers)
+    if (crank == 1 && elect_one()) {
+      int ws = 0;
+      uint32_t wph = 0;
+      for (long long tile = t0; tile < t_end; tile += tstep)
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&wr_full[ws], wph);
+          mbar_arrive_cluster(&wr_full2[ws], 0);
+          if (++ws == a.wring) { ws = 0; wph ^= 1; }
+        }
+    }
   } else if (warp == E + kCvtWarps + 1) {
-    // ================================================================ MMA issuer
-    if (elect_one()) {
+    // ================================================================ MMA issuer (pair: the leader CTA only)
+    if (elect_one() && (!pair || crank == 0)) {
       constexpr uint64_t kDesc = umma_smem_desc(16, 1024, kLayoutSw128);
-      const uint32_t idesc = idesc_bf16(128, 32 * S);
+      const uint32_t idesc = idesc_bf16(pair ? 256 : 128, 32 * S);
       if (a.resident) mbar_wait(&w_full, 0);
       const uint32_t wb = smem_u32(s_w);
-      const uint32_t idesc32 = umma_idesc_tf32(128, 32 * S, 0, 0);
+      const uint32_t idesc32 = umma_idesc_tf32(pair ? 256 : 128, 32 * S, 0, 0);
       const uint32_t rb = smem_u32(s_ring);
       int as_ = 0, ws = 0, slot = 0;
       uint32_t aph = 0, wph = 0, ph = 0;
       long long it = 0;
       for (long long tile = t0; tile < t_end; tile += tstep, ++it) {
         const int st = (int)(it & 1);
-        mbar_wait(&acc_empty[st], (((uint32_t)(it >> 1)) & 1) ^ 1);
+        if (pair) mbar_wait_cluster(&acc_empty[st], (((uint32_t)(it >> 1)) & 1) ^ 1);
+        else mbar_wait(&acc_empty[st], (((uint32_t)(it >> 1)) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d = tmem + (uint32_t)st * a.stage_cols;
         for (int kc = 0; kc < nk; ++kc) {
           if (!a.resident) mbar_wait(&wr_full[ws], wph);
+          if (pair) mbar_wait_cluster(&wr_full2[ws], wph);
           const uint32_t wk = wb + (a.resident ? kc : ws) * w_slice;
           if (a.prec == PREC_TF32) {
             // A: the fp32 chunk as TMA delivered it (K-major, SWIZZLE_128B); W slice: 32 tf32-rounded fp32 per row
-            mbar_wait(&raw_full[slot], ph);
+            if (pair) mbar_wait_cluster(&cvt_full[slot], ph);  // both CTAs' chunks (forwarded by their A-producer warps)
+            else mbar_wait(&raw_full[slot], ph);
             tc_fence_after();
             const uint32_t ab = rb + slot * kChunk;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              umma_tf32_ss_(d, umma_desc_at(kDesc, ab + 32 * ks), umma_desc_at(kDesc, wk + 32 * ks), idesc32,
-                            (kc > 0 || ks > 0) ? 1u : 0u);
-            umma_commit(&slot_empty[slot]);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = umma_desc_at(kDesc, ab + 32 * ks), db = umma_desc_at(kDesc, wk + 32 * ks);
+              if (pair) umma_tf32_ss_pair(d, da, db, idesc32, (kc > 0 || ks > 0) ? 1u : 0u);
+              else umma_tf32_ss_(d, da, db, idesc32, (kc > 0 || ks > 0) ? 1u : 0u);
+            }
+            if (pair) umma_commit_pair(&slot_empty[slot], 3);
+            else umma_commit(&slot_empty[slot]);
             if (++slot == ring) { slot = 0; ph ^= 1; }
           } else if (a.ss) {
             // bf16x3 with the chunk split IN PLACE in shared memory: [hi(32) | lo(32)] bf16 per 128-byte row
-            mbar_wait(&cvt_full[slot], ph);
+            if (pair) mbar_wait_cluster(&cvt_full[slot], ph);
+            else mbar_wait(&cvt_full[slot], ph);
             tc_fence_after();
             const uint32_t ab = rb + slot * kChunk;
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t a_hi = umma_desc_at(kDesc, ab + 32 * ks), a_lo = umma_desc_at(kDesc, ab + 64 + 32 * ks);
               const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
-              umma_bf16_ss(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
-              umma_bf16_ss(d, a_hi, w_lo, idesc, 1u);
-              umma_bf16_ss(d, a_hi, w_hi, idesc, 1u);
+              if (pair) {
+                umma_bf16_ss_pair(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                umma_bf16_ss_pair(d, a_hi, w_lo, idesc, 1u);
+                umma_bf16_ss_pair(d, a_hi, w_hi, idesc, 1u);
+              } else {
+                umma_bf16_ss(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                umma_bf16_ss(d, a_hi, w_lo, idesc, 1u);
+                umma_bf16_ss(d, a_hi, w_hi, idesc, 1u);
+              }
             }
-            umma_commit(&slot_empty[slot]);
+            if (pair) umma_commit_pair(&slot_empty[slot], 3);
+            else umma_commit(&slot_empty[slot]);
             if (++slot == ring) { slot = 0; ph ^= 1; }
           } else {
             mbar_wait(&a_full[as_], aph);
@@ -300,12 +341,14 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             if (++as_ == kASlots) { as_ = 0; aph ^= 1; }
           }
           if (!a.resident) {
-            if (cs > 1) umma_commit_multicast(&wr_empty[ws], cmask);
+            if (pair) umma_commit_pair(&wr_empty[ws], 3);
+            else if (cs > 1) umma_commit_multicast(&wr_empty[ws], cmask);
             else umma_commit(&wr_empty[ws]);
             if (++ws == a.wring) { ws = 0; wph ^= 1; }
           }
         }
-        umma_commit(&acc_full[st]);
+        if (pair) umma_commit_pair(&acc_full[st], 3);
+        else umma_commit(&acc_full[st]);
       }
     }
   } else if (warp >= E) {
@@ -330,7 +373,9 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       for (int i = threadIdx.x - E * 32; i < nk * 32; i += kCvtWarps * 32) s_colsum[i] = 0.f;
       named_bar_sync(1, kCvtWarps * 32);
     }
-    if (convert || do_colsum) {
+    // (pair, TF32 without column sums: one warp per team only forwards the chunk's arrival to the leader; the others must
+    // not wait on barriers whose progress does not depend on them -- they could fall a whole ring cycle behind)
+    if (convert || do_colsum || (pair && q == 0)) {
       long long c = 0;  // running chunk index of this CTA
       for (long long tile = t0; tile < t_end; tile += tstep)
         for (int kc = 0; kc < nk; ++kc, ++c) {
@@ -344,6 +389,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           const int slot = (int)(c % ring);
           const uint32_t ph = (uint32_t)(c / ring) & 1;
           mbar_wait(&raw_full[slot], ph);
+          if (pair && !convert) {
+            if (q == 0 && lane == 0) mbar_arrive_cluster(&cvt_full[slot], 0);  // this CTA's chunk has landed
+            if (!do_colsum) continue;
+          }
           const uint32_t base = ring_u32 + slot * kChunk + row * 128;
           float4 v[8];
 #pragma unroll
@@ -389,7 +438,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             }
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&cvt_full[slot]);
+            if (lane == 0) {
+              if (pair) mbar_arrive_cluster(&cvt_full[slot], 0);  // the leader issues the MMAs of both CTAs
+              else mbar_arrive(&cvt_full[slot]);
+            }
             continue;
           }
           __syncwarp();  // every lane holds its row in registers: the shared-memory slot can be refilled
@@ -442,18 +494,21 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       const long long grow = tile * kBM + q * 32 + lane;
       uint32_t dkey = 0;
       if (MODE == MODE_GELU || MODE == MODE_GELU_GRAD) dkey = a.drop_thresh ? hs::drop_row_key(a.seed, grow) : 0u;
-      if (spw == 0) {  // more groups than slabs: stay in step with the accumulator stages
+      auto release_stage = [&]() {  // this thread's part of the accumulator stage is in registers (or unused)
         tc_fence_before();
-        mbar_arrive(&acc_empty[as]);
-      }
+        if (pair) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&acc_empty[as], 0);
+        } else {
+          mbar_arrive(&acc_empty[as]);
+        }
+      };
+      if (spw == 0) release_stage();  // more groups than slabs: stay in step with the accumulator stages
       for (int s = g; s < S; s += NG) {
         uint32_t acc[32];
         tmem_ld32(tmem + lane_addr + (uint32_t)as * a.stage_cols + 32 * s, acc);
         tmem_wait_ld();
-        if (s + NG >= S) {  // this thread's last slab of the tile is in registers
-          tc_fence_before();
-          mbar_arrive(&acc_empty[as]);
-        }
+        if (s + NG >= S) release_stage();  // this thread's last slab of the tile is in registers
         const int jc = n0 + 32 * s;
 #pragma unroll
         for (int st = 0; st < kStores; ++st, ++cnt) {
@@ -526,7 +581,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (cs > 1) cluster_sync_all();  // no CTA leaves while a peer may still multicast into it
-  if (warp == E + kCvtWarps + 1) tmem_dealloc(tmem, 512);
+  if (warp == E + kCvtWarps + 1) {
+    if (pair) tmem_dealloc_pair(tmem, 512);
+    else tmem_dealloc(tmem, 512);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -594,6 +652,14 @@ int plan(G3Args& a, int mode, int E) {
   a.ss = (a.prec == PREC_TF32 || (a.prec == PREC_BF16X3 && (long long)a.N * a.K > 130ll * (a.N + a.K) && a.K >= 256)) ? 1 : 0;
   if (const char* e = getenv("HEALSWIN_GEMM3_SS")) a.ss = (a.prec == PREC_TF32) ? 1 : (atoi(e) != 0 && a.prec == PREC_BF16X3);
   a.stage_cols = a.ss ? 256 : 192;
+  // CTA pairs (cta_group::2, M = 256): each CTA of a pair stages only half of every W slice, which halves the B-operand
+  // traffic of its shared memory -- the co-limiter of the ss modes (per K = 16 step and CTA: 76 KB of shared-memory
+  // traffic = 594 cycles against 384 cycles of MMA time alone; 56 KB = 437 cycles in a pair)
+  // Measured at stages 2-3 (profiles/r2p_gemm3_pair.log): bf16x3 5-8 % faster (tensor pipe 67 -> 75 % active under ncu);
+  // the single-MMA TF32 mode does not gain (it waits for operand data, not for shared-memory bandwidth), so it stays
+  // with one CTA per tile.  HEALSWIN_GEMM3_PAIR=0 / 1 forces it off / on for every ss launch (experiments).
+  a.pair = (a.ss && a.prec == PREC_BF16X3 && a.tiles >= 2) ? 1 : 0;
+  if (const char* e = getenv("HEALSWIN_GEMM3_PAIR")) a.pair = (atoi(e) != 0 && a.ss && a.tiles >= 2) ? 1 : 0;
   int first = (a.N + a.stage_cols - 1) / a.stage_cols;  // number of chunks
   first = (((a.N + first - 1) / first) + 15) / 16 * 16;  // equal chunks, 16-column granularity
   if (const char* e = getenv("HEALSWIN_GEMM3_NTILE")) {  // experiments only
@@ -606,9 +672,9 @@ int plan(G3Args& a, int mode, int E) {
     const int stride = cand[ci];
     if (stride > first || (ci > 0 && stride == first)) continue;
     const int box = (stride + 31) / 32 * 32;
-    const int w_slice = box * 128;
+    const int w_slice = (a.pair ? box / 2 : box) * 128;
     const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0);
-    const int resident = ((long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
+    const int resident = (!a.pair && (long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
     int wring = nk < 3 ? nk : 3;
     if (const char* e = getenv("HEALSWIN_GEMM3_WRING")) {  // experiments only
       const int v = atoi(e);
@@ -643,12 +709,13 @@ int plan(G3Args& a, int mode, int E) {
     if ((v == 1 || v == 2 || v == 4) && !a.resident && a.n_box % (16 * v) == 0) a.cluster = v;
     if (v == 1) a.cluster = 1;
   }
+  if (a.pair) a.cluster = 2;
   return HS_OK;
 }
 
 template <int E>
 size_t smem_bytes(const G3Args& a) {
-  const int nk = (a.K + 31) / 32, w_slice = a.n_box * 128;
+  const int nk = (a.K + 31) / 32, w_slice = (a.pair ? a.n_box / 2 : a.n_box) * 128;
   return (size_t)(a.resident ? nk : a.wring) * w_slice + (size_t)a.ring * kChunk + (size_t)E * a.rw * kRegion +
          (a.colsum ? (size_t)nk * 128 : 0) + 1024;
 }
@@ -656,6 +723,35 @@ size_t smem_bytes(const G3Args& a) {
 struct Maps {
   CUtensorMap a, w, aux, d, d2;
 };
+
+template <int E, int MODE, bool PAIR>
+int launch_kernel(const Maps& m, const G3Args& a, size_t smem, int per_chunk, cudaStream_t stream) {
+  // the dynamic shared-memory limit is raised once per (instantiation, device) to the largest plan; an immutable cache
+  // (the value never changes afterwards), so that no attribute call happens inside a CUDA-graph capture
+  static bool raised[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !raised[dev]) {
+    HS_CUDA(cudaFuncSetAttribute(gemm3_kernel<E, MODE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAvail + 1024));
+    if (dev >= 0 && dev < 64) raised[dev] = true;
+  }
+  const int cs = a.cluster;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(a.n_chunks * per_chunk));
+  cfg.blockDim = dim3(block_threads<E, PAIR>());
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cs > 1 ? 1 : 0;
+  HS_CUDA(cudaLaunchKernelEx(&cfg, gemm3_kernel<E, MODE, PAIR>, m.a, m.w, m.aux, m.d, m.d2, a));
+  HS_LAUNCH_CHECK();
+  return HS_OK;
+}
 
 template <int E, int MODE>
 int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, float* d_dev, float* d2_dev, G3Args& a,
@@ -670,36 +766,14 @@ int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, floa
   if (aux_dev && (rc = hs::tc::make_map(&m.aux, aux_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
   if (d2_dev && (rc = hs::tc::make_map(&m.d2, d2_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
   const size_t smem = smem_bytes<E>(a);
-  // the dynamic shared-memory limit is raised once per (instantiation, device) to the largest plan; an immutable cache
-  // (the value never changes afterwards), so that no attribute call happens inside a CUDA-graph capture
-  static bool raised[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !raised[dev]) {
-    HS_CUDA(cudaFuncSetAttribute(gemm3_kernel<E, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAvail + 1024));
-    if (dev >= 0 && dev < 64) raised[dev] = true;
-  }
   const int cs = a.cluster;
   int per_chunk = hs::tc::sm_count() / a.n_chunks;
   if (per_chunk > a.tiles) per_chunk = (int)a.tiles;
   per_chunk = per_chunk / cs * cs;
   if (per_chunk < cs) per_chunk = cs;
   if ((rc = make_map_bf16(&m.w, w_dev, a.N, 2ll * ((a.K + 31) / 32 * 32), 64, a.n_box / cs))) return rc;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(a.n_chunks * per_chunk));
-  cfg.blockDim = dim3((E + kCvtWarps + 3) * 32);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = cs > 1 ? 1 : 0;
-  HS_CUDA(cudaLaunchKernelEx(&cfg, gemm3_kernel<E, MODE>, m.a, m.w, m.aux, m.d, m.d2, a));
-  HS_LAUNCH_CHECK();
-  return HS_OK;
+  return a.pair ? launch_kernel<E, MODE, true>(m, a, smem, per_chunk, stream)
+                : launch_kernel<E, MODE, false>(m, a, smem, per_chunk, stream);
 }
 
 }  // namespace

@@ -83,6 +83,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polling wait (test_wait never suspends the warp): for a lane that shares its warp with another lane spinning on a
+// different barrier -- a suspended try_wait of one divergent path would hold the other one back.
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_test_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -267,6 +277,75 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
       "h"(cta_mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+// Two CTAs of a cluster (ranks 0 and 1, same TPC) run ONE tcgen05.mma of M = 256: each provides its own 128 rows of A and
+// its own half (N / 2 rows) of B at the SAME shared-memory offsets, each receives its 128 rows of D at the same TMEM
+// address.  Only the leader (rank 0) issues the MMAs and the commits; everything it waits for from the peer arrives on the
+// leader's own mbarriers through the cluster-mapped address.
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {  // one warp of EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the mbarrier at this shared-memory offset in CTA `cta` of the cluster.  Default semantics (release at CTA
+// scope), as CUTLASS's ClusterBarrier::arrive(cta_id): `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR in front of
+// every arrive, which cost the converter warps more than the conversion itself (profiles/r2p_gemm3_pair_*).  What the
+// arrive has to order here is a CTA's generic-proxy writes to its OWN shared memory (already fenced towards the async
+// proxy) before MMAs that the leader issues later and that read that same CTA's shared memory.
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait with acquire at cluster scope (the arrivals may come from the peer CTA); same 2 s trap as mbar_wait
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+#ifdef HS_PAIR_ACQUIRE_CLUSTER
+      "{\n.reg .pred P;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\nselp.u32 %0, 1, 0, P;\n}\n"
+#else
+      "{\n.reg .pred P;\nmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\nselp.u32 %0, 1, 0, P;\n}\n"
+#endif
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// completion of all prior cta_group::2 MMAs of this thread -> one arrive on the mbarrier at this offset in every CTA of mask
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// D[tmem, 2 x 128 rows] (+)= A[smem of both CTAs] * B[smem halves of both CTAs]
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 

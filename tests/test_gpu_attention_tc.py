@@ -68,6 +68,35 @@ def test_tc_backward_full_size_linearity_property():
     assert torch.equal(g3[0], g3[2]) and torch.equal(g3[1], g3[7])
 
 
+@pytest.mark.parametrize("cos", [False, True])
+def test_tc_backward_is_bit_identical_run_to_run(cos):
+    """dqkv has no atomics in its path: every element is written once by one thread, so repeated launches on the same
+    inputs must agree bit for bit.  A race in the kernel's barrier protocol (warp roles that alternate between units,
+    ring slots, staging tiles) shows up here as run-to-run differences -- with a nest_roll shift so that both the TMA
+    and the gathered-window paths run, at a size that gives every CTA dozens of units."""
+    from heal_swin_b200 import hp_index, ops
+    from scripts.tc_check import tables
+
+    dev = torch.device("cuda:0")
+    B, nside, base_pix, H, ws, D = 2, 128, 12, 3, 64, 32
+    C, N = H * D, base_pix * nside * nside
+    g = torch.Generator().manual_seed(11)
+    qkv = torch.randn(B, N, 3 * C, generator=g).to(dev)
+    table = (torch.randn(225, H, generator=g) * 0.5).to(dev)
+    rel_index = hp_index.rel_pos_index(ws).to(torch.int32).reshape(-1).contiguous().to(dev)
+    ls = (torch.log(torch.tensor(10.0)) + 0.3 * torch.randn(H, 1, 1, generator=g)).to(dev) if cos else None
+    src, grp = tables("nest_roll", nside, base_pix, ws, dev)
+    dout = torch.randn(B, N, C, generator=g).to(dev)
+    grads = []
+    for _ in range(4):
+        q = qkv.clone().requires_grad_(True)
+        out = ops.window_attention_core(q, table, ls, src, grp, None, rel_index, D ** -0.5, H, ws, cos)
+        (gq,) = torch.autograd.grad(out, q, dout)
+        grads.append(gq)
+    for gq in grads[1:]:
+        assert torch.equal(grads[0], gq)
+
+
 def test_tc_forward_vs_oracle_through_the_block():
     """SwinTransformerBlock attention (ring shift, cos, bias) on the tensor-core path vs the CPU oracle."""
     from heal_swin_b200 import ops
