@@ -67,7 +67,10 @@ constexpr bool kL2Prefetch = HS_BWD_PREFETCH != 0;  // L2 prefetch of the next u
 // F.normalize / logit_scale terms), so the key-row threads take the tile (held transposed, dbt[j][i]); without, the
 // query-row threads do (measured on one box, stage 0: cos 1.47 -> 1.40 ms, plain 1.01 -> 1.05 ms the other way round;
 // splitting the tile between the halves by 32 x 32 quadrant was slower than either: 1.54 / 1.08 ms).
-__host__ __device__ constexpr bool dbt_on_key_rows(bool cos) { return cos; }
+#ifndef HS_BWD_DBT_KEY_ROWS
+#define HS_BWD_DBT_KEY_ROWS 2  // 0: query rows, 1: key rows, 2: key rows for cos attention only
+#endif
+__host__ __device__ constexpr bool dbt_on_key_rows(bool cos) { return HS_BWD_DBT_KEY_ROWS == 2 ? cos : HS_BWD_DBT_KEY_ROWS != 0; }
 // Mirrored stacking on TMEM stage 1: its units are computed as [K;Q] [K;Q]^T and [V;dO] [V;dO]^T, so the key-row
 // orientation sits on lanes 0-63 and the query rows on lanes 64-127 -- every TMEM column offset of the unmirrored map
 // XOR 64.  A TMEM lane quadrant is tied to a warp (id % 4) and thereby to a scheduler; without the mirror the two
