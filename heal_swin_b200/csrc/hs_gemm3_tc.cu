@@ -655,10 +655,10 @@ int plan(G3Args& a, int mode, int E) {
   // CTA pairs (cta_group::2, M = 256): each CTA of a pair stages only half of every W slice, which halves the B-operand
   // traffic of its shared memory -- the co-limiter of the ss modes (per K = 16 step and CTA: 76 KB of shared-memory
   // traffic = 594 cycles against 384 cycles of MMA time alone; 56 KB = 437 cycles in a pair)
-  // Measured at stages 2-3 (profiles/r2p_gemm3_pair.log): bf16x3 5-8 % faster (tensor pipe 67 -> 75 % active under ncu);
-  // the single-MMA TF32 mode does not gain (it waits for operand data, not for shared-memory bandwidth), so it stays
-  // with one CTA per tile.  HEALSWIN_GEMM3_PAIR=0 / 1 forces it off / on for every ss launch (experiments).
-  a.pair = (a.ss && a.prec == PREC_BF16X3 && a.tiles >= 2) ? 1 : 0;
+  // Measured at stages 2-3 (profiles/r2p_gemm3_pair.log): bf16x3 5-8 % faster (tensor pipe 67 -> 75 % active under ncu),
+  // the single-MMA TF32 mode 5-6 % with a W ring of four half-slices (none with three: the round trip slice released ->
+  // reloaded -> forwarded by the peer is longer than in one CTA).  HEALSWIN_GEMM3_PAIR=0 / 1 forces it off / on.
+  a.pair = (a.ss && a.tiles >= 2) ? 1 : 0;
   if (const char* e = getenv("HEALSWIN_GEMM3_PAIR")) a.pair = (atoi(e) != 0 && a.ss && a.tiles >= 2) ? 1 : 0;
   int first = (a.N + a.stage_cols - 1) / a.stage_cols;  // number of chunks
   first = (((a.N + first - 1) / first) + 15) / 16 * 16;  // equal chunks, 16-column granularity
@@ -675,7 +675,7 @@ int plan(G3Args& a, int mode, int E) {
     const int w_slice = (a.pair ? box / 2 : box) * 128;
     const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0);
     const int resident = (!a.pair && (long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
-    int wring = nk < 3 ? nk : 3;
+    int wring = a.pair ? (nk < 4 ? nk : 4) : (nk < 3 ? nk : 3);  // (a pair's slices are half the size)
     if (const char* e = getenv("HEALSWIN_GEMM3_WRING")) {  // experiments only
       const int v = atoi(e);
       if (v >= 2 && v <= kMaxWRing && v <= nk) wring = v;

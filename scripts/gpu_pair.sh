@@ -10,5 +10,5 @@ run() {  # label, env...
 }
 run p0 HEALSWIN_GEMM3_PAIR=0
 run p1 HEALSWIN_GEMM3_PAIR=1
-
-
+run p1w4 HEALSWIN_GEMM3_PAIR=1 HEALSWIN_GEMM3_WRING=4
+run p1w6 HEALSWIN_GEMM3_PAIR=1 HEALSWIN_GEMM3_WRING=6
