@@ -31,7 +31,11 @@
 // aux sub-slabs are brought in by TMA into the staging regions ahead of time and combined in place.
 //
 // Warps: [0, E) epilogue (TMEM lane quadrant = warp % 4), [E, E+8) converters, E+8 A producer, E+9 MMA issuer,
-// E+10 W producer.
+// E+10 W producer (+ E+11, pair kernels: forwards the arrival of the peer's W half-slices to the leader).
+//
+// CTA pairs (template PAIR; the tensor-bound "ss" launches): the two CTAs of a cluster take neighbouring token tiles of the
+// same column chunk and run tcgen05.mma.cta_group::2 (M = 256) issued by the leader; each stages only half of every W
+// slice, which halves the B-operand traffic on its shared-memory port.
 #include <cstdlib>
 
 #include "hs_common.h"
@@ -696,9 +700,8 @@ int plan(G3Args& a, int mode, int E) {
     left -= (long long)ring * kChunk;
     a.rw = rw_min + (int)(left / ((long long)E * kRegion));  // (staging_min already holds rw_min regions + the column sums)
     // Streamed W slices can be loaded once per cluster of 2 / 4 CTAs and multicast (HEALSWIN_GEMM3_CLUSTER): verified
-    // correct on the B200 and measured to change nothing (profiles/r2i_gemm3_check.log) -- the shapes that stream W are
-    // bound by the tensor pipe at the power-capped clock (81 % of the sustained cuBLAS bf16 rate with three MMAs per
-    // product), not by L2 -> SM traffic -- so the default stays one CTA per cluster.
+    // correct on the B200 and measured to change nothing (profiles/r2q_cluster_exp.log) -- the shapes that stream W are
+    // not bound by L2 -> SM traffic but by the shared-memory port (see a.pair) -- so multicast stays off.
     a.cluster = 1;
     if (a.rw > rw_max) a.rw = rw_max;
     if (ring >= 4) break;
