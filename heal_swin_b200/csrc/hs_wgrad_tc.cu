@@ -51,10 +51,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
   __shared__ uint32_t tmem_base;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kTT = a.tt, kSlab = a.tt * 128;
-  const int q_slabs = a.NQ / 32;
+  const int q_slabs = (a.NQ + 31) / 32;  // a ragged last slab (NQ % 32 != 0) is zero-filled by TMA beyond the tensor
   const int ones = a.colsum ? 1 : 0;  // one extra Q slab holding the constant column (1, 0, ..., 0)
   // D columns: one MMA of N = NQ (+32 for the ones slab) when that is <= 256, else two halves (multiples of 32)
-  const int n_all = a.NQ + 32 * ones;
+  const int n_all = 32 * (q_slabs + ones);
   const int n1 = n_all <= 256 ? n_all : ((q_slabs + 1) / 2) * 32;
   const int n2 = n_all - n1;
   const int crank = PAIR ? (int)cluster_ctarank() : 0;
@@ -100,7 +100,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
     mbar_init(&done, 1);
     mbar_fence_init();
   }
-  const uint32_t tmem_cols = (a.NQ + 32 * ones > 256) ? 512u : 256u;
+  const uint32_t tmem_cols = (n_all > 256) ? 512u : 256u;
   if (warp == 5) {
     if (PAIR) tmem_alloc_pair(&tmem_base, tmem_cols);
     else tmem_alloc(&tmem_base, tmem_cols);
@@ -188,22 +188,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_p, const __grid_constant
         tmem_wait_ld();
         if (p < a.NP) {
           float* dst = a.out + (long long)p * a.ldo_p + (long long)c0 * a.ldo_q;
+          const int nc = a.NQ - c0 < 32 ? a.NQ - c0 : 32;  // (NQ is a multiple of 4)
           if (a.ldo_q == 1) {  // my 32 columns are contiguous in memory: 128-bit vector reductions
 #pragma unroll
             for (int c = 0; c < 32; c += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c),
-                           "f"(__uint_as_float(r[c]) * a.fix), "f"(__uint_as_float(r[c + 1]) * a.fix),
-                           "f"(__uint_as_float(r[c + 2]) * a.fix), "f"(__uint_as_float(r[c + 3]) * a.fix)
-                           : "memory");
+              if (c < nc)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c),
+                             "f"(__uint_as_float(r[c]) * a.fix), "f"(__uint_as_float(r[c + 1]) * a.fix),
+                             "f"(__uint_as_float(r[c + 2]) * a.fix), "f"(__uint_as_float(r[c + 3]) * a.fix)
+                             : "memory");
           } else {  // transposed output: consecutive lanes (rows p) are contiguous, one coalesced reduction per column
 #pragma unroll
-            for (int c = 0; c < 32; ++c) atomicAdd(dst + (long long)c * a.ldo_q, __uint_as_float(r[c]) * a.fix);
+            for (int c = 0; c < 32; ++c)
+              if (c < nc) atomicAdd(dst + (long long)c * a.ldo_q, __uint_as_float(r[c]) * a.fix);
           }
         }
       }
       if (ones) {  // column NQ of D = sum_t P[t][p] * 1
         uint32_t r[32];
-        tmem_ld32(tmem + lane_addr + a.NQ, r);
+        tmem_ld32(tmem + lane_addr + 32 * q_slabs, r);
         tmem_wait_ld();
         if (p < a.NP) atomicAdd(a.colsum + p, __uint_as_float(r[0]) * a.fix1);
       }
@@ -224,19 +227,22 @@ extern "C" {
 
 // 0: not covered (the caller keeps the library GEMM); 1: dW covered; 2: dW and the fused bias gradient covered
 int hs_linear_wgrad_supported(int64_t T, int N, int K) {
-  if (T < 4096 || N < 32 || K < 32 || (N % 4) || (K % 4)) return 0;
+  if (T < 4096 || N < 4 || K < 4 || (N % 4) || (K % 4)) return 0;
   const int q = N < K ? N : K;
+  if ((N < K ? K : N) < 32) return 0;
   if (q > 512) return (q <= 1024 && q % 64 == 0) ? 1 : 0;  // two launches over the column halves of the smaller operand
-  if (q % 32 != 0) return 0;
-  return (N >= K && K + 32 <= 256) ? 2 : 1;
+  // (a smaller operand that is not a multiple of 32 -- the patch embedding's 48 input features -- takes a zero-filled
+  // last slab; above 256 columns the two-MMA split wants whole slabs)
+  if (q % 32 != 0 && q > 224) return 0;
+  return (N >= K && (K + 31) / 32 * 32 + 32 <= 256) ? 2 : 1;
 }
 
 int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, int64_t T, int N, int K, uint32_t flags,
                     void* stream) {
   HS_REQUIRE(dy && x && dw && T > 0 && N > 0 && K > 0, "hs_linear_wgrad: bad arguments");
   if (!hs_linear_wgrad_supported(T, N, K))
-    return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: shape T=%lld N=%d K=%d is not covered (min(N, K) must be a "
-                    "multiple of 32 and <= 512, or a multiple of 64 and <= 1024)", (long long)T, N, K);
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: shape T=%lld N=%d K=%d is not covered (see "
+                    "hs_linear_wgrad_supported in include/healswin_b200.h)", (long long)T, N, K);
   HS_REQUIRE(!((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15), "hs_linear_wgrad: unaligned input");
   // P = operand with more features (rows of D), Q = the other (<= 512 columns per launch)
   const bool p_is_dy = N >= K;
@@ -247,7 +253,7 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, in
   // each reading its half of Q through the row pitch and writing its column block of dW
   const int parts = NQ_all > 512 ? 2 : 1;
   const int NQ = NQ_all / parts;
-  if (dbias && !(p_is_dy && parts == 1 && NQ + 32 <= 256))
+  if (dbias && !(p_is_dy && parts == 1 && (NQ + 31) / 32 * 32 + 32 <= 256))
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_linear_wgrad: the fused bias gradient needs N >= K and K <= 224 (N=%d K=%d)", N, K);
   for (int part = 0; part < parts; ++part) {
     WgArgs a{};
@@ -257,7 +263,7 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, in
     a.ldo_p = p_is_dy ? K : 1; a.ldo_q = p_is_dy ? 1 : K;
     a.out = dw + (long long)part * NQ * a.ldo_q;
     a.p_blocks = (a.NP + 127) / 128;
-    a.tt = a.NQ <= 256 ? 64 : 32;
+    a.tt = (a.NQ + 31) / 32 * 32 + (dbias ? 32 : 0) <= 256 ? 64 : 32;
     const int kTT = a.tt, kSlab = a.tt * 128;
     const long long tiles = (T + kTT - 1) / kTT;
     int splits = hs::tc::sm_count() / a.p_blocks;
@@ -265,7 +271,7 @@ int hs_linear_wgrad(const float* dy, const float* x, float* dw, float* dbias, in
     if (splits > tiles) splits = (int)tiles;
     a.splits = splits;
     // CTA pairs where the stage is dominated by Q (>= 6 slabs), the P blocks come in twos and every MMA's slabs halve
-    const int q_slabs = a.NQ / 32, s1 = a.NQ <= 256 ? q_slabs : (q_slabs + 1) / 2, s2 = q_slabs - s1;
+    const int q_slabs = (a.NQ + 31) / 32, s1 = 32 * q_slabs <= 256 ? q_slabs : (q_slabs + 1) / 2, s2 = q_slabs - s1;
     bool pair = !dbias && q_slabs >= 6 && a.p_blocks % 2 == 0 && s1 % 2 == 0 && s2 % 2 == 0 && splits >= 1;
     if (const char* e = getenv("HEALSWIN_WGRAD_PAIR")) pair = pair && atoi(e) != 0;
     const int stage_bytes = (4 + (pair ? q_slabs / 2 : q_slabs) + (dbias ? 1 : 0)) * kSlab;

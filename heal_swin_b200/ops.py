@@ -610,7 +610,7 @@ def _wgrad(dy2, x2, need_bias):
         STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, _tc_flags(),
                      current_stream(), tag=(T, N, K))
     else:
-        # shapes outside the kernel (min(N, K) > 512: stage 3; K < 32: patch embedding): the library GEMM, in the same
+        # shapes outside the kernel (fewer than 4096 tokens, feature counts that are not multiples of 4): the library GEMM, in the same
         # arithmetic as the kernel (TF32 operands, fp32 accumulation) whatever torch's global switch says -- as fp32
         # these run as SIMT sgemm kernels, 11 ms per step of the N_side=256 network
         # (with the kernel switched off -- HEALSWIN_CUSTOM_WGRAD=0, the exact-fp32 tests -- torch's switch decides)

@@ -187,9 +187,10 @@ int hs_bias_gelu_bwd(const float* dh_dev, const float* z_dev, const float* bias_
  * and optionally the bias gradient in the same pass:   dbias[n] += sum_t dy[t][n]   (dbias may be NULL).
  * TF32 tensor-core kernel with the token range split over the SMs; dw / dbias are ACCUMULATED into (zero them for a
  * plain gradient).  hs_linear_wgrad_supported returns 0 when the shape is not covered (it then stays with the library
- * GEMM; covered: min(N, K) a multiple of 32 and <= 512, or a multiple of 64 and <= 1024 -- two launches over the column
- * halves of the smaller operand --, T >= 4096), 1 when dw is covered, 2 when dbias can be fused too
- * (N >= K, K <= 224).  flags: HS_ATTN_NO_TRUNC_COMP only.
+ * GEMM; covered: T >= 4096, N and K multiples of 4, max(N, K) >= 32, and min(N, K) <= 224 (any multiple of 4: a ragged
+ * last 32-feature slab is zero-filled -- the patch embedding's 12 inputs), or a multiple of 32 and <= 512, or a multiple
+ * of 64 and <= 1024 -- two launches over the column halves of the smaller operand), 1 when dw is covered, 2 when dbias
+ * can be fused too (N >= K, K <= 224).  flags: HS_ATTN_NO_TRUNC_COMP only.
  */
 int hs_linear_wgrad_supported(int64_t T, int N, int K);
 int hs_linear_wgrad(const float* dy_dev, const float* x_dev, float* dw_dev, float* dbias_dev, int64_t T, int N, int K,

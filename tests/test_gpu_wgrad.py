@@ -29,7 +29,12 @@ def _wgrad(dy, x):
                                    (8192, 1152, 384), (8192, 384, 384), (6000, 384, 1536), (8192, 640, 512),
                                    (8192, 288, 320),
                                    # smaller feature dimension in (512, 1024]: two launches over its column halves (stage 3)
-                                   (24576, 2304, 768), (8192, 768, 768), (6000, 768, 3072), (8192, 1536, 1024)])
+                                   (24576, 2304, 768), (8192, 768, 768), (6000, 768, 3072), (8192, 1536, 1024),
+                                   # smaller feature dimension not a multiple of 32 (patch embedding: 4 * 4 * 3 = 48 inputs):
+                                   # zero-filled last slab
+                                   (8192, 96, 48), (8192, 48, 96), (5000, 128, 36), (8192, 1536, 200), (8192, 96, 12), (8192, 12, 96),
+                                   # CTA pairs (>= 6 slabs of the smaller operand, even number of 128-row blocks)
+                                   (16384, 768, 192), (16384, 192, 768), (8192, 1536, 384), (6000, 3072, 768)])
 def test_wgrad_matches_fp32_product(T, N, K):
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(T + N + K)
@@ -40,7 +45,8 @@ def test_wgrad_matches_fp32_product(T, N, K):
     assert rel_err(got.cpu(), want.cpu()) < TOL
 
 
-def test_wgrad_exact_on_tf32_representable_data_and_accumulates():
+@pytest.mark.parametrize("N,K", [(288, 96), (96, 48), (96, 12)])  # (96, 12): the patch embedding, ragged slab + fused bias gradient
+def test_wgrad_exact_on_tf32_representable_data_and_accumulates(N, K):
     """Small integers are exact in TF32 and the sums stay below 2^24: the result must be bit-exact once the truncation
     compensation is switched off; a second call accumulates (+=)."""
     import ctypes as C
@@ -49,7 +55,7 @@ def test_wgrad_exact_on_tf32_representable_data_and_accumulates():
     from heal_swin_b200._lib import check, current_stream, lib, ptr
 
     dev = torch.device("cuda:0")
-    T, N, K = 16384, 288, 96
+    T = 16384
     g = torch.Generator().manual_seed(1)
     dy = torch.randint(-4, 5, (T, N), generator=g).float().to(dev)
     x = torch.randint(-4, 5, (T, K), generator=g).float().to(dev)
