@@ -220,3 +220,35 @@ def test_full_size_launches_are_exact_on_small_integer_data(T, N, K, prec):
     torch.backends.cuda.matmul.allow_tf32 = False
     want = a @ w.t()  # exact: |sum| <= 3072 * 16 < 2^24
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("T", [256, 384, 300, 129, 1000, 2048 + 17])
+@pytest.mark.parametrize("N,K", [(1152, 384), (384, 1536), (200, 512)])
+def test_cta_pair_regime_small_and_ragged_token_counts(T, N, K):
+    """The tensor-bound regime (streamed weights, K >= 256) runs as CTA pairs (tcgen05.mma.cta_group::2, M = 256): two
+    neighbouring 128-token tiles per cluster, each CTA staging half of every weight slice.  Token counts that leave the
+    second tile of the last pair partly or wholly outside the tensor, an odd number of tiles, a ragged last column chunk
+    (N = 200), both operand precisions, every epilogue mode and the column sums."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T + N + K)
+    a = torch.randn(T, K, generator=g).to(dev)
+    w = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    aux = torch.randn(T, N, generator=g).to(dev)
+    ref = a.double() @ w.double().t()
+    for prec, tol in ((0, TOL), (1, 2e-3)):
+        ws = _split(w, prec=prec)
+        cs = torch.zeros(K, device=dev)
+        d0 = _gemm3(a, ws, N, bias, prec=prec, colsum=cs)
+        assert rel_err(d0.cpu(), (ref + bias.double()).cpu()) < tol
+        assert rel_err(cs.cpu(), a.double().sum(0).cpu()) < 1e-5
+        d1 = _gemm3(a, ws, N, None, aux, mode=1, prec=prec)
+        assert rel_err(d1.cpu(), (ref + aux.double()).cpu()) < tol
+    ws = _split(w)
+    z, h = _gemm3(a, ws, N, bias, mode=2)
+    assert rel_err(z.cpu(), ref.cpu()) < TOL
+    assert rel_err(h.cpu(), torch.nn.functional.gelu(ref + bias.double()).cpu()) < TOL
+    gg = _gemm3(a, ws, N, bias, aux, mode=3)
+    u = (aux.double() + bias.double()).requires_grad_(True)
+    torch.nn.functional.gelu(u).sum().backward()
+    assert rel_err(gg.cpu(), (ref * u.grad).cpu()) < TOL
