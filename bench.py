@@ -219,6 +219,8 @@ def alg_bytes(name, tag):
     if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
         return tag[0] * (tag[1] + 2 * tag[2]) * 4
     if name == "gemm3":            # tag (T, N, K, mode, precision): a (T, K) in, d (T, N) out, + aux in (modes 1, 3) / d2 out (2)
+        if tag[3] >= 4:            # hs_gemm3_ln: mode tag 4 + (1: shortcut in) + (2: pre-norm tensor out as well); y out
+            return tag[0] * (tag[2] + tag[1] * (1 + ((tag[3] - 4) & 1) + ((tag[3] - 4) >> 1))) * 4
         return tag[0] * (tag[2] + tag[1] * (1 if tag[3] == 0 else 2)) * 4
     return None
 

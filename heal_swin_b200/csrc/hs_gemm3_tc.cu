@@ -28,6 +28,10 @@
 //     MODE_ADD        add the bias and an fp32 tensor of D's shape (aux) -- the residual-shortcut gradient in a dgrad
 //     MODE_GELU       write z = acc (D) and h = dropout(GELU(acc + bias)) (D2): Mlp fc1 + act + drop in one pass
 //     MODE_GELU_GRAD  D = acc * GELU'(aux + bias) * dropmask: the fc2 input gradient through the activation
+//     MODE_LN         D2 = [aux +] LayerNorm_G(acc + bias) * gamma + beta over groups of G consecutive output columns, with
+//                     D = acc + bias (the pre-norm tensor the backward needs) and the row statistics as optional outputs:
+//                     PatchExpand's Linear -> view (B, 4N, C/2) -> LayerNorm (swin_hp_transformer.py:420-430) and the
+//                     `x + norm(branch(x))` tail of a v2 block (:333-338) without a pass of their own over (T, N)
 // aux sub-slabs are brought in by TMA into the staging regions ahead of time and combined in place.
 //
 // Warps: [0, E) epilogue (TMEM lane quadrant = warp % 4), [E, E+8) converters, E+8 A producer, E+9 MMA issuer,
@@ -58,7 +62,8 @@ constexpr int kTeam = 4;               // converter warps per chunk (one per TME
 constexpr int kASlots = 4;             // A-operand slots of 32 TMEM columns behind two 192-column accumulator stages
 constexpr int kACol0 = 2 * 192;
 
-enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3 };
+enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3, MODE_LN = 4 };
+constexpr int kLnExch = 2 * 2 * 128 * 2 * 8;  // MODE_LN: partial row statistics exchanged between the two epilogue groups
 // operand precision: three bf16 MMAs per product (fp32-class), one TF32 MMA (A straight from the fp32 tile, no conversion;
 // input gradients of the tensor-bound stages), one bf16 MMA ("bf16 operands, fp32 accumulate": BASELINE configs[3])
 enum : int { PREC_BF16X3 = 0, PREC_TF32 = 1, PREC_BF16 = 2 };
@@ -79,6 +84,15 @@ struct G3Args {
   uint32_t drop_thresh;
   float drop_scale;
   uint64_t seed;
+  // MODE_LN: LayerNorm over groups of G output columns (G a multiple of 32, <= 192, dividing N and the column chunk)
+  const float* gamma;  // (G)
+  const float* beta;   // (G)
+  float* mean_out;     // (T * N / G) or null: row r of the (T N / G, G) view = token r / (N / G), group r % (N / G)
+  float* rstd_out;
+  int G;
+  float eps;
+  int save_pre;  // D (= acc + bias) is written as well
+  int has_aux;   // D2 += aux
 };
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major
@@ -203,8 +217,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == E + kCvtWarps + 2 && lane == 0) tma_prefetch_desc(&map_w);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_d);
-    if (kAux) tma_prefetch_desc(&map_aux);
-    if (MODE == MODE_GELU) tma_prefetch_desc(&map_d2);
+    if (kAux || MODE == MODE_LN) tma_prefetch_desc(&map_aux);
+    if (MODE == MODE_GELU || MODE == MODE_LN) tma_prefetch_desc(&map_d2);
   }
   tc_fence_before();
   __syncthreads();
@@ -480,6 +494,201 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     const int spw = S > g ? (S - g + NG - 1) / NG : 0;            // slabs of this warp per tile
     const long long my_tiles = t_end > t0 ? (t_end - t0 + tstep - 1) / tstep : 0;
     const long long total = my_tiles * spw;                       // aux loads of this warp over the whole launch
+    if constexpr (MODE == MODE_LN) {
+      // ---------------------------------------------------------------- LayerNorm epilogue
+      // An LN group is G / 32 consecutive slabs of the row a thread owns; its slabs are spread over the NG = 2 epilogue
+      // groups like all others, so the two warps that share a lane quadrant (g = 0, 1; same rows, same lanes) exchange
+      // partial statistics (mean, M2 of their slabs; merged with Chan's formula) through shared memory once per tile.
+      // Pass 1 reads the accumulator for the statistics, pass 2 reads it again (TMEM reads are cheap), normalises and
+      // stores; the accumulator stage is released after the second read.
+      static_assert(NG == 2, "the LN epilogue pairs the two epilogue groups");
+      const int G = a.G, SG = G >> 5;
+      const int ngr = n_this / G;                    // LN groups of this column chunk: 1 or 2
+      const int gpr = a.N / G, grp0 = n0 / G;        // groups per row of D; first group of this chunk
+      const bool save_pre = a.save_pre != 0, has_aux = a.has_aux != 0;
+      const int rq0 = save_pre ? 1 : 0, rq = rw - rq0;  // region 0: pre-norm stores; regions [rq0, rw): aux in / D2 out
+      const int nst = save_pre ? 2 : 1;
+      float2* exch = reinterpret_cast<float2*>(s_colsum);  // [tile parity][g][row of the tile][group]
+      const float inv_g = 1.0f / (float)G;
+      auto slabs_of = [&](int gg, int j) {           // slabs of LN group j that epilogue group gg owns
+        const int lo = j * SG, hi = min((j + 1) * SG, S);
+        int c = 0;
+        for (int s2 = lo; s2 < hi; ++s2) c += ((s2 & 1) == gg);
+        return c;
+      };
+      auto wait_read_n = [&](int n) {
+        switch (n) {
+          case 0: tma_store_wait_read<0>(); break;
+          case 1: tma_store_wait_read<1>(); break;
+          case 2: tma_store_wait_read<2>(); break;
+          case 3: tma_store_wait_read<3>(); break;
+          case 4: tma_store_wait_read<4>(); break;
+          default: tma_store_wait_read<5>(); break;
+        }
+      };
+      auto issue_aux_ln = [&](long long u) {         // slab use u -> its staging region (lane 0 only)
+        const long long tile = t0 + (u / spw) * tstep;
+        const int s = g + NG * (int)(u % spw);
+        const int reg = rq0 + (int)(u % rq);
+        mbar_arrive_expect_tx(&my_full[reg], kRegion);
+        tma_load_2d(my + reg * kRegion, &map_aux, &my_full[reg], n0 + 32 * s, (int)(tile * kBM) + 32 * q);
+      };
+      if (has_aux && lane == 0)
+        for (long long u = 0; u < rq && u < total; ++u) issue_aux_ln(u);
+      auto merge = [](float& n, float& mean, float& m2, float nb, float mb, float m2b) {
+        const float nt = n + nb;
+        if (nt > 0.f) {
+          const float delta = mb - mean, f = nb / nt;
+          mean += delta * f;
+          m2 += m2b + delta * delta * n * f;
+        }
+        n = nt;
+      };
+      // The refill of a shortcut region (wait until its store has read it, request the sub-slab rq uses ahead) is not done
+      // right after the store -- lane 0 would sit in that wait while the warp still owes the accumulator stage its last
+      // reads -- but at the next point where the warp has nothing urgent: after the next accumulator read, or at the top
+      // of the next tile.
+      long long refill = -1;
+      auto flush_refill = [&]() {
+        if (refill >= 0) {
+          tma_store_wait_read<0>();
+          issue_aux_ln(refill);
+          refill = -1;
+        }
+      };
+      long long u = 0, it = 0;
+      for (long long tile = t0; tile < t_end; tile += tstep, ++it) {
+        const int as = (int)(it & 1);
+        if (lane == 0) flush_refill();
+        mbar_wait(&acc_full[as], ((uint32_t)(it >> 1)) & 1);
+        tc_fence_after();
+        const long long grow = tile * kBM + q * 32 + lane;
+        const uint32_t acc_addr = tmem + lane_addr + (uint32_t)as * a.stage_cols;
+        // ---- pass 1: statistics of my slabs, per LN group
+        float n_0 = 0.f, m_0 = 0.f, q_0 = 0.f, n_1 = 0.f, m_1 = 0.f, q_1 = 0.f;
+        for (int s = g; s < S; s += NG) {
+          uint32_t acc[32];
+          tmem_ld32(acc_addr + 32 * s, acc);
+          tmem_wait_ld();
+          const int jc = n0 + 32 * s;
+          float piv = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + jc + 4 * c));
+            const float v0 = __uint_as_float(acc[4 * c + 0]) + bv.x, v1 = __uint_as_float(acc[4 * c + 1]) + bv.y;
+            const float v2 = __uint_as_float(acc[4 * c + 2]) + bv.z, v3 = __uint_as_float(acc[4 * c + 3]) + bv.w;
+            if (c == 0) piv = v0;   // pivot inside the data range: the one-pass variance below does not cancel
+            const float d0 = v0 - piv, d1 = v1 - piv, d2 = v2 - piv, d3 = v3 - piv;
+            s1 += (d0 + d1) + (d2 + d3);
+            s2 = fmaf(d0, d0, s2); s2 = fmaf(d1, d1, s2); s2 = fmaf(d2, d2, s2); s2 = fmaf(d3, d3, s2);
+          }
+          const float mb = piv + s1 * (1.0f / 32.0f), m2b = fmaxf(s2 - s1 * s1 * (1.0f / 32.0f), 0.f);
+          if (s / SG == 0) merge(n_0, m_0, q_0, 32.f, mb, m2b);
+          else merge(n_1, m_1, q_1, 32.f, mb, m2b);
+        }
+        float2* ex = exch + (size_t)(it & 1) * (2 * 128 * 2);
+        ex[(g * 128 + q * 32 + lane) * 2 + 0] = make_float2(m_0, q_0);
+        ex[(g * 128 + q * 32 + lane) * 2 + 1] = make_float2(m_1, q_1);
+        named_bar_sync(2 + q, 64);  // the two warps of this lane quadrant (double-buffered: one barrier per tile)
+        float mean0, rstd0, mean1 = 0.f, rstd1 = 0.f;
+        {
+          const float2 o0 = ex[((g ^ 1) * 128 + q * 32 + lane) * 2 + 0], o1 = ex[((g ^ 1) * 128 + q * 32 + lane) * 2 + 1];
+          // merge in the fixed order (group 0, group 1) so that both warps compute bit-identical statistics
+          float na = 32.f * slabs_of(0, 0), ma = g == 0 ? m_0 : o0.x, qa = g == 0 ? q_0 : o0.y;
+          merge(na, ma, qa, 32.f * slabs_of(1, 0), g == 0 ? o0.x : m_0, g == 0 ? o0.y : q_0);
+          mean0 = ma;
+          rstd0 = rsqrtf(qa * inv_g + a.eps);
+          if (ngr > 1) {
+            float nb = 32.f * slabs_of(0, 1), mb = g == 0 ? m_1 : o1.x, qb = g == 0 ? q_1 : o1.y;
+            merge(nb, mb, qb, 32.f * slabs_of(1, 1), g == 0 ? o1.x : m_1, g == 0 ? o1.y : q_1);
+            mean1 = mb;
+            rstd1 = rsqrtf(qb * inv_g + a.eps);
+          }
+        }
+        if (g == 0 && a.mean_out && grow < a.T) {
+          a.mean_out[grow * gpr + grp0] = mean0;
+          a.rstd_out[grow * gpr + grp0] = rstd0;
+          if (ngr > 1) {
+            a.mean_out[grow * gpr + grp0 + 1] = mean1;
+            a.rstd_out[grow * gpr + grp0 + 1] = rstd1;
+          }
+        }
+        // ---- pass 2: normalise and store
+        if (spw == 0) {
+          tc_fence_before();
+          mbar_arrive(&acc_empty[as]);
+        }
+        for (int s = g; s < S; s += NG, ++u) {
+          uint32_t acc[32];
+          tmem_ld32(acc_addr + 32 * s, acc);
+          tmem_wait_ld();
+          if (s + NG >= S) {  // this thread's last read of the accumulator stage
+            tc_fence_before();
+            mbar_arrive(&acc_empty[as]);
+          }
+          if (lane == 0) flush_refill();
+          const int jc = n0 + 32 * s;
+          const bool second = (s / SG) != 0;
+          const float mean = second ? mean1 : mean0, rstd = second ? rstd1 : rstd0;
+          const int gc = 32 * s - (second ? G : 0);  // column inside the LN group
+          if (save_pre) {
+            if (lane == 0) tma_store_wait_read<1>();  // my previous pre-norm store has read region 0
+            __syncwarp();
+            const uint32_t brow = my_u32 + lane * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + jc + 4 * c));
+              sts_f4(brow + ((c ^ sw) << 4),
+                     make_float4(__uint_as_float(acc[4 * c + 0]) + bv.x, __uint_as_float(acc[4 * c + 1]) + bv.y,
+                                 __uint_as_float(acc[4 * c + 2]) + bv.z, __uint_as_float(acc[4 * c + 3]) + bv.w));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_d, my, jc, (int)(tile * kBM) + 32 * q);
+              tma_store_commit();
+            }
+          }
+          const int reg = rq0 + (int)(u % rq);
+          if (has_aux) {
+            mbar_wait(&my_full[reg], ((uint32_t)(u / rq)) & 1);  // the shortcut's sub-slab has landed
+          } else {
+            // the D2 store that used this region rq uses ago must have read it
+            if (lane == 0) wait_read_n((rq - 1) * nst + (nst - 1));
+            __syncwarp();
+          }
+          const uint32_t brow = my_u32 + reg * kRegion + lane * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const uint32_t p = brow + ((c ^ sw) << 4);
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.bias) bv = __ldg(reinterpret_cast<const float4*>(a.bias + jc + 4 * c));
+            const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + gc + 4 * c));
+            const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta + gc + 4 * c));
+            float4 o;
+            o.x = fmaf((__uint_as_float(acc[4 * c + 0]) + bv.x - mean) * rstd, gm.x, bt.x);
+            o.y = fmaf((__uint_as_float(acc[4 * c + 1]) + bv.y - mean) * rstd, gm.y, bt.y);
+            o.z = fmaf((__uint_as_float(acc[4 * c + 2]) + bv.z - mean) * rstd, gm.z, bt.z);
+            o.w = fmaf((__uint_as_float(acc[4 * c + 3]) + bv.w - mean) * rstd, gm.w, bt.w);
+            if (has_aux) {
+              const float4 x = lds_f4(p);
+              o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+            }
+            sts_f4(p, o);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_d2, my + reg * kRegion, jc, (int)(tile * kBM) + 32 * q);
+            tma_store_commit();
+            if (has_aux && u + rq < total) refill = u + rq;  // this region's next shortcut sub-slab (see flush_refill)
+          }
+        }
+      }
+      if (lane == 0) tma_store_wait<0>();
+    } else {
     auto issue_aux = [&](long long u) {                           // slab use u -> its staging region (lane 0 only)
       const long long tile = t0 + (u / spw) * tstep;
       const int s = g + NG * (int)(u % spw);
@@ -581,6 +790,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       }
     }
     if (lane == 0) tma_store_wait<0>();
+    }  // (plain / add / GELU epilogues)
   }
   tc_fence_before();
   __syncthreads();
@@ -650,11 +860,15 @@ int plan(G3Args& a, int mode, int E) {
   a.tiles = (a.T + kBM - 1) / kBM;
   const int nk = (a.K + 31) / 32;
   const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
-  const int rw_min = aux ? 2 : 1, rw_max = aux ? 3 : 2;
+  const bool ln = (mode == MODE_LN);
+  // (LN: one region for the pre-norm stores + two for shortcut-in / result-out, so that a shortcut sub-slab is requested
+  // two slab uses -- about one tile -- before it is needed)
+  const int rw_min = ln ? (a.save_pre ? 3 : 2) : (aux ? 2 : 1), rw_max = (aux || ln) ? 3 : 2;
   // tensor-bound launches (streamed W, long contraction) keep A in shared memory and use 256-column stages: fewer, wider
   // MMAs (ncu: 69 % tensor-pipe active against 59 % with 192-column chunks); HBM-bound launches take A through TMEM
   a.ss = (a.prec == PREC_TF32 || (a.prec == PREC_BF16X3 && (long long)a.N * a.K > 130ll * (a.N + a.K) && a.K >= 256)) ? 1 : 0;
   if (const char* e = getenv("HEALSWIN_GEMM3_SS")) a.ss = (a.prec == PREC_TF32) ? 1 : (atoi(e) != 0 && a.prec == PREC_BF16X3);
+  if (ln) a.ss = 0;  // the LN epilogue works on 192-column stages whose chunks hold whole LN groups
   a.stage_cols = a.ss ? 256 : 192;
   // CTA pairs (cta_group::2, M = 256): each CTA of a pair stages only half of every W slice, which halves the B-operand
   // traffic of its shared memory -- the co-limiter of the ss modes (per K = 16 step and CTA: 76 KB of shared-memory
@@ -670,23 +884,33 @@ int plan(G3Args& a, int mode, int E) {
     const int v = atoi(e);
     if (v >= 32 && v <= a.stage_cols && v % 16 == 0 && v < first) first = v;
   }
+  if (ln) {  // one or two whole LN groups per chunk
+    first = (192 / a.G >= 2 ? 2 : 1) * a.G;
+    if (first > a.N) first = a.N;
+  }
   const int cand[7] = {first, 192, 160, 128, 96, 64, 32};
   int best_ring = 0;
-  for (int ci = 0; ci < 7; ++ci) {
+  for (int ci = 0; ci < (ln ? 1 : 7); ++ci) {
     const int stride = cand[ci];
     if (stride > first || (ci > 0 && stride == first)) continue;
     const int box = (stride + 31) / 32 * 32;
     const int w_slice = (a.pair ? box / 2 : box) * 128;
-    const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0);
+    const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0) + (ln ? kLnExch : 0);
     const int resident = (!a.pair && (long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
     int wring = a.pair ? (nk < 4 ? nk : 4) : (nk < 3 ? nk : 3);  // (a pair's slices are half the size)
     if (const char* e = getenv("HEALSWIN_GEMM3_WRING")) {  // experiments only
       const int v = atoi(e);
       if (v >= 2 && v <= kMaxWRing && v <= nk) wring = v;
     }
-    const long long w_bytes = (long long)(resident ? nk : wring) * w_slice;
+    long long w_bytes = (long long)(resident ? nk : wring) * w_slice;
     long long left = kSmemAvail - w_bytes - staging_min;
     int ring = left > 0 ? (int)(left / kChunk) : 0;
+    if (ln && !resident && ring < 4 && wring == 3) {  // the LN staging is large: two W slices in flight are enough (L2 hits)
+      wring = 2;
+      w_bytes = (long long)wring * w_slice;
+      left = kSmemAvail - w_bytes - staging_min;
+      ring = left > 0 ? (int)(left / kChunk) : 0;
+    }
     if (ring > kMaxRing) ring = kMaxRing;
     ring &= ~1;  // even: chunk c and chunk c + ring are converted by the same team
     if (ring <= best_ring) continue;
@@ -720,7 +944,7 @@ template <int E>
 size_t smem_bytes(const G3Args& a) {
   const int nk = (a.K + 31) / 32, w_slice = (a.pair ? a.n_box / 2 : a.n_box) * 128;
   return (size_t)(a.resident ? nk : a.wring) * w_slice + (size_t)a.ring * kChunk + (size_t)E * a.rw * kRegion +
-         (a.colsum ? (size_t)nk * 128 : 0) + 1024;
+         (a.colsum ? (size_t)nk * 128 : 0) + (a.G > 0 ? (size_t)kLnExch : 0) + 1024;
 }
 
 struct Maps {
@@ -775,8 +999,10 @@ int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, floa
   per_chunk = per_chunk / cs * cs;
   if (per_chunk < cs) per_chunk = cs;
   if ((rc = make_map_bf16(&m.w, w_dev, a.N, 2ll * ((a.K + 31) / 32 * 32), 64, a.n_box / cs))) return rc;
-  return a.pair ? launch_kernel<E, MODE, true>(m, a, smem, per_chunk, stream)
-                : launch_kernel<E, MODE, false>(m, a, smem, per_chunk, stream);
+  if constexpr (MODE == MODE_LN) return launch_kernel<E, MODE, false>(m, a, smem, per_chunk, stream);  // (never a pair)
+  else
+    return a.pair ? launch_kernel<E, MODE, true>(m, a, smem, per_chunk, stream)
+                  : launch_kernel<E, MODE, false>(m, a, smem, per_chunk, stream);
 }
 
 }  // namespace
@@ -830,6 +1056,33 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
       if (K <= 256) return launch<16, MODE_GELU_GRAD>(a_dev, wsplit_dev, aux_dev, d_dev, nullptr, a, st);
       return launch<8, MODE_GELU_GRAD>(a_dev, wsplit_dev, aux_dev, d_dev, nullptr, a, st);
   }
+}
+
+int hs_gemm3_ln_supported(int64_t T, int N, int K, int G) {
+  return (hs_gemm3_supported(T, N, K) && G >= 32 && G <= 192 && G % 32 == 0 && N % G == 0) ? 1 : 0;
+}
+
+int hs_gemm3_ln(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* gamma_dev,
+                const float* beta_dev, const float* aux_dev, float* pre_dev, float* y_dev, float* mean_dev, float* rstd_dev,
+                int64_t T, int N, int K, int G, float eps, int precision, void* stream) {
+  HS_REQUIRE(a_dev && wsplit_dev && gamma_dev && beta_dev && y_dev && T > 0, "hs_gemm3_ln: bad arguments");
+  HS_REQUIRE(precision == PREC_BF16X3 || precision == PREC_BF16, "hs_gemm3_ln: precision must be bf16x3 or bf16");
+  HS_REQUIRE((mean_dev == nullptr) == (rstd_dev == nullptr), "hs_gemm3_ln: mean and rstd go together");
+  if (!hs_gemm3_ln_supported(T, N, K, G))
+    return hs::fail(HS_ERR_UNSUPPORTED,
+                    "hs_gemm3_ln: shape T=%lld N=%d K=%d G=%d is not covered (G a multiple of 32, <= 192, dividing N)",
+                    (long long)T, N, K, G);
+  HS_REQUIRE(!((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(wsplit_dev) |
+                reinterpret_cast<uintptr_t>(bias_dev) | reinterpret_cast<uintptr_t>(aux_dev) |
+                reinterpret_cast<uintptr_t>(pre_dev) | reinterpret_cast<uintptr_t>(y_dev) |
+                reinterpret_cast<uintptr_t>(gamma_dev) | reinterpret_cast<uintptr_t>(beta_dev)) & 15),
+             "hs_gemm3_ln: tensors must be 16-byte aligned");
+  G3Args a{};
+  a.bias = bias_dev; a.T = T; a.N = N; a.K = K; a.prec = precision;
+  a.drop_scale = 1.0f;
+  a.gamma = gamma_dev; a.beta = beta_dev; a.mean_out = mean_dev; a.rstd_out = rstd_dev;
+  a.G = G; a.eps = eps; a.save_pre = pre_dev ? 1 : 0; a.has_aux = aux_dev ? 1 : 0;
+  return launch<8, MODE_LN>(a_dev, wsplit_dev, aux_dev, pre_dev ? pre_dev : y_dev, y_dev, a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -37,7 +37,7 @@ __device__ __forceinline__ float group_sum(float v, int T) {
 }
 
 template <int V, bool kDrop>
-__global__ void __launch_bounds__(kThreads, (V <= 3 ? (kDrop ? 4 : 6) : (V <= 6 ? 3 : 1)))
+__global__ void __launch_bounds__(kThreads, (V <= 3 ? (kDrop ? 4 : 5) : (V <= 6 ? 3 : 1)))
 ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias, const float4* __restrict__ res,
               const float4* __restrict__ gamma, const float4* __restrict__ beta, float4* __restrict__ y,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int T, float eps,
@@ -51,9 +51,13 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
   for (long long base = warp0 * rpw; base < rows; base += stride) {
     const long long row = base + sub;
     const bool ok = row < rows;
-    float4 a[V];
+    float4 a[V], r4[V];
     float s = 0.f;
     const uint32_t dkey = kDrop ? hs::drop_row_key(ex.seed, row) : 0u;
+    // the residual is requested together with x: issued after the two row reductions its latency was exposed once per row
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+      r4[v] = (ok && res) ? __ldcs(res + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       a[v] = ok ? __ldcs(x + row * C4 + t + T * v) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -82,10 +86,7 @@ ln_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ pre_bias,
         o.y = fmaf(a[v].y * rs, g.y, b.y) * osc;
         o.z = fmaf(a[v].z * rs, g.z, b.z) * osc;
         o.w = fmaf(a[v].w * rs, g.w, b.w) * osc;
-        if (res) {
-          const float4 r4 = __ldcs(res + row * C4 + t + T * v);
-          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-        }
+        o.x += r4[v].x; o.y += r4[v].y; o.z += r4[v].z; o.w += r4[v].w;
         y[row * C4 + t + T * v] = o;
       }
       if (t == 0 && mean_out) {

@@ -69,6 +69,14 @@ class Mlp(nn.Module):
         y, shortcut = self._core(x, fork=True)
         return y, self.fc2.bias, self._drop_p(), shortcut
 
+    def ln_fusable(self, x, norm):
+        """Whether ``x + norm(self(x))`` runs with the LayerNorm and the residual add in fc2's epilogue."""
+        return self._fusable() and self._drop_p() == 0.0 and ops.mlp_ln_supported(x, self.fc1, self.fc2, norm)
+
+    def forward_ln(self, x, norm):
+        """``x + norm(self(x))``: fc1 + GELU, then fc2 + bias + LayerNorm + residual, two launches (``ln_fusable``)."""
+        return ops.mlp_ln(x, self.fc1, self.fc2, norm)
+
     def _core(self, x, fork=False):
         """fc2(drop(GELU(fc1(x)))) without fc2's bias: one fused autograd node when the shapes allow it."""
         if ops.mlp_supported(x, self.fc1, self.fc2):
@@ -133,16 +141,19 @@ class WindowAttention(nn.Module):
         out = self._core(ops.linear(x, self.qkv.weight, self.qkv.bias), window_size, src, groups, None)
         return self.proj_drop(ops.linear(out, self.proj.weight, self.proj.bias))
 
-    def forward_tokens_split(self, x, window_size, src=None, groups=None):
+    def forward_tokens_split(self, x, window_size, src=None, groups=None, defer_proj=False):
         """As forward_tokens, but returns (proj output WITHOUT its bias and WITHOUT proj_drop, that bias or None, the
         dropout probability still to be applied, the input as residual shortcut) so that the caller can fuse bias and
         dropout into the LayerNorm that follows (v2 norm placement); the shortcut's gradient is folded into the qkv
-        input-gradient GEMM."""
+        input-gradient GEMM.  With ``defer_proj`` the first item is the attention output BEFORE ``self.proj``: the caller
+        runs the projection itself, with the LayerNorm and the residual add in its epilogue (``_residual_tail``)."""
         if self.proj.bias is None:
             return self.forward_tokens(x, window_size, src, groups), None, 0.0, x
         qkv, shortcut = ops.linear(x, self.qkv.weight, self.qkv.bias, fork=True)
         out = self._core(qkv, window_size, src, groups, None)
-        return ops.linear(out, self.proj.weight), self.proj.bias, (self.proj_drop.p if self.training else 0.0), shortcut
+        if not defer_proj:
+            out = ops.linear(out, self.proj.weight)
+        return out, self.proj.bias, (self.proj_drop.p if self.training else 0.0), shortcut
 
     def forward(self, x, mask=None):
         """x: (num_windows*B, N, C); mask: (num_windows, N, N) additive or None   [:124-174]"""
@@ -217,10 +228,11 @@ class SwinTransformerBlock(nn.Module):
             x = ops.layer_norm(x, self.norm1)
         # shift + partition + W-MSA/SW-MSA + reverse + shift back, one kernel chain   [:319-330]
         if self.use_v2_norm_placement:
+            defer = self.attn.proj.bias is not None
             x, pre_bias, pdrop, shortcut = self.attn.forward_tokens_split(x, self.window_size, self._hs_src,
-                                                                          self._hs_groups)
-        else:
-            x, pre_bias, pdrop = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups), None, 0.0
+                                                                          self._hs_groups, defer_proj=defer)
+            return _residual_tail(self, shortcut, x, pre_bias, pdrop, proj=self.attn.proj if defer else None)
+        x, pre_bias, pdrop = self.attn.forward_tokens(x, self.window_size, self._hs_src, self._hs_groups), None, 0.0
         return _residual_tail(self, shortcut, x, pre_bias, pdrop)
 
     def extra_repr(self) -> str:
@@ -228,15 +240,26 @@ class SwinTransformerBlock(nn.Module):
                 f" window_size={self.window_size}, shift_size={self.shift_size}, mlp_ratio={self.mlp_ratio}")
 
 
-def _residual_tail(blk, shortcut, x, pre_bias=None, pre_drop=0.0):
+def _residual_tail(blk, shortcut, x, pre_bias=None, pre_drop=0.0, proj=None):
     """The two residual branches after the attention   [swin_hp_transformer.py:333-338 / swin_transformer.py:394-401].
     ``x`` is the attention branch, ``pre_bias`` / ``pre_drop`` the not-yet-applied bias and dropout of its output
-    projection.  In the v2 placement every ``shortcut + drop_path(norm(drop(branch + bias)))`` is ONE fused launch
-    (bias, dropout, LayerNorm, per-sample stochastic-depth scale, residual add)."""
+    projection (``proj``: that projection itself, when the caller deferred it).  In the v2 placement every
+    ``shortcut + drop_path(norm(drop(branch + bias)))`` is ONE fused launch (bias, dropout, LayerNorm, per-sample
+    stochastic-depth scale, residual add) -- and without dropout / stochastic depth, where the GEMM covers the width
+    (LayerNorm over <= 192 channels), it is not a launch at all but the epilogue of the proj / fc2 GEMM."""
     dp = blk.drop_path
     scale_of = (lambda t: dp.sample_scale(t)) if isinstance(dp, DropPath) else (lambda t: None)
     if blk.use_v2_norm_placement:
-        x = ops.layer_norm(x, blk.norm1, residual=shortcut, pre_bias=pre_bias, row_scale=scale_of(x), in_drop=pre_drop)
+        plain = not (isinstance(dp, DropPath) and dp.training and dp.drop_prob)  # no stochastic-depth scale to apply
+        if proj is not None and plain and pre_drop == 0.0 and ops.linear_ln_supported(x, proj.weight, blk.norm1):
+            x = ops.linear_ln(x, proj.weight, pre_bias, blk.norm1, residual=shortcut)
+        else:
+            if proj is not None:
+                x = ops.linear(x, proj.weight)
+            x = ops.layer_norm(x, blk.norm1, residual=shortcut, pre_bias=pre_bias, row_scale=scale_of(x),
+                               in_drop=pre_drop)
+        if plain and blk.mlp.ln_fusable(x, blk.norm2):
+            return blk.mlp.forward_ln(x, blk.norm2)
         h, hb, hdrop, x = blk.mlp.forward_split(x)
         return ops.layer_norm(h, blk.norm2, residual=x, pre_bias=hb, row_scale=scale_of(x), in_drop=hdrop)
     x = shortcut + dp(x)
@@ -280,7 +303,14 @@ class PatchExpand(nn.Module):
 
     def forward(self, x):
         if isinstance(self.expand, nn.Linear):
-            x = ops.linear(x, self.expand.weight, self.expand.bias)
+            w = self.expand.weight
+            if w.shape[0] % 4 == 0 and ops.linear_ln_supported(x, w, self.norm) \
+                    and self.norm.normalized_shape[0] == w.shape[0] // 4:
+                # fused gather + linear + norm: the four children of a token are the four C/2-wide column groups of its
+                # expanded row, so the LayerNorm of the (B, 4N, C/2) view runs in the GEMM's epilogue
+                B, N, _ = x.shape
+                return ops.linear_ln(x, w, self.expand.bias, self.norm).view(B, 4 * N, w.shape[0] // 4)
+            x = ops.linear(x, w, self.expand.bias)
         B, N, C = x.shape
         return ops.layer_norm(x.contiguous().view(B, 4 * N, C // 4), self.norm)
 

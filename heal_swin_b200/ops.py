@@ -557,6 +557,114 @@ def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, s
     return (d, d2) if mode == _lib.GEMM_GELU else d
 
 
+_FUSED_LINEAR_LN = os.environ.get("HEALSWIN_FUSED_LINEAR_LN", "1") == "1"
+
+
+def _gemm3_ln(a2, wsplit, N, bias, gamma, beta, G, eps, aux=None, save=True):
+    """hs_gemm3_ln: y = [aux +] LayerNorm_G(a2 @ W^T + bias) * gamma + beta in the GEMM's epilogue.  Returns
+    (y, pre, mean, rstd); the last three (what hs_layernorm_bwd needs) only with ``save``."""
+    T, K = a2.shape
+    y = torch.empty((T, N), device=a2.device, dtype=torch.float32)
+    pre = torch.empty_like(y) if save else None
+    mean = torch.empty((T * (N // G),), device=a2.device, dtype=torch.float32) if save else None
+    rstd = torch.empty_like(mean) if save else None
+    prec = _fwd_prec()
+    STATS.launch("gemm3", lib.hs_gemm3_ln, ptr(a2), ptr(wsplit), ptr(bias), ptr(gamma), ptr(beta), ptr(aux), ptr(pre), ptr(y),
+                 ptr(mean), ptr(rstd), T, N, K, G, C.c_float(eps), prec, current_stream(),
+                 tag=(T, N, K, 4 + (1 if aux is not None else 0) + (2 if save else 0), prec))
+    return y, pre, mean, rstd
+
+
+def _ln_tail_bwd(dy2, pre, mean, rstd, gamma, need_w, need_b, need_lin_bias=False):
+    """Backward of the LN epilogue: d(pre) (T, N), d(gamma), d(beta) from dy over the (T N / G, G) view, and -- for G = N,
+    on request -- the column sums of d(pre), i.e. the gradient of the linear's bias, from the same pass (the kernel's
+    pre-bias path with a zero pre-bias)."""
+    G = gamma.numel()
+    rows = pre.numel() // G
+    dpre = torch.empty_like(pre)
+    dw = torch.zeros(G, device=pre.device, dtype=torch.float32) if need_w else None
+    db = torch.zeros(G, device=pre.device, dtype=torch.float32) if need_b else None
+    lin_bias = need_lin_bias and G == pre.shape[-1]
+    pb = torch.zeros(G, device=pre.device, dtype=torch.float32) if lin_bias else None
+    dpb = torch.zeros(G, device=pre.device, dtype=torch.float32) if lin_bias else None
+    STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(pre), ptr(pb), ptr(mean), ptr(rstd), ptr(gamma),
+                 None, 0, C.c_float(0.0), C.c_uint64(0), ptr(dpre), ptr(dw), ptr(db), ptr(dpb), rows, G,
+                 current_stream(), tag=(rows, G))
+    return dpre, dw, db, dpb
+
+
+def _fusable_ln(norm, N) -> bool:
+    return bool(_FUSED_LINEAR_LN and isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine
+                and norm.bias is not None and len(norm.normalized_shape) == 1 and N % norm.normalized_shape[0] == 0)
+
+
+def linear_ln_supported(x, weight, norm) -> bool:
+    """Whether ``linear_ln`` runs as ONE launch (LayerNorm in the GEMM epilogue): affine LayerNorm over G = a divisor of
+    the output width, G a multiple of 32 and <= 192."""
+    N = weight.shape[0]
+    return bool(gemm3_ok(x, weight) and _fusable_ln(norm, N)
+                and lib.hs_gemm3_ln_supported(x.numel() // x.shape[-1], N, weight.shape[1], norm.normalized_shape[0]))
+
+
+class _LinearLnFn(torch.autograd.Function):
+    """``[residual +] LayerNorm_G(F.linear(x, weight, bias))`` with the normalisation (over groups of G = gamma.numel()
+    output columns), the affine and the residual add in the GEMM's epilogue (hs_gemm3_ln).  Backward: hs_layernorm_bwd on
+    the saved pre-norm tensor, then the linear's input / weight / bias gradients as in _LinearFn."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, beta, residual, eps):
+        ctx.set_materialize_grads(False)
+        N, K = weight.shape
+        x2 = _f32c(x).reshape(-1, K)
+        res2 = _f32c(residual).reshape(-1, N) if residual is not None else None
+        save = any(ctx.needs_input_grad[:5])
+        y, pre, mean, rstd = _gemm3_ln(x2, split_weight(weight), N, _f32c(bias), _f32c(gamma), _f32c(beta), gamma.numel(),
+                                       eps, res2, save)
+        if save:
+            ctx.save_for_backward(x2, weight, gamma, pre, mean, rstd)
+        ctx.meta = (x.shape, bias is not None, residual is not None)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xshape, has_bias, has_res = ctx.meta
+        if dy is None:
+            return (None,) * 7
+        x2, weight, gamma, pre, mean, rstd = ctx.saved_tensors
+        N, K = weight.shape
+        dy2 = _f32c(dy).reshape(-1, N)
+        need_b = has_bias and ctx.needs_input_grad[2]
+        dpre, dgamma, dbeta, db = _ln_tail_bwd(dy2, pre, mean, rstd, _f32c(gamma), ctx.needs_input_grad[3],
+                                               ctx.needs_input_grad[4], need_b)
+        dx = dw = None
+        need_b = need_b and db is None
+        b_in_wgrad = need_b and ctx.needs_input_grad[1] and _wgrad_fuses_bias(dpre, x2)
+        if ctx.needs_input_grad[0]:
+            if need_b and not b_in_wgrad:
+                dx, db = _dgrad(dpre, weight, None, xshape, want_bias_grad=True)
+            else:
+                dx = _dgrad(dpre, weight, None, xshape)
+        if ctx.needs_input_grad[1]:
+            dw, db2 = _wgrad(dpre, x2, need_b and db is None)
+            db = db if db is not None else db2
+        elif need_b and db is None:
+            db = dpre.sum(0)
+        return dx, dw, db, dgamma, dbeta, (dy if has_res else None), None
+
+
+def linear_ln(x, weight, bias, norm, residual=None):
+    """``[residual +] norm(F.linear(x, weight, bias).view(..., N // G, G)).view(..., N)`` for an affine LayerNorm over
+    G = norm.normalized_shape[0] columns: one launch where ``linear_ln_supported``, else the linear and the LayerNorm
+    as two launches.  The caller reshapes the result (PatchExpand: (B, N, 2C) -> (B, 4N, C/2))."""
+    N = weight.shape[0]
+    if linear_ln_supported(x, weight, norm) and (residual is None or residual.is_cuda):
+        return _LinearLnFn.apply(x, weight, bias, norm.weight, norm.bias, residual, float(norm.eps))
+    G = norm.normalized_shape[0]
+    y = linear(x, weight, bias)
+    y = layer_norm(y.reshape(*y.shape[:-1], N // G, G), norm).reshape(y.shape)
+    return y if residual is None else residual + y
+
+
 def _gemm_fwd(x2, weight, bias):
     """x2 (T, K) @ weight (N, K)^T + bias."""
     if gemm3_ok(x2, weight):
@@ -673,27 +781,48 @@ class _MlpFn(torch.autograd.Function):
     (and fc1's bias gradient) from the token-split wgrad kernel."""
 
     @staticmethod
-    def forward(ctx, x, w1, b1, w2, drop, seed, fork):
+    def forward(ctx, x, w1, b1, w2, drop, seed, fork, b2=None, gamma=None, beta=None, eps=0.0):
         ctx.set_materialize_grads(False)
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
         z, h = _gemm3(x2, split_weight(w1), w1.shape[0], _f32c(b1), None, _lib.GEMM_GELU, drop, seed)
-        y = _gemm3(h, split_weight(w2), w2.shape[0])
-        ctx.save_for_backward(x2, w1, b1, w2, z, h)
         ctx.drop = (float(drop), int(seed))
         ctx.xshape = x.shape
+        ctx.ln = gamma is not None
+        if ctx.ln:
+            # the whole second half of a v2 block: x + norm2(fc2(h) + b2) -- bias, LayerNorm and the residual add in
+            # fc2's epilogue (swin_hp_transformer.py:336-338)
+            y, pre, mean, rstd = _gemm3_ln(h, split_weight(w2), w2.shape[0], _f32c(b2), _f32c(gamma), _f32c(beta),
+                                           gamma.numel(), eps, x2, True)
+            ctx.save_for_backward(x2, w1, b1, w2, z, h, gamma, pre, mean, rstd)
+            ctx.has_b2 = b2 is not None
+            return y.view(*x.shape[:-1], w2.shape[0])
+        y = _gemm3(h, split_weight(w2), w2.shape[0])
+        ctx.save_for_backward(x2, w1, b1, w2, z, h)
         y = y.view(*x.shape[:-1], w2.shape[0])
         return (y, x.view_as(x)) if fork else y
 
     @staticmethod
     def backward(ctx, dy, d_pass=None):
         if dy is None:
-            return d_pass, None, None, None, None, None, None
-        x2, w1, b1, w2, z, h = ctx.saved_tensors
-        T, K = x2.shape
-        J, Cout = w1.shape[0], w2.shape[0]
-        dy2 = _f32c(dy).reshape(T, Cout)
-        dw2, _ = _wgrad(dy2, h, False)
+            return (d_pass,) + (None,) * 10
+        db2 = dgamma = dbeta = None
+        if ctx.ln:
+            x2, w1, b1, w2, z, h, gamma, pre, mean, rstd = ctx.saved_tensors
+            d_pass = dy  # the residual shortcut: added in fc1's input-gradient epilogue
+            need_b2 = ctx.has_b2 and ctx.needs_input_grad[7]
+            dy2, dgamma, dbeta, db2 = _ln_tail_bwd(_f32c(dy).reshape(pre.shape), pre, mean, rstd, _f32c(gamma),
+                                                   ctx.needs_input_grad[8], ctx.needs_input_grad[9], need_b2)
+            T, K = x2.shape
+            J, Cout = w1.shape[0], w2.shape[0]
+            dw2, db2b = _wgrad(dy2, h, need_b2 and db2 is None)
+            db2 = db2 if db2 is not None else db2b
+        else:
+            x2, w1, b1, w2, z, h = ctx.saved_tensors
+            T, K = x2.shape
+            J, Cout = w1.shape[0], w2.shape[0]
+            dy2 = _f32c(dy).reshape(T, Cout)
+            dw2, _ = _wgrad(dy2, h, False)
         if _TF32_MLP_DGRAD and lib.hs_mlp_dgrad_gelu_supported(T, Cout, J):
             dz = torch.empty_like(z)
             STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1),
@@ -711,7 +840,7 @@ class _MlpFn(torch.autograd.Function):
                 dx, db1 = _dgrad(dz, w1, d_pass, ctx.xshape, want_bias_grad=True)
         dw1, db1b = _wgrad(dz, x2, db1 is None)
         db1 = db1 if db1 is not None else db1b
-        return dx, dw1, db1, dw2, None, None, None
+        return dx, dw1, db1, dw2, None, None, None, db2, dgamma, dbeta, None
 
 
 def mlp_supported(x, fc1, fc2):
@@ -731,6 +860,24 @@ def mlp_core(x, fc1, fc2, drop=0.0, seed=None, fork=False):
     drop = float(drop)
     seed = _pick_seed(seed, drop)
     return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0), bool(fork))
+
+
+def mlp_ln_supported(x, fc1, fc2, norm) -> bool:
+    """Whether ``mlp_ln`` covers ``x + norm(mlp(x))`` as one autograd node with the LayerNorm in fc2's epilogue."""
+    if not (mlp_supported(x, fc1, fc2) and _fusable_ln(norm, fc2.weight.shape[0])):
+        return False
+    N, K = fc2.weight.shape
+    return bool(norm.normalized_shape[0] == N == x.shape[-1]
+                and lib.hs_gemm3_ln_supported(x.numel() // x.shape[-1], N, K, N))
+
+
+def mlp_ln(x, fc1, fc2, norm, drop=0.0, seed=None):
+    """``x + norm(fc2(dropout(GELU(fc1(x)))))`` -- the MLP half of a v2-placement block (swin_hp_transformer.py:336-338
+    with drop_path = identity and no dropout after fc2) in two launches; check ``mlp_ln_supported``."""
+    drop = float(drop)
+    seed = _pick_seed(seed, drop)
+    return _MlpFn.apply(x, fc1.weight, fc1.bias, fc2.weight, drop, int(seed or 0), False, fc2.bias, norm.weight, norm.bias,
+                        float(norm.eps))
 
 
 class _CatLinearFn(torch.autograd.Function):

@@ -246,6 +246,25 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
              void* stream);
 
 /*
+ * Linear followed by LayerNorm over groups of G consecutive output columns, in the GEMM's epilogue (no pass of its own
+ * over the (T, N) tensor):
+ *     pre[t][n] = acc[t][n] + bias[n]
+ *     y[t][n]   = (pre[t][n] - mean[t][n / G]) * rstd[t][n / G] * gamma[n % G] + beta[n % G]  (+ aux[t][n])
+ * with mean / rstd the statistics of pre[t][g G : (g + 1) G] (biased variance, rstd = 1 / sqrt(var + eps)).
+ *   G = N:      the `shortcut + norm(branch)` tail of a v2-placement block (swin_hp_transformer.py:333-338): the proj /
+ *               Mlp.fc2 linear, its bias, norm1 / norm2 and the residual add (aux = shortcut) in one launch;
+ *   G = N / 4:  PatchExpand (:420-430: Linear(C -> 2C) -> view (B, 4N, C/2) -> LayerNorm(C/2)); the (T, N) output IS the
+ *               (4T, C/2) tensor of the view, and mean / rstd are laid out as its rows (index t * (N / G) + group).
+ * pre_dev (the pre-norm tensor, what hs_layernorm_bwd needs), mean_dev / rstd_dev, bias_dev and aux_dev may be NULL.
+ * hs_gemm3_ln_supported: hs_gemm3_supported and G a multiple of 32, G <= 192, N a multiple of G.
+ * precision: HS_GEMM_BF16X3 or HS_GEMM_BF16.
+ */
+int hs_gemm3_ln_supported(int64_t T, int N, int K, int G);
+int hs_gemm3_ln(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* gamma_dev,
+                const float* beta_dev, const float* aux_dev, float* pre_dev, float* y_dev, float* mean_dev, float* rstd_dev,
+                int64_t T, int N, int K, int G, float eps, int precision, void* stream);
+
+/*
  * Decoder tail, fused: logits = Conv1d_1x1(LayerNorm(x)) (FinalPatchExpand_X4.norm + SwinHPTransformerSys.output,
  * swin_hp_transformer.py:450, 781-786, 945) in one pass, and its backward in one pass.
  *   x: (rows, C) fp32 with rows = B * rows_per_sample; gamma, beta: (C); w: (K, C) = output.weight[:, :, 0];

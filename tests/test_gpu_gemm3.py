@@ -252,3 +252,121 @@ def test_cta_pair_regime_small_and_ragged_token_counts(T, N, K):
     u = (aux.double() + bias.double()).requires_grad_(True)
     torch.nn.functional.gelu(u).sum().backward()
     assert rel_err(gg.cpu(), (ref * u.grad).cpu()) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm in the GEMM's epilogue (hs_gemm3_ln): PatchExpand's Linear -> view -> LayerNorm and the
+# `shortcut + norm(branch)` tail of a v2 block (swin_hp_transformer.py:420-430, 333-338)
+
+def _gemm3_ln(a, ws, N, G, bias, gamma, beta, aux=None, save=True, eps=1e-5):
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    T, K = a.shape
+    y = torch.full((T, N), float("nan"), device=a.device)
+    pre = torch.full((T, N), float("nan"), device=a.device) if save else None
+    mean = torch.full((T * (N // G),), float("nan"), device=a.device) if save else None
+    rstd = torch.full((T * (N // G),), float("nan"), device=a.device) if save else None
+    check(lib.hs_gemm3_ln(ptr(a), ptr(ws), ptr(bias), ptr(gamma), ptr(beta), ptr(aux), ptr(pre), ptr(y), ptr(mean), ptr(rstd),
+                          T, N, K, G, C.c_float(eps), 0, current_stream()))
+    return y, pre, mean, rstd
+
+
+LN_TOL = 2e-5  # the products are good to 2^-16; the statistics are exact fp32 (pivoted one-pass sums merged pairwise)
+
+
+@pytest.mark.parametrize("T,N,K,G", [
+    (300, 96, 96, 96),        # block tail at stage 0 (proj): one LN group, three slabs over two epilogue groups, ragged tokens
+    (4096, 96, 384, 96),      # block tail at stage 0 (fc2), resident W with 12 K slices
+    (1000, 192, 192, 192),    # stage 1: one group of six slabs
+    (2048, 192, 768, 192),    # stage 1 fc2: streamed W
+    (1024, 384, 192, 96),     # PatchExpand 1 -> 0: four groups, two per column chunk
+    (640, 768, 384, 192),     # PatchExpand 2 -> 1: four chunks of one group
+    (512, 128, 128, 128),     # C = 128 (BASELINE configs[3]) stage 0
+    (256, 96, 64, 32),        # one slab per group: an epilogue group that owns no slab of a group
+    (200, 288, 96, 96),       # three groups: ragged last chunk holds a single group
+    (384, 64, 32, 64),
+])
+@pytest.mark.parametrize("with_aux", [False, True])
+def test_ln_epilogue_matches_fp64(T, N, K, G, with_aux):
+    a, w, b = _data(T, N, K, seed=5)
+    dev = a.device
+    g = torch.Generator().manual_seed(T + N)
+    gamma = (1.0 + 0.3 * torch.randn(G, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(G, generator=g)).to(dev)
+    aux = torch.randn(T, N, generator=g).to(dev) if with_aux else None
+    a = a + 0.7  # a non-zero row mean: the one-pass variance must not cancel
+    pre_w = a.double() @ w.double().t() + b.double()
+    v = pre_w.view(T * (N // G), G)
+    mean_w, var_w = v.mean(1), v.var(1, unbiased=False)
+    y_w = ((v - mean_w[:, None]) / torch.sqrt(var_w[:, None] + 1e-5) * gamma.double() + beta.double()).view(T, N)
+    if with_aux:
+        y_w = y_w + aux.double()
+    for save in (True, False):
+        y, pre, mean, rstd = _gemm3_ln(a, _split(w), N, G, b, gamma, beta, aux, save)
+        assert rel_err(y.cpu(), y_w.cpu()) < LN_TOL, (save, rel_err(y.cpu(), y_w.cpu()))
+        if save:
+            assert rel_err(pre.cpu(), pre_w.cpu()) < TOL
+            assert rel_err(mean.cpu(), mean_w.cpu()) < 1e-5
+            assert rel_err(rstd.cpu(), (1.0 / torch.sqrt(var_w + 1e-5)).cpu()) < 1e-5
+    # no bias
+    y, _, _, _ = _gemm3_ln(a, _split(w), N, G, None, gamma, beta, aux, False)
+    v = (pre_w - b.double()).view(T * (N // G), G)
+    y_w = ((v - v.mean(1, keepdim=True)) / torch.sqrt(v.var(1, unbiased=False, keepdim=True) + 1e-5) * gamma.double()
+           + beta.double()).view(T, N)
+    if with_aux:
+        y_w = y_w + aux.double()
+    assert rel_err(y.cpu(), y_w.cpu()) < LN_TOL
+
+
+def test_ln_epilogue_full_size_is_deterministic_and_matches_two_launches():
+    """BASELINE stage-0 shape (T = 1.57 M tokens, C = 96): two runs are bit-identical and equal the unfused pair
+    (hs_gemm3 + hs_layernorm_fwd with the residual) to fp32 rounding."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    T, Cc = 8 * 196608, 96
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(T, Cc, device=dev, generator=g)
+    sc = torch.randn(T, Cc, device=dev, generator=g)
+    lin = torch.nn.Linear(Cc, Cc).to(dev)
+    norm = torch.nn.LayerNorm(Cc).to(dev)
+    with torch.no_grad():
+        norm.weight.add_(0.1 * torch.randn(Cc, device=dev))
+        norm.bias.add_(0.1 * torch.randn(Cc, device=dev))
+        assert ops.linear_ln_supported(x, lin.weight, norm)
+        y1 = ops.linear_ln(x, lin.weight, lin.bias, norm, residual=sc)
+        y2 = ops.linear_ln(x, lin.weight, lin.bias, norm, residual=sc)
+        assert torch.equal(y1, y2)
+        want = ops.layer_norm(ops.linear(x, lin.weight), norm, residual=sc, pre_bias=lin.bias)
+        assert float((y1 - want).abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("T,Cin,Cout,G,res", [(777, 96, 96, 96, True), (512, 192, 384, 96, False), (384, 384, 192, 192, True)])
+def test_linear_ln_autograd_matches_torch_fp64(T, Cin, Cout, G, res):
+    """ops.linear_ln forward and all five gradients (x, W, b, gamma, beta) + the residual's against fp64 autograd."""
+    from heal_swin_b200 import ops
+
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T)
+    x = torch.randn(T, Cin, generator=g).to(dev).requires_grad_()
+    r = torch.randn(T, Cout, generator=g).to(dev).requires_grad_() if res else None
+    lin = torch.nn.Linear(Cin, Cout).to(dev)
+    norm = torch.nn.LayerNorm(G).to(dev)
+    with torch.no_grad():
+        norm.weight.add_(0.2 * torch.randn(G, device=dev))
+        norm.bias.add_(0.2 * torch.randn(G, device=dev))
+    assert ops.linear_ln_supported(x, lin.weight, norm)
+    y = ops.linear_ln(x, lin.weight, lin.bias, norm, residual=r)
+    dy = torch.randn(T, Cout, generator=g).to(dev)
+    params = [x, lin.weight, lin.bias, norm.weight, norm.bias] + ([r] if res else [])
+    got = torch.autograd.grad(y, params, dy)
+    p64 = [p.detach().double().requires_grad_() for p in params]
+    pre = torch.nn.functional.linear(p64[0], p64[1], p64[2])
+    y64 = torch.nn.functional.layer_norm(pre.view(T, Cout // G, G), (G,), p64[3], p64[4], 1e-5).view(T, Cout)
+    if res:
+        y64 = y64 + p64[5]
+    want = torch.autograd.grad(y64, p64, dy.double())
+    assert rel_err(y.detach().cpu(), y64.detach().cpu()) < LN_TOL
+    for name, a_, b_ in zip(["x", "W", "b", "gamma", "beta", "res"], got, want):
+        tol = 2e-3 if name == "W" else 2e-4  # weight gradients are TF32 tensor-core sums (tests/test_gpu_wgrad.py)
+        assert rel_err(a_.cpu(), b_.cpu()) < tol, (name, rel_err(a_.cpu(), b_.cpu()))
