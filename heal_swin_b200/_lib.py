@@ -50,6 +50,8 @@ SIGNATURES = {
     "hs_gemm3": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _f, _u64, _p],
     "hs_gemm3_ln_supported": [_i64, _i, _i, _i],
     "hs_gemm3_ln": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _f, _i, _p],
+    "hs_gemm3_lnin_supported": [_i64, _i, _i],
+    "hs_gemm3_lnin": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _f, _i, _p],
     "hs_ln_head_supported": [_i64, _i, _i],
     "hs_ln_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _f, _p],
     "hs_ln_head_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _p],

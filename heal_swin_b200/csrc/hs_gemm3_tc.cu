@@ -32,6 +32,11 @@
 //                     D = acc + bias (the pre-norm tensor the backward needs) and the row statistics as optional outputs:
 //                     PatchExpand's Linear -> view (B, 4N, C/2) -> LayerNorm (swin_hp_transformer.py:420-430) and the
 //                     `x + norm(branch(x))` tail of a v2 block (:333-338) without a pass of their own over (T, N)
+//     MODE_LN_IN      D = LayerNorm_K(a) W^T for a LayerNorm over the whole input row: PatchMerging's view -> LayerNorm(4C) ->
+//                     Linear(4C -> 2C) (swin_hp_transformer.py:378-395) without materialising the normalised tensor.  With
+//                     W' = W diag(gamma):  D = rstd (a W'^T - mean s) + b0,  s = W' 1,  b0 = W beta  -- the GEMM runs on
+//                     the RAW rows, the converters (which see every element anyway) take the row statistics, and the
+//                     epilogue applies them.
 // aux sub-slabs are brought in by TMA into the staging regions ahead of time and combined in place.
 //
 // Warps: [0, E) epilogue (TMEM lane quadrant = warp % 4), [E, E+8) converters, E+8 A producer, E+9 MMA issuer,
@@ -62,7 +67,7 @@ constexpr int kTeam = 4;               // converter warps per chunk (one per TME
 constexpr int kASlots = 4;             // A-operand slots of 32 TMEM columns behind two 192-column accumulator stages
 constexpr int kACol0 = 2 * 192;
 
-enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3, MODE_LN = 4 };
+enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3, MODE_LN = 4, MODE_LN_IN = 5 };
 constexpr int kLnExch = 2 * 2 * 128 * 2 * 8;  // MODE_LN: partial row statistics exchanged between the two epilogue groups
 // operand precision: three bf16 MMAs per product (fp32-class), one TF32 MMA (A straight from the fp32 tile, no conversion;
 // input gradients of the tensor-bound stages), one bf16 MMA ("bf16 operands, fp32 accumulate": BASELINE configs[3])
@@ -93,6 +98,8 @@ struct G3Args {
   float eps;
   int save_pre;  // D (= acc + bias) is written as well
   int has_aux;   // D2 += aux
+  // MODE_LN_IN: s[n] = sum_k gamma[k] W[n][k] (bias holds b0 = W beta; mean_out / rstd_out (T) optional; eps as above)
+  const float* wsum;
 };
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major
@@ -393,6 +400,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     // (pair, TF32 without column sums: one warp per team only forwards the chunk's arrival to the leader; the others must
     // not wait on barriers whose progress does not depend on them -- they could fall a whole ring cycle behind)
+    float ln_piv = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;
     if (convert || do_colsum || (pair && q == 0)) {
       long long c = 0;  // running chunk index of this CTA
       for (long long tile = t0; tile < t_end; tile += tstep)
@@ -415,6 +423,26 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
           float4 v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = lds_f4(base + ((j ^ sw) << 4));
+          if constexpr (MODE == MODE_LN_IN) {
+            // row statistics of the raw input over this team's chunks of the tile (pivoted one-pass sums; the epilogue
+            // merges the two teams' partial results): handed over through shared memory, four tiles deep -- the converters
+            // never run that far ahead of the epilogue (rings of <= 10 chunks, >= 5 chunks per tile)
+            const long long cb = c - kc;                          // running index of the tile's first chunk
+            const int first_kc = ((int)(cb & 1) == team) ? 0 : 1;
+            const int last_kc = ((int)((cb + nk - 1) & 1) == team) ? nk - 1 : nk - 2;
+            if (kc == first_kc) { ln_piv = v[0].x; ln_s1 = 0.f; ln_s2 = 0.f; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float d0 = v[j].x - ln_piv, d1 = v[j].y - ln_piv, d2 = v[j].z - ln_piv, d3 = v[j].w - ln_piv;
+              ln_s1 += (d0 + d1) + (d2 + d3);
+              ln_s2 = fmaf(d0, d0, ln_s2); ln_s2 = fmaf(d1, d1, ln_s2); ln_s2 = fmaf(d2, d2, ln_s2); ln_s2 = fmaf(d3, d3, ln_s2);
+            }
+            if (kc == last_kc) {
+              const float inv_n = 1.0f / (float)(32 * ((last_kc - first_kc) / 2 + 1));
+              reinterpret_cast<float2*>(s_colsum)[((int)((cb / nk) & 3) * 2 + team) * 128 + row] =
+                  make_float2(ln_piv + ln_s1 * inv_n, fmaxf(ln_s2 - ln_s1 * ln_s1 * inv_n, 0.f));
+            }
+          }
           if (do_colsum) {
             // column sums of this warp's 32 rows x 32 columns: a reduce-scatter over the lanes (16 + 8 + 4 + 2 + 1
             // shuffles) leaves one column per lane, which adds it to the CTA's running sums
@@ -707,6 +735,21 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       const long long grow = tile * kBM + q * 32 + lane;
       uint32_t dkey = 0;
       if (MODE == MODE_GELU || MODE == MODE_GELU_GRAD) dkey = a.drop_thresh ? hs::drop_row_key(a.seed, grow) : 0u;
+      float ln_mean = 0.f, ln_rstd = 0.f;
+      if constexpr (MODE == MODE_LN_IN) {  // the converters' partial row statistics of this tile -> mean, 1 / std
+        const float2* st = reinterpret_cast<const float2*>(s_colsum) + (size_t)(it & 3) * 256 + q * 32 + lane;
+        const float2 p0 = st[0], p1 = st[128];
+        const long long cb = it * nk;
+        const int n_even = (nk + 1) / 2, n_odd = nk / 2;              // chunks at even / odd offsets inside the tile
+        const float na = 32.f * ((cb & 1) ? n_odd : n_even), nb = 32.f * ((cb & 1) ? n_even : n_odd);  // team 0, team 1
+        const float nt = na + nb, delta = p1.x - p0.x, f = nb / nt;
+        ln_mean = p0.x + delta * f;
+        ln_rstd = rsqrtf((p0.y + p1.y + delta * delta * na * f) / nt + a.eps);
+        if (g == 0 && chunk == 0 && a.mean_out && grow < a.T) {
+          a.mean_out[grow] = ln_mean;
+          a.rstd_out[grow] = ln_rstd;
+        }
+      }
       auto release_stage = [&]() {  // this thread's part of the accumulator stage is in registers (or unused)
         tc_fence_before();
         if (pair) {
@@ -748,6 +791,11 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
               bv = __ldg(reinterpret_cast<const float4*>(a.bias + jc + 4 * c));
             if (MODE == MODE_PLAIN) {
               o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+            } else if (MODE == MODE_LN_IN) {
+              float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (jc + 4 * c < a.N) sv = __ldg(reinterpret_cast<const float4*>(a.wsum + jc + 4 * c));
+              o.x = fmaf(fmaf(-ln_mean, sv.x, o.x), ln_rstd, bv.x); o.y = fmaf(fmaf(-ln_mean, sv.y, o.y), ln_rstd, bv.y);
+              o.z = fmaf(fmaf(-ln_mean, sv.z, o.z), ln_rstd, bv.z); o.w = fmaf(fmaf(-ln_mean, sv.w, o.w), ln_rstd, bv.w);
             } else if (MODE == MODE_ADD) {
               const float4 x = lds_f4(p);
               o.x += bv.x + x.x; o.y += bv.y + x.y; o.z += bv.z + x.z; o.w += bv.w + x.w;
@@ -895,7 +943,8 @@ int plan(G3Args& a, int mode, int E) {
     if (stride > first || (ci > 0 && stride == first)) continue;
     const int box = (stride + 31) / 32 * 32;
     const int w_slice = (a.pair ? box / 2 : box) * 128;
-    const long long staging_min = (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0) + (ln ? kLnExch : 0);
+    const long long staging_min =
+        (long long)E * rw_min * kRegion + (a.colsum ? nk * 128 : 0) + ((ln || mode == MODE_LN_IN) ? kLnExch : 0);
     const int resident = (!a.pair && (long long)nk * w_slice + 4 * kChunk + staging_min <= kSmemAvail) ? 1 : 0;
     int wring = a.pair ? (nk < 4 ? nk : 4) : (nk < 3 ? nk : 3);  // (a pair's slices are half the size)
     if (const char* e = getenv("HEALSWIN_GEMM3_WRING")) {  // experiments only
@@ -944,7 +993,7 @@ template <int E>
 size_t smem_bytes(const G3Args& a) {
   const int nk = (a.K + 31) / 32, w_slice = (a.pair ? a.n_box / 2 : a.n_box) * 128;
   return (size_t)(a.resident ? nk : a.wring) * w_slice + (size_t)a.ring * kChunk + (size_t)E * a.rw * kRegion +
-         (a.colsum ? (size_t)nk * 128 : 0) + (a.G > 0 ? (size_t)kLnExch : 0) + 1024;
+         (a.colsum ? (size_t)nk * 128 : 0) + ((a.G > 0 || a.wsum) ? (size_t)kLnExch : 0) + 1024;
 }
 
 struct Maps {
@@ -1083,6 +1132,29 @@ int hs_gemm3_ln(const float* a_dev, const uint16_t* wsplit_dev, const float* bia
   a.gamma = gamma_dev; a.beta = beta_dev; a.mean_out = mean_dev; a.rstd_out = rstd_dev;
   a.G = G; a.eps = eps; a.save_pre = pre_dev ? 1 : 0; a.has_aux = aux_dev ? 1 : 0;
   return launch<8, MODE_LN>(a_dev, wsplit_dev, aux_dev, pre_dev ? pre_dev : y_dev, y_dev, a, (cudaStream_t)stream);
+}
+
+int hs_gemm3_lnin_supported(int64_t T, int N, int K) {
+  return (hs_gemm3_supported(T, N, K) && K % 32 == 0 && K >= 160) ? 1 : 0;
+}
+
+int hs_gemm3_lnin(const float* a_dev, const uint16_t* wsplit_dev, const float* wsum_dev, const float* b0_dev, float* d_dev,
+                  float* mean_dev, float* rstd_dev, int64_t T, int N, int K, float eps, int precision, void* stream) {
+  HS_REQUIRE(a_dev && wsplit_dev && wsum_dev && d_dev && T > 0, "hs_gemm3_lnin: bad arguments");
+  HS_REQUIRE(precision == PREC_BF16X3 || precision == PREC_BF16, "hs_gemm3_lnin: precision must be bf16x3 or bf16");
+  HS_REQUIRE((mean_dev == nullptr) == (rstd_dev == nullptr), "hs_gemm3_lnin: mean and rstd go together");
+  if (!hs_gemm3_lnin_supported(T, N, K))
+    return hs::fail(HS_ERR_UNSUPPORTED, "hs_gemm3_lnin: shape T=%lld N=%d K=%d is not covered (K a multiple of 32, >= 160)",
+                    (long long)T, N, K);
+  HS_REQUIRE(!((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(wsplit_dev) |
+                reinterpret_cast<uintptr_t>(wsum_dev) | reinterpret_cast<uintptr_t>(b0_dev) |
+                reinterpret_cast<uintptr_t>(d_dev)) & 15),
+             "hs_gemm3_lnin: tensors must be 16-byte aligned");
+  G3Args a{};
+  a.bias = b0_dev; a.wsum = wsum_dev; a.T = T; a.N = N; a.K = K; a.prec = precision;
+  a.drop_scale = 1.0f;
+  a.mean_out = mean_dev; a.rstd_out = rstd_dev; a.eps = eps;
+  return launch<8, MODE_LN_IN>(a_dev, wsplit_dev, nullptr, d_dev, nullptr, a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -282,8 +282,9 @@ class PatchMerging(nn.Module):
         B, N, C = x.shape
         assert N % 4 == 0, f"x size {N} is not divisible by 4 as necessary for patching."
         # cat(x[:,0::4], ..., x[:,3::4]) on the channel axis is a plain view in nested order
+        # (fused gather + norm + linear: the LayerNorm is folded into the reduction GEMM, ops.ln_linear)
         x = x.contiguous().view(B, N // 4, 4 * C)
-        return ops.linear(ops.layer_norm(x, self.norm), self.reduction.weight, self.reduction.bias)
+        return ops.ln_linear(x, self.norm, self.reduction.weight, self.reduction.bias)
 
     def extra_repr(self) -> str:
         return f"dim={self.dim}"

@@ -665,6 +665,81 @@ def linear_ln(x, weight, bias, norm, residual=None):
     return y if residual is None else residual + y
 
 
+def ln_linear_supported(x, norm, weight) -> bool:
+    """Whether ``ln_linear`` runs as one launch: affine LayerNorm over the whole input row (a multiple of 32, >= 160
+    wide -- PatchMerging's 4C) feeding a Linear the hand-written GEMM covers."""
+    K = weight.shape[1]
+    return bool(_FUSED_LINEAR_LN and gemm3_ok(x, weight) and _fusable_norm(norm, x)
+                and lib.hs_gemm3_lnin_supported(x.numel() // K, weight.shape[0], K))
+
+
+class _LnLinearFn(torch.autograd.Function):
+    """``F.linear(LayerNorm(x), weight)`` (no bias) with the normalisation folded into the GEMM (hs_gemm3_lnin): the
+    product runs on the raw rows with gamma folded into the weight, the row statistics come out of the GEMM's own operand
+    pass and are applied in its epilogue; the normalised (T, K) tensor is neither written nor kept for the backward (it is
+    rebuilt there by one LayerNorm pass for the weight gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, weight, eps):
+        ctx.set_materialize_grads(False)
+        N, K = weight.shape
+        x2 = _f32c(x).reshape(-1, K)
+        T = x2.shape[0]
+        w = _f32c(weight.detach())
+        g, b = _f32c(gamma.detach()), _f32c(beta.detach())
+        wg = w * g                       # W diag(gamma)
+        wsum = wg.sum(1)                 # s = W' 1
+        b0 = w @ b                       # W beta
+        save = any(ctx.needs_input_grad[:4])
+        d = torch.empty((T, N), device=x2.device, dtype=torch.float32)
+        mean = torch.empty((T,), device=x2.device, dtype=torch.float32) if save else None
+        rstd = torch.empty_like(mean) if save else None
+        prec = _fwd_prec()
+        STATS.launch("gemm3", lib.hs_gemm3_lnin, ptr(x2), ptr(split_weight(wg)), ptr(wsum), ptr(b0), ptr(d), ptr(mean),
+                     ptr(rstd), T, N, K, C.c_float(eps), prec, current_stream(), tag=(T, N, K, 8, prec))
+        if save:
+            ctx.save_for_backward(x2, gamma, beta, weight, mean, rstd)
+        ctx.meta = (x.shape, float(eps))
+        return d.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy is None:
+            return (None,) * 5
+        x2, gamma, beta, weight, mean, rstd = ctx.saved_tensors
+        xshape, eps = ctx.meta
+        N, K = weight.shape
+        T = x2.shape[0]
+        dy2 = _f32c(dy).reshape(T, N)
+        g = _f32c(gamma)
+        dx = dw = dgamma = dbeta = None
+        if ctx.needs_input_grad[3]:  # dW = dy^T LayerNorm(x): the normalised rows are rebuilt (one pass) for this product
+            xn = torch.empty_like(x2)
+            STATS.launch("layernorm_fwd", lib.hs_layernorm_fwd, ptr(x2), None, None, ptr(g), ptr(_f32c(beta)), None, 0,
+                         C.c_float(0.0), C.c_uint64(0), ptr(xn), None, None, T, K, C.c_float(eps), current_stream(),
+                         tag=(T, K, 0))
+            dw, _ = _wgrad(dy2, xn, False)
+            del xn
+        if any(ctx.needs_input_grad[:3]):
+            dxn = _dgrad(dy2, weight, None, (T, K))
+            dx = torch.empty_like(x2)
+            dgamma = torch.zeros(K, device=x2.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+            dbeta = torch.zeros(K, device=x2.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+            STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dxn), ptr(x2), None, ptr(mean), ptr(rstd), ptr(g), None, 0,
+                         C.c_float(0.0), C.c_uint64(0), ptr(dx), ptr(dgamma), ptr(dbeta), None, T, K, current_stream(),
+                         tag=(T, K))
+            dx = dx.view(xshape)
+        return dx, dgamma, dbeta, dw, None
+
+
+def ln_linear(x, norm, weight, bias=None):
+    """``F.linear(norm(x), weight, bias)`` for an affine LayerNorm over the last dim: one launch where
+    ``ln_linear_supported`` (and no bias), else the LayerNorm and the linear as two launches."""
+    if bias is None and ln_linear_supported(x, norm, weight):
+        return _LnLinearFn.apply(x, norm.weight, norm.bias, weight, float(norm.eps))
+    return linear(layer_norm(x, norm), weight, bias)
+
+
 def _gemm_fwd(x2, weight, bias):
     """x2 (T, K) @ weight (N, K)^T + bias."""
     if gemm3_ok(x2, weight):

@@ -265,6 +265,19 @@ int hs_gemm3_ln(const float* a_dev, const uint16_t* wsplit_dev, const float* bia
                 int64_t T, int N, int K, int G, float eps, int precision, void* stream);
 
 /*
+ * LayerNorm over the whole input row followed by a bias-free Linear, without materialising the normalised tensor:
+ * PatchMerging (swin_hp_transformer.py:378-395: view (B, N/4, 4C) -> LayerNorm(4C) -> Linear(4C -> 2C); in NESTED order the
+ * four siblings of a token are consecutive, so the gather IS the view).  With W' = W diag(gamma):
+ *     d[t][n] = rstd[t] * (sum_k a[t][k] W'[n][k] - mean[t] * wsum[n]) + b0[n],   wsum = W' 1,  b0 = W beta
+ * wsplit: hs_weight_split of W' (format 0).  The GEMM runs on the raw rows; its operand converters take the row statistics
+ * (exact fp32, pivoted sums) and the epilogue applies them.  mean_dev / rstd_dev (T; what hs_layernorm_bwd needs) and
+ * b0_dev may be NULL.  hs_gemm3_lnin_supported: hs_gemm3_supported and K a multiple of 32, K >= 160.
+ */
+int hs_gemm3_lnin_supported(int64_t T, int N, int K);
+int hs_gemm3_lnin(const float* a_dev, const uint16_t* wsplit_dev, const float* wsum_dev, const float* b0_dev, float* d_dev,
+                  float* mean_dev, float* rstd_dev, int64_t T, int N, int K, float eps, int precision, void* stream);
+
+/*
  * Decoder tail, fused: logits = Conv1d_1x1(LayerNorm(x)) (FinalPatchExpand_X4.norm + SwinHPTransformerSys.output,
  * swin_hp_transformer.py:450, 781-786, 945) in one pass, and its backward in one pass.
  *   x: (rows, C) fp32 with rows = B * rows_per_sample; gamma, beta: (C); w: (K, C) = output.weight[:, :, 0];

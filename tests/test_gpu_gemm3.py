@@ -370,3 +370,66 @@ def test_linear_ln_autograd_matches_torch_fp64(T, Cin, Cout, G, res):
     for name, a_, b_ in zip(["x", "W", "b", "gamma", "beta", "res"], got, want):
         tol = 2e-3 if name == "W" else 2e-4  # weight gradients are TF32 tensor-core sums (tests/test_gpu_wgrad.py)
         assert rel_err(a_.cpu(), b_.cpu()) < tol, (name, rel_err(a_.cpu(), b_.cpu()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm folded into the GEMM from the input side (hs_gemm3_lnin): PatchMerging (swin_hp_transformer.py:378-395)
+
+@pytest.mark.parametrize("T,N,K", [
+    (300, 96, 192),       # tiny config (C = 48): 6 chunks per tile, ragged tokens
+    (4096, 192, 384),     # stage 0 -> 1: A through tensor memory, 12 chunks
+    (1000, 384, 768),     # stage 1 -> 2: in-place split ("ss"), CTA pairs, ragged tokens
+    (1536, 768, 1536),    # stage 2 -> 3
+    (640, 200, 224),      # odd chunk count (7): the two converter teams swap parity every tile; N not a multiple of 32
+    (129, 64, 160),
+])
+def test_ln_prologue_matches_fp64(T, N, K):
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    a, w, _ = _data(T, N, K, seed=9)
+    dev = a.device
+    g = torch.Generator().manual_seed(T + K)
+    gamma = (1.0 + 0.3 * torch.randn(K, generator=g)).to(dev)
+    beta = (0.2 * torch.randn(K, generator=g)).to(dev)
+    a = a * (0.5 + torch.rand(T, 1, generator=g).to(dev)) + 1.5 * torch.randn(T, 1, generator=g).to(dev)  # row mean / scale vary
+    assert lib.hs_gemm3_lnin_supported(T, N, K)
+    wg = (w * gamma).contiguous()
+    wsum, b0 = wg.sum(1), w @ beta
+    d = torch.full((T, N), float("nan"), device=dev)
+    mean = torch.full((T,), float("nan"), device=dev)
+    rstd = torch.full((T,), float("nan"), device=dev)
+    check(lib.hs_gemm3_lnin(ptr(a), ptr(_split(wg)), ptr(wsum), ptr(b0), ptr(d), ptr(mean), ptr(rstd), T, N, K,
+                            C.c_float(1e-5), 0, current_stream()))
+    xn = torch.nn.functional.layer_norm(a.double(), (K,), gamma.double(), beta.double(), 1e-5)
+    want = xn @ w.double().t()
+    # the epilogue subtracts mean * s from the raw product: where |mean| >> std the result carries the product's 2^-16
+    # relative error amplified by that ratio (here <= ~6), still well inside the network's 1e-3
+    assert rel_err(d.cpu(), want.cpu()) < 1e-4, rel_err(d.cpu(), want.cpu())
+    assert rel_err(mean.cpu(), a.double().mean(1).cpu()) < 1e-5
+    assert rel_err(rstd.cpu(), (1.0 / torch.sqrt(a.double().var(1, unbiased=False) + 1e-5)).cpu()) < 1e-5
+
+
+def test_patch_merging_module_matches_torch_fp64():
+    """PatchMerging through ops.ln_linear: output and gradients (x, norm, reduction) against fp64 autograd."""
+    from heal_swin_b200 import ops
+    from heal_swin_b200.models_torch.swin_hp_transformer import PatchMerging
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    m = PatchMerging(96).to(dev)
+    with torch.no_grad():
+        m.norm.weight.add_(0.2 * torch.randn(384, device=dev))
+        m.norm.bias.add_(0.2 * torch.randn(384, device=dev))
+    x = torch.randn(2, 4 * 1100, 96, device=dev, requires_grad=True)
+    assert ops.ln_linear_supported(x.view(2, 1100, 384), m.norm, m.reduction.weight)
+    y = m(x)
+    gy = torch.randn_like(y)
+    params = [x, m.norm.weight, m.norm.bias, m.reduction.weight]
+    got = torch.autograd.grad(y, params, gy)
+    p64 = [p.detach().double().requires_grad_() for p in params]
+    y64 = torch.nn.functional.linear(
+        torch.nn.functional.layer_norm(p64[0].view(2, 1100, 384), (384,), p64[1], p64[2], 1e-5), p64[3])
+    want = torch.autograd.grad(y64, p64, gy.double())
+    assert rel_err(y.detach().cpu(), y64.detach().cpu()) < 1e-4
+    for name, a_, b_ in zip(["x", "gamma", "beta", "W"], got, want):
+        assert rel_err(a_.cpu(), b_.cpu()) < (2e-3 if name == "W" else 3e-4), (name, rel_err(a_.cpu(), b_.cpu()))
