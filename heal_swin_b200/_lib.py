@@ -46,6 +46,7 @@ SIGNATURES = {
     "hs_mlp_dgrad_gelu_supported": [_i64, _i, _i],
     "hs_mlp_dgrad_gelu": [_p, _p, _p, _p, _f, _u64, _p, _i64, _i, _i, _u32, _p],
     "hs_weight_split": [_p, _i, _i, _i, _i, _i, _p, _p],
+    "hs_weight_split_batch": [_p, _i, _i, _p],
     "hs_gemm3_supported": [_i64, _i, _i],
     "hs_gemm3": [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _f, _u64, _p],
     "hs_gemm3_ln_supported": [_i64, _i, _i, _i],

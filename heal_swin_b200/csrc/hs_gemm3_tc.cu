@@ -853,10 +853,10 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
 // W (rows x cols fp32, row stride ld; element (r, c) = w[r * ld + c], or w[c * ld + r] when transposed) ->
 // out (rows, ceil(cols / 32), 64) bf16 = [hi(32) | lo(32)] per 32-wide chunk of the contraction axis (zero padded).
 // format 1: out (rows, ceil(cols / 32), 32) fp32 rounded to the nearest TF32 (the single-MMA TF32 mode; same bytes per row).
-__global__ void weight_split_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int rows, int cols, int ld,
-                                    int transposed, int format) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+__device__ __forceinline__ void weight_split_tile(float (*tile)[33], const float* __restrict__ w, uint16_t* __restrict__ out,
+                                                  int rows, int cols, int ld, int transposed, int format, int bx, int by,
+                                                  int nbx) {
+  const int r0 = by * 32, c0 = bx * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     float v = 0.f;
@@ -875,16 +875,43 @@ __global__ void weight_split_kernel(const float* __restrict__ w, uint16_t* __res
     if (format == 1) {
       uint32_t t;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
-      reinterpret_cast<uint32_t*>(out)[((long long)(r0 + i) * gridDim.x + blockIdx.x) * 32 + tx] = t;
+      reinterpret_cast<uint32_t*>(out)[((long long)(r0 + i) * nbx + bx) * 32 + tx] = t;
       continue;
     }
     const uint32_t hb = cvt_bf16x2(0.f, x) & 0xffffu;
     const float h = __uint_as_float(hb << 16);
     const uint32_t lb = cvt_bf16x2(0.f, x - h) & 0xffffu;
-    uint16_t* o = out + ((long long)(r0 + i) * gridDim.x + blockIdx.x) * 64;
+    uint16_t* o = out + ((long long)(r0 + i) * nbx + bx) * 64;
     o[tx] = (uint16_t)hb;
     o[32 + tx] = (uint16_t)lb;
   }
+}
+
+__global__ void weight_split_kernel(const float* __restrict__ w, uint16_t* __restrict__ out, int rows, int cols, int ld,
+                                    int transposed, int format) {
+  __shared__ float tile[32][33];
+  weight_split_tile(tile, w, out, rows, cols, ld, transposed, format, blockIdx.x, blockIdx.y, gridDim.x);
+}
+
+// All weight operands of a model in ONE launch (hs_weight_split_batch): block b finds its matrix by binary search over the
+// running tile counts.  Same per-tile code as above.
+struct SplitDesc {   // mirrored by heal_swin_b200/ops.py:_SplitDesc
+  const float* w;
+  uint16_t* out;
+  int rows, cols, ld, transposed, format, tiles_x, tile0, pad;
+};
+__global__ void weight_split_batch_kernel(const SplitDesc* __restrict__ descs, int n) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.x;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {  // last descriptor with tile0 <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile0 <= b) lo = mid;
+    else hi = mid - 1;
+  }
+  const SplitDesc d = descs[lo];
+  const int t = b - d.tile0;
+  weight_split_tile(tile, d.w, d.out, d.rows, d.cols, d.ld, d.transposed, d.format, t % d.tiles_x, t / d.tiles_x, d.tiles_x);
 }
 
 int make_map_bf16(CUtensorMap* m, const uint16_t* base, long long rows, long long cols, int box_cols, int box_rows) {
@@ -1063,6 +1090,15 @@ int hs_weight_split(const float* w, int rows, int cols, int ld, int transposed, 
   HS_REQUIRE(format == 0 || format == 1, "hs_weight_split: unknown format %d", format);
   dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
   weight_split_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, out, rows, cols, ld, transposed, format);
+  HS_LAUNCH_CHECK();
+  return HS_OK;
+}
+
+int hs_weight_split_batch(const void* descs_dev, int n, int total_tiles, void* stream) {
+  HS_REQUIRE(descs_dev && n > 0 && total_tiles > 0, "hs_weight_split_batch: bad arguments");
+  static_assert(sizeof(SplitDesc) == 48, "descriptor layout is part of the ABI");
+  weight_split_batch_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const SplitDesc*>(descs_dev), n);
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

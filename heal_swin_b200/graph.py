@@ -63,6 +63,7 @@ class GraphedTrainStep:
         self.preprocess = preprocess
         self.graph = None
         self.loss = torch.zeros((), device=example_x.device, dtype=torch.float32)
+        self.arena = ops.ZeroArena(example_x.device)
 
     def capture(self):
         """Warm-up on a side stream, then capture (done lazily by the first replaying call)."""
@@ -73,20 +74,33 @@ class GraphedTrainStep:
             for _ in range(self.warmup):
                 self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            loss = self._fwd_bwd()
-            self.loss.copy_(loss)
+        # Inside the graph the weight operands are NOT re-split (one small kernel per linear and orientation): all of them
+        # are refreshed by one batched launch before every replay (__call__), and the small zero-initialised accumulators
+        # of the backward come out of one arena cleared by a single memset.
+        ops.refresh_weight_splits(self.x.device)
+        prev = ops.maintain_weight_splits(True)
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                loss = self._fwd_bwd()
+                self.loss.copy_(loss)
+        finally:
+            ops.maintain_weight_splits(prev)
         self.flat_grad.zero_()
         ops.STATS.timing = was_timing
 
     def _fwd_bwd(self):
         self.seed_counter.add_(1)  # (captured: every replay advances the counter behind the indirect dropout seeds)
         self.flat_grad.zero_()
-        x, t = (self.x, self.t) if self.preprocess is None else self.preprocess(self.x, self.t)
-        loss = self.loss_fn(self.model(x), t)
-        loss.backward()  # accumulates in place into the views of flat_grad
-        return loss.detach()
+        self.arena.begin()
+        prev = ops.use_zero_arena(self.arena)
+        try:
+            x, t = (self.x, self.t) if self.preprocess is None else self.preprocess(self.x, self.t)
+            loss = self.loss_fn(self.model(x), t)
+            loss.backward()  # accumulates in place into the views of flat_grad
+            return loss.detach().clone()  # (the loss sums live in the arena)
+        finally:
+            ops.use_zero_arena(prev)
 
     def __call__(self, x, t, eager=False):
         """``eager=True`` runs the very same step without the graph (per-kernel timing, debugging)."""
@@ -97,6 +111,7 @@ class GraphedTrainStep:
         else:
             if self.graph is None:
                 self.capture()
+            ops.refresh_weight_splits(self.x.device)  # the operands the replay reads, from the current parameters
             self.graph.replay()
         if self.world > 1:
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM)

@@ -64,6 +64,58 @@ def get_attention_precision() -> str:
     return _ATTN_PRECISION
 
 
+class ZeroArena:
+    """One flat fp32 buffer that serves the small zero-initialised accumulators of a training step (weight / bias / norm
+    gradients, loss sums: ~360 per step of the N_side=256 network) from ONE memset instead of one fill kernel each.
+    Used by heal_swin_b200.graph.GraphedTrainStep: ``begin()`` zeroes the buffer and rewinds it, every ``zeros()`` below
+    carves the next 256-byte-aligned slice.  A first pass with an empty arena only measures the demand."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.buf = None
+        self.off = 0
+        self.need = 0
+
+    def begin(self):
+        if self.buf is None and self.need:
+            self.buf = torch.empty(self.need, device=self.device, dtype=torch.float32)
+        if self.buf is not None:
+            self.buf.zero_()
+        self.off = 0
+        self.need = 0
+
+    def take(self, n):
+        a = (n + 63) // 64 * 64
+        self.need += a
+        if self.buf is None or self.off + a > self.buf.numel():
+            return None
+        v = self.buf[self.off:self.off + n]
+        self.off += a
+        return v
+
+
+_ARENA = [None]
+
+
+def use_zero_arena(arena):
+    """Install (or, with None, remove) the arena ``zeros`` serves from; returns the previous one."""
+    prev, _ARENA[0] = _ARENA[0], arena
+    return prev
+
+
+def zeros(shape, device):
+    """fp32 zeros for a gradient accumulator: a slice of the active ZeroArena, else ``torch.zeros``."""
+    ar = _ARENA[0]
+    if ar is not None and ar.device == torch.device(device):
+        n = 1
+        for d in (shape if isinstance(shape, (tuple, list, torch.Size)) else (shape,)):
+            n *= int(d)
+        v = ar.take(n)
+        if v is not None:
+            return v.view(shape)
+    return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
 def _f32c(t):
     if t is None:
         return None
@@ -185,15 +237,15 @@ class WindowAttnCore(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         need_table = has_table and ctx.needs_input_grad[1]
         need_ls = (ls is not None) and ctx.needs_input_grad[2]
-        dbias = torch.zeros((H, ws, ws), device=qkv.device, dtype=torch.float32) if need_table else None
-        dls = torch.zeros((H,), device=qkv.device, dtype=torch.float32) if need_ls else None
+        dbias = zeros((H, ws, ws), qkv.device) if need_table else None
+        dls = zeros((H,), qkv.device) if need_ls else None
         STATS.launch("window_attn_bwd", lib.hs_window_attn_bwd, ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(src), ptr(groups), ptr(mask),
                      ptr(bias), ptr(ls), C.c_float(scale), C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dqkv),
                      ptr(dbias), ptr(dls), B, N, Cc, H, ws,
                      flags, stream, tag=(B, N, Cc, H, ws))
         dtable = None
         if need_table:
-            dtable = torch.zeros(table_shape, device=qkv.device, dtype=torch.float32)
+            dtable = zeros(table_shape, qkv.device)
             STATS.launch("rel_bias_reduce", lib.hs_rel_bias_reduce, ptr(dbias), ptr(rel_index), ptr(dtable),
                          table_shape[0], H, ws, stream)
         if need_ls:
@@ -249,9 +301,9 @@ class LayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(x2)
         need_w, need_b = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         need_pb = pb is not None and ctx.needs_input_grad[4]
-        dw = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_w else None
-        db = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_b else None
-        dpb = torch.zeros(Cc, device=x2.device, dtype=torch.float32) if need_pb else None
+        dw = zeros(Cc, x2.device) if need_w else None
+        db = zeros(Cc, x2.device) if need_b else None
+        dpb = zeros(Cc, x2.device) if need_pb else None
         STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(x2), ptr(pb), ptr(mean), ptr(rstd), ptr(w),
                      ptr(rsc), rps, C.c_float(in_drop), C.c_uint64(seed), ptr(dx), ptr(dw), ptr(db), ptr(dpb), rows, Cc,
                      current_stream(), tag=(rows, Cc))
@@ -272,7 +324,7 @@ class _CrossEntropyFn(torch.autograd.Function):
         t = target.contiguous()
         assert t.numel() == B * P and t.dtype in (torch.uint8, torch.int64), "targets: (B, P) uint8 or int64"
         dl = torch.empty_like(x)
-        acc = torch.zeros(2, device=x.device, dtype=torch.float32)
+        acc = zeros(2, x.device)
         STATS.launch("cross_entropy", lib.hs_cross_entropy, ptr(x), ptr(t), t.element_size(), ptr(dl), ptr(acc), B, K, P,
                      int(ignore_index), current_stream(), tag=(B * P, K))
         ctx.save_for_backward(dl, acc)
@@ -354,8 +406,8 @@ class LnHeadFn(torch.autograd.Function):
         B, P, Cc, K, has_bias = ctx.meta
         dl = _f32c(dlogits)
         dx = torch.empty_like(x2)
-        s_acc = torch.zeros((K, Cc), device=x2.device, dtype=torch.float32)
-        g_acc = torch.zeros((K,), device=x2.device, dtype=torch.float32)
+        s_acc = zeros((K, Cc), x2.device)
+        g_acc = zeros((K,), x2.device)
         STATS.launch("ln_head_bwd", lib.hs_ln_head_bwd, ptr(dl), ptr(x2), ptr(mean), ptr(rstd), ptr(gamma), ptr(w), ptr(dx),
                      ptr(s_acc), ptr(g_acc), B * P, P, Cc, K, current_stream(), tag=(B * P, Cc, K))
         dw = gamma * s_acc + beta * g_acc[:, None]
@@ -398,7 +450,7 @@ class BiasGeluFn(torch.autograd.Function):
         dh2 = _f32c(dh).reshape(rows, Cc)
         dz = torch.empty_like(z2)
         need_b = b is not None and ctx.needs_input_grad[1]
-        db = torch.zeros(Cc, device=z2.device, dtype=torch.float32) if need_b else None
+        db = zeros(Cc, z2.device) if need_b else None
         STATS.launch("bias_gelu_bwd", lib.hs_bias_gelu_bwd, ptr(dh2), ptr(z2), ptr(b), C.c_float(ctx.drop[0]),
                      C.c_uint64(ctx.drop[1]), ptr(dz), ptr(db), rows, Cc, current_stream(), tag=(rows, Cc))
         return dz.view(ctx.shape), db, None, None
@@ -506,8 +558,10 @@ def split_weight(weight, transposed=False, cols=None, prec=0):
     ent = _SPLITS.get(key)
     ver = weight._version
     if ent is not None and ent[0]() is weight and ent[2] == w.data_ptr():
-        if (ent[1] == ver and ent[4] == _SPLIT_EPOCH[0]
-                and not (w.is_cuda and torch.cuda.is_current_stream_capturing())):
+        capturing = w.is_cuda and torch.cuda.is_current_stream_capturing()
+        if ent[1] == ver and ent[4] == _SPLIT_EPOCH[0] and not capturing:
+            return ent[3]
+        if capturing and _SPLITS_MAINTAINED[0]:  # refreshed by one batched launch before every replay
             return ent[3]
         out = ent[3]
     else:
@@ -527,6 +581,59 @@ def split_weight(weight, transposed=False, cols=None, prec=0):
 
 def invalidate_weight_splits() -> None:
     _SPLITS.clear()
+    _SPLIT_TABLES.clear()
+
+
+class _SplitDesc(C.Structure):  # csrc/hs_gemm3_tc.cu: SplitDesc
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("ld", C.c_int),
+                ("transposed", C.c_int), ("format", C.c_int), ("tiles_x", C.c_int), ("tile0", C.c_int), ("pad", C.c_int)]
+
+
+_SPLITS_MAINTAINED = [False]
+_SPLIT_TABLES = {}  # device -> (signature, device table, n, total tiles)
+
+
+def maintain_weight_splits(on: bool) -> bool:
+    """While on, ``split_weight`` inside a CUDA-graph capture trusts the cached operands instead of re-launching their
+    split kernels (195 launches per step of the N_side=256 network): the owner of the graph promises to call
+    ``refresh_weight_splits`` before every replay.  Returns the previous setting."""
+    prev, _SPLITS_MAINTAINED[0] = _SPLITS_MAINTAINED[0], bool(on)
+    return prev
+
+
+def refresh_weight_splits(device) -> int:
+    """Re-split EVERY cached weight operand on ``device`` from the current parameter values in ONE launch
+    (hs_weight_split_batch) and mark the cache entries current.  The descriptor table lives on the device and is rebuilt
+    only when the set of operands or one of their addresses changes.  Returns the number of operands."""
+    device = torch.device(device)
+    ents, sig = [], []
+    for key, ent in _SPLITS.items():
+        wt = ent[0]()
+        if wt is None or ent[3].device != device or wt.data_ptr() != ent[2]:
+            continue
+        ents.append((key, ent, wt))
+        sig.append((key, ent[2], ent[3].data_ptr()))
+    if not ents:
+        return 0
+    sig = tuple(sig)
+    tab = _SPLIT_TABLES.get(device)
+    if tab is None or tab[0] != sig:
+        descs = (_SplitDesc * len(ents))()
+        tile0 = 0
+        for d, (key, ent, wt) in zip(descs, ents):
+            _, transposed, c0, K, fmt = key
+            N, ld = wt.shape
+            rows, ncols = (K, N) if transposed else (N, K)
+            d.w, d.out = wt.data_ptr() + 4 * c0, ent[3].data_ptr()
+            d.rows, d.cols, d.ld, d.transposed, d.format = rows, ncols, ld, int(transposed), fmt
+            d.tiles_x, d.tile0, d.pad = (ncols + 31) // 32, tile0, 0
+            tile0 += d.tiles_x * ((rows + 31) // 32)
+        host = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+        tab = _SPLIT_TABLES[device] = (sig, host.to(device), len(ents), tile0)
+    STATS.launch("weight_split_batch", lib.hs_weight_split_batch, ptr(tab[1]), tab[2], tab[3], current_stream())
+    for key, ent, wt in ents:
+        _SPLITS[key] = (ent[0], wt._version, ent[2], ent[3], _SPLIT_EPOCH[0])
+    return len(ents)
 
 
 def _on_device(t) -> bool:
@@ -582,11 +689,11 @@ def _ln_tail_bwd(dy2, pre, mean, rstd, gamma, need_w, need_b, need_lin_bias=Fals
     G = gamma.numel()
     rows = pre.numel() // G
     dpre = torch.empty_like(pre)
-    dw = torch.zeros(G, device=pre.device, dtype=torch.float32) if need_w else None
-    db = torch.zeros(G, device=pre.device, dtype=torch.float32) if need_b else None
+    dw = zeros(G, pre.device) if need_w else None
+    db = zeros(G, pre.device) if need_b else None
     lin_bias = need_lin_bias and G == pre.shape[-1]
-    pb = torch.zeros(G, device=pre.device, dtype=torch.float32) if lin_bias else None
-    dpb = torch.zeros(G, device=pre.device, dtype=torch.float32) if lin_bias else None
+    pb = zeros(G, pre.device) if lin_bias else None
+    dpb = zeros(G, pre.device) if lin_bias else None
     STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dy2), ptr(pre), ptr(pb), ptr(mean), ptr(rstd), ptr(gamma),
                  None, 0, C.c_float(0.0), C.c_uint64(0), ptr(dpre), ptr(dw), ptr(db), ptr(dpb), rows, G,
                  current_stream(), tag=(rows, G))
@@ -723,8 +830,8 @@ class _LnLinearFn(torch.autograd.Function):
         if any(ctx.needs_input_grad[:3]):
             dxn = _dgrad(dy2, weight, None, (T, K))
             dx = torch.empty_like(x2)
-            dgamma = torch.zeros(K, device=x2.device, dtype=torch.float32) if ctx.needs_input_grad[1] else None
-            dbeta = torch.zeros(K, device=x2.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+            dgamma = zeros(K, x2.device) if ctx.needs_input_grad[1] else None
+            dbeta = zeros(K, x2.device) if ctx.needs_input_grad[2] else None
             STATS.launch("layernorm_bwd", lib.hs_layernorm_bwd, ptr(dxn), ptr(x2), None, ptr(mean), ptr(rstd), ptr(g), None, 0,
                          C.c_float(0.0), C.c_uint64(0), ptr(dx), ptr(dgamma), ptr(dbeta), None, T, K, current_stream(),
                          tag=(T, K))
@@ -757,7 +864,7 @@ def _dgrad(dy2, weight, d_pass, xshape, want_bias_grad=False):
     db = None
     if _dgrad_ok(dy2, weight):
         if want_bias_grad:
-            db = torch.zeros((N,), device=dy2.device, dtype=torch.float32)
+            db = zeros((N,), dy2.device)
         prec = _dgrad_prec(dy2.shape[0], K, N)
         dx = _gemm3(dy2, split_weight(weight, transposed=True, prec=prec), K, None, c,
                     _lib.GEMM_PLAIN if c is None else _lib.GEMM_ADD, colsum=db, prec=prec)
@@ -787,9 +894,9 @@ def _wgrad(dy2, x2, need_bias):
     db = None
     cover = lib.hs_linear_wgrad_supported(T, N, K) if (_CUSTOM_WGRAD and _on_device(dy2)) else 0
     if cover:
-        dw = torch.zeros((N, K), device=x2.device, dtype=torch.float32)
+        dw = zeros((N, K), x2.device)
         if need_bias and cover == 2:  # bias gradient in the same pass over dy
-            db = torch.zeros((N,), device=x2.device, dtype=torch.float32)
+            db = zeros((N,), x2.device)
         STATS.launch("linear_wgrad", lib.hs_linear_wgrad, ptr(dy2), ptr(x2), ptr(dw), ptr(db), T, N, K, _tc_flags(),
                      current_stream(), tag=(T, N, K))
     else:
@@ -983,7 +1090,7 @@ class _CatLinearFn(torch.autograd.Function):
         K1, K2 = a1.shape[1], a2.shape[1]
         dy2 = _f32c(dy).reshape(-1, N)
         need_b = has_bias and ctx.needs_input_grad[3]
-        db = torch.zeros((N,), device=dy2.device, dtype=torch.float32) if need_b else None
+        db = zeros((N,), dy2.device) if need_b else None
         dx1 = dx2 = dw = None
         if ctx.needs_input_grad[0]:
             p1 = _dgrad_prec(dy2.shape[0], K1, N)

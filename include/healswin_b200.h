@@ -240,6 +240,14 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
  */
 int hs_weight_split(const float* w_dev, int rows, int cols, int ld, int transposed, int format, uint16_t* out_dev,
                     void* stream);
+/*
+ * hs_weight_split for n matrices in one launch (the weight operands of a whole model, refreshed once per optimizer step).
+ * descs_dev: n device-resident descriptors of 48 bytes each,
+ *     { const float* w; uint16_t* out; int32 rows, cols, ld, transposed, format, tiles_x, tile0, pad; }
+ * with tiles_x = ceil(cols / 32), tile0 = running sum of tiles_x * ceil(rows / 32) over the preceding descriptors
+ * (ascending), total_tiles = that sum over all n.
+ */
+int hs_weight_split_batch(const void* descs_dev, int n, int total_tiles, void* stream);
 int hs_gemm3_supported(int64_t T, int N, int K);
 int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_dev, const float* aux_dev, float* d_dev,
              float* d2_dev, float* colsum_dev, int64_t T, int N, int K, int mode, int precision, float drop, uint64_t seed,

@@ -433,3 +433,36 @@ def test_patch_merging_module_matches_torch_fp64():
     assert rel_err(y.detach().cpu(), y64.detach().cpu()) < 1e-4
     for name, a_, b_ in zip(["x", "gamma", "beta", "W"], got, want):
         assert rel_err(a_.cpu(), b_.cpu()) < (2e-3 if name == "W" else 3e-4), (name, rel_err(a_.cpu(), b_.cpu()))
+
+
+def test_batched_weight_split_equals_individual_splits():
+    """ops.refresh_weight_splits (one hs_weight_split_batch launch over every cached operand) writes bit-identical
+    operands to the per-matrix kernel, for forward / transposed / column-block / TF32-format entries, and picks up
+    parameter updates that did not bump the version counter (fused optimizers)."""
+    from heal_swin_b200 import _lib, ops
+
+    dev = torch.device("cuda:0")
+    ops.invalidate_weight_splits()
+    torch.manual_seed(0)
+    ws = [torch.nn.Parameter(torch.randn(n, k, device=dev)) for n, k in [(96, 96), (288, 96), (200, 100), (96, 384), (384, 192)]]
+    outs = []
+    for w in ws:
+        outs.append(ops.split_weight(w))
+        outs.append(ops.split_weight(w, transposed=True))
+        outs.append(ops.split_weight(w, transposed=True, prec=_lib.PREC_TF32))
+    outs.append(ops.split_weight(ws[4], cols=(96, 96)))
+    with torch.no_grad():
+        for w in ws:
+            w.data.mul_(1.5).add_(0.25)  # (no version bump through .data)
+    n = ops.refresh_weight_splits(dev)
+    assert n == len(outs)
+    got = [o.clone() for o in outs]
+    ops.invalidate_weight_splits()
+    want = []
+    for w in ws:
+        want.append(ops.split_weight(w))
+        want.append(ops.split_weight(w, transposed=True))
+        want.append(ops.split_weight(w, transposed=True, prec=_lib.PREC_TF32))
+    want.append(ops.split_weight(ws[4], cols=(96, 96)))
+    for a_, b_ in zip(got, want):
+        assert torch.equal(a_.view(torch.int16), b_.view(torch.int16))
