@@ -511,13 +511,21 @@ def _fwd_prec() -> int:
     return _lib.PREC_BF16 if _GEMM_PRECISION == "bf16" else _lib.PREC_BF16X3
 
 
+def _dgrad_tensor_bound(n_out, k_contract) -> bool:
+    """Whether three bf16 MMAs per product would make an input-gradient GEMM dx (T, n_out) = dy (T, k_contract) @ W
+    tensor-bound (per output element 6 * k flops at ~1.2 PFLOP/s against 4 * (n + k) / n bytes at ~6 TB/s, i.e.
+    n k / (n + k) > ~130: stages 2-3 of the N_side=256 network, the MLP gradients from stage 1 on)."""
+    return _TF32_DGRAD and n_out * k_contract > 130 * (n_out + k_contract)
+
+
 def _dgrad_prec(T, n_out, k_contract) -> int:
-    """Input-gradient GEMM dx (T, n_out) = dy (T, k_contract) @ W: TF32 where three bf16 MMAs per product would make the
-    launch tensor-bound (per output element 6 * k flops at ~1.2 PFLOP/s against 4 * (n + k) / n bytes at ~6 TB/s, i.e.
-    n k / (n + k) > ~130: stages 2-3 of the N_side=256 network), bf16x3 where the launch is HBM-bound anyway."""
+    """Input-gradient GEMM: fp32-class (bf16x3) where the launch is HBM-bound anyway; one TF32 MMA per product where it
+    would be tensor-bound -- gradients are compared at 5e-3 and the weight gradients are TF32 already.  (Tried and
+    rejected on the B200: two MMAs with dy split into bf16 hi / lo and the weight in FP16 -- a kind::f16 MMA with MIXED
+    operand formats is an illegal instruction, and with both operands bf16 the weight keeps 8 bits, 4x coarser than TF32.)"""
     if _GEMM_PRECISION == "bf16":
         return _lib.PREC_BF16
-    if _TF32_DGRAD and n_out * k_contract > 130 * (n_out + k_contract):
+    if _dgrad_tensor_bound(n_out, k_contract):
         return _lib.PREC_TF32
     return _lib.PREC_BF16X3
 
@@ -1005,7 +1013,11 @@ class _MlpFn(torch.autograd.Function):
             J, Cout = w1.shape[0], w2.shape[0]
             dy2 = _f32c(dy).reshape(T, Cout)
             dw2, _ = _wgrad(dy2, h, False)
-        if _TF32_MLP_DGRAD and lib.hs_mlp_dgrad_gelu_supported(T, Cout, J):
+        # stage 0 (HBM-bound): the dedicated TF32 kernel; from stage 1 on, where one TF32 MMA per product is what
+        # _dgrad_prec picks anyway, the general GEMM with the GELU' epilogue is faster (C = 192: 0.54 against 0.65 ms,
+        # scripts/mlp_dgrad_s1.py)
+        if (_TF32_MLP_DGRAD and lib.hs_mlp_dgrad_gelu_supported(T, Cout, J)
+                and not (_GEMM_PRECISION != "bf16" and _dgrad_tensor_bound(J, Cout))):
             dz = torch.empty_like(z)
             STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1),
                          C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, _tc_flags(), current_stream(),
