@@ -7,8 +7,10 @@ backward once and replays it: one launch per step, no host work in between.
 What makes the capture legal: every hs_* entry point takes its stream explicitly (``ops.current_stream()`` is the
 capturing stream, also on the autograd thread), allocates nothing and never synchronises; TMA descriptors are kernel
 parameters built on the host from addresses that torch serves from the graph's private pool, hence stable across replays;
-the weight-split cache re-launches its (cheap) split kernels inside a capture instead of trusting the host-side version
-check, so a replay always sees the weights the optimizer just wrote.
+the weight operands of the GEMMs (split / rounded copies of the parameters) are refreshed by ONE batched launch before
+every replay (``ops.refresh_weight_splits``), so a replay always sees the weights the optimizer just wrote without ~200
+split kernels inside the graph; the small zero-initialised accumulators of the backward (~360 per step) are slices of one
+arena that the captured step clears with a single memset (``ops.ZeroArena``).
 
 Data parallelism: the captured part is rank-local.  Gradients live in ONE flat buffer (each ``p.grad`` is a view), so the
 exchange step after the replay is a single NCCL all-reduce over NVLink, followed by the (eager, fused) optimizer step.
