@@ -333,12 +333,16 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             for (int ks = 0; ks < 2; ++ks) {
               const uint64_t a_hi = umma_desc_at(kDesc, ab + 32 * ks), a_lo = umma_desc_at(kDesc, ab + 64 + 32 * ks);
               const uint64_t w_hi = umma_desc_at(kDesc, wk + 32 * ks), w_lo = umma_desc_at(kDesc, wk + 64 + 32 * ks);
-              if (pair) {
-                umma_bf16_ss_pair(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+              const uint32_t acc0 = (kc > 0 || ks > 0) ? 1u : 0u;
+              if (a.prec == PREC_BF16) {  // "bf16 operands, fp32 accumulate": the hi terms only
+                if (pair) umma_bf16_ss_pair(d, a_hi, w_hi, idesc, acc0);
+                else umma_bf16_ss(d, a_hi, w_hi, idesc, acc0);
+              } else if (pair) {
+                umma_bf16_ss_pair(d, a_lo, w_hi, idesc, acc0);
                 umma_bf16_ss_pair(d, a_hi, w_lo, idesc, 1u);
                 umma_bf16_ss_pair(d, a_hi, w_hi, idesc, 1u);
               } else {
-                umma_bf16_ss(d, a_lo, w_hi, idesc, (kc > 0 || ks > 0) ? 1u : 0u);
+                umma_bf16_ss(d, a_lo, w_hi, idesc, acc0);
                 umma_bf16_ss(d, a_hi, w_lo, idesc, 1u);
                 umma_bf16_ss(d, a_hi, w_hi, idesc, 1u);
               }
@@ -941,8 +945,16 @@ int plan(G3Args& a, int mode, int E) {
   const int rw_min = ln ? (a.save_pre ? 3 : 2) : (aux ? 2 : 1), rw_max = (aux || ln) ? 3 : 2;
   // tensor-bound launches (streamed W, long contraction) keep A in shared memory and use 256-column stages: fewer, wider
   // MMAs (ncu: 69 % tensor-pipe active against 59 % with 192-column chunks); HBM-bound launches take A through TMEM
-  a.ss = (a.prec == PREC_TF32 || (a.prec == PREC_BF16X3 && (long long)a.N * a.K > 130ll * (a.N + a.K) && a.K >= 256)) ? 1 : 0;
-  if (const char* e = getenv("HEALSWIN_GEMM3_SS")) a.ss = (a.prec == PREC_TF32) ? 1 : (atoi(e) != 0 && a.prec == PREC_BF16X3);
+  // (PREC_BF16, one MMA per product, takes the same route: what binds it first is not the tensor pipe but the L2 ->
+  // shared-memory stream of W slices, which the pair's M = 256 tiles halve per token.  BASELINE configs[3], C = 128, one
+  // training step: 191.3 ms with the TMEM-A route everywhere, 183.8 / 178.6 / 178.2 ms with the threshold at 390 / 200 / 130)
+  long long ridge_k = a.prec == PREC_BF16 ? 160 : 130;
+  if (const char* e = getenv("HEALSWIN_GEMM3_BF16_RIDGE")) {  // experiments only
+    if (a.prec == PREC_BF16 && atoll(e) > 0) ridge_k = atoll(e);
+  }
+  const long long ai = (long long)a.N * a.K, ridge = ridge_k * (a.N + a.K);
+  a.ss = (a.prec == PREC_TF32 || (ai > ridge && a.K >= 256)) ? 1 : 0;
+  if (const char* e = getenv("HEALSWIN_GEMM3_SS")) a.ss = (a.prec == PREC_TF32) ? 1 : (atoi(e) != 0);
   if (ln) a.ss = 0;  // the LN epilogue works on 192-column stages whose chunks hold whole LN groups
   a.stage_cols = a.ss ? 256 : 192;
   // CTA pairs (cta_group::2, M = 256): each CTA of a pair stages only half of every W slice, which halves the B-operand
