@@ -52,13 +52,14 @@ class GraphedTrainStep:
         self.seed_counter = ops.seed_counter(example_x.device)
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.params = [q for q in model.parameters() if q.requires_grad]
-        total = sum(q.numel() for q in self.params)
+        pad = lambda n: (n + 63) // 64 * 64  # every slice starts on a 256-byte boundary
+        total = sum(pad(q.numel()) for q in self.params)
         self.flat_grad = torch.zeros(total, device=example_x.device, dtype=torch.float32)
         off = 0
         for q in self.params:
             assert q.dtype == torch.float32
             q.grad = self.flat_grad[off:off + q.numel()].view_as(q)
-            off += q.numel()
+            off += pad(q.numel())
         self.x = example_x.clone()
         self.t = example_t.clone()
         self.warmup = warmup
