@@ -216,11 +216,17 @@ def alg_bytes(name, tag):
         return tag[0] * (tag[1] + tag[2] + 2) * 4
     if name == "ln_head_bwd":      # x, dlogits, mean, rstd in, dx out
         return tag[0] * (2 * tag[1] + tag[2] + 2) * 4
-    if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible
+    if name == "mlp_dgrad_gelu":   # dy (T, C), z (T, J) in, dz (T, J) out; W2 negligible (compact form: FP16 g' instead of z)
+        if len(tag) > 3 and tag[3]:
+            return tag[0] * (tag[1] * 4 + tag[2] * 6)
         return tag[0] * (tag[1] + 2 * tag[2]) * 4
     if name == "gemm3":            # tag (T, N, K, mode, precision): a (T, K) in, d (T, N) out, + aux in (modes 1, 3) / d2 out (2)
-        if tag[3] >= 4:            # hs_gemm3_ln: mode tag 4 + (1: shortcut in) + (2: pre-norm tensor out as well); y out
-            return tag[0] * (tag[2] + tag[1] * (1 + ((tag[3] - 4) & 1) + ((tag[3] - 4) >> 1))) * 4
+        if tag[3] == 20:           # hs_gemm3_lnin (PatchMerging): raw rows in, result out
+            return tag[0] * (tag[2] + tag[1]) * 4
+        if tag[3] >= 10:           # hs_gemm3_ln: mode tag 10 + (1: shortcut in) + (2: pre-norm tensor out as well); y out
+            return tag[0] * (tag[2] + tag[1] * (1 + ((tag[3] - 10) & 1) + ((tag[3] - 10) >> 1))) * 4
+        if tag[3] in (6, 7):       # compact GELU modes: h (fp32) + g' (FP16) out / g' in + dz out
+            return tag[0] * (tag[2] * 4 + tag[1] * 6)
         return tag[0] * (tag[2] + tag[1] * (1 if tag[3] == 0 else 2)) * 4
     return None
 

@@ -16,7 +16,9 @@ SHIFT_NONE, SHIFT_NEST_ROLL, SHIFT_NEST_GRID, SHIFT_RING = 0, 1, 2, 3
 ATTN_COS = 1
 ATTN_NO_TC = 2
 ATTN_NO_TRUNC_COMP = 4
+MLP_GRAD16 = 256
 GEMM_PLAIN, GEMM_ADD, GEMM_GELU, GEMM_GELU_GRAD = 0, 1, 2, 3
+GEMM_GELU_C, GEMM_GELU_GRAD_C = 6, 7  # compact forms: the activation's derivative as FP16 instead of z
 PREC_BF16X3, PREC_TF32, PREC_BF16 = 0, 1, 2
 
 STRATEGY_CODES = {"nest_roll": SHIFT_NEST_ROLL, "nest_grid_shift": SHIFT_NEST_GRID, "ring_shift": SHIFT_RING}

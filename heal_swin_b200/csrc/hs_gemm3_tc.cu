@@ -28,6 +28,9 @@
 //     MODE_ADD        add the bias and an fp32 tensor of D's shape (aux) -- the residual-shortcut gradient in a dgrad
 //     MODE_GELU       write z = acc (D) and h = dropout(GELU(acc + bias)) (D2): Mlp fc1 + act + drop in one pass
 //     MODE_GELU_GRAD  D = acc * GELU'(aux + bias) * dropmask: the fc2 input gradient through the activation
+//     MODE_GELU_C     as MODE_GELU, but instead of z the epilogue writes g' = GELU'(acc + bias) * dropmask as FP16 (a quarter
+//                     of the bytes of z and h together; g' lies in [-0.13, 1.13] / (1 - p)): all the backward needs
+//     MODE_GELU_GRAD_C  D = acc * g' with that FP16 tensor read straight from global memory (no GELU arithmetic, no mask)
 //     MODE_LN         D2 = [aux +] LayerNorm_G(acc + bias) * gamma + beta over groups of G consecutive output columns, with
 //                     D = acc + bias (the pre-norm tensor the backward needs) and the row statistics as optional outputs:
 //                     PatchExpand's Linear -> view (B, 4N, C/2) -> LayerNorm (swin_hp_transformer.py:420-430) and the
@@ -46,6 +49,8 @@
 // same column chunk and run tcgen05.mma.cta_group::2 (M = 256) issued by the leader; each stages only half of every W
 // slice, which halves the B-operand traffic on its shared-memory port.
 #include <cstdlib>
+
+#include <cuda_fp16.h>
 
 #include "hs_common.h"
 #include "hs_gelu.cuh"
@@ -67,7 +72,8 @@ constexpr int kTeam = 4;               // converter warps per chunk (one per TME
 constexpr int kASlots = 4;             // A-operand slots of 32 TMEM columns behind two 192-column accumulator stages
 constexpr int kACol0 = 2 * 192;
 
-enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3, MODE_LN = 4, MODE_LN_IN = 5 };
+enum : int { MODE_PLAIN = 0, MODE_ADD = 1, MODE_GELU = 2, MODE_GELU_GRAD = 3, MODE_LN = 4, MODE_LN_IN = 5, MODE_GELU_C = 6,
+              MODE_GELU_GRAD_C = 7 };
 constexpr int kLnExch = 2 * 2 * 128 * 2 * 8;  // MODE_LN: partial row statistics exchanged between the two epilogue groups
 // operand precision: three bf16 MMAs per product (fp32-class), one TF32 MMA (A straight from the fp32 tile, no conversion;
 // input gradients of the tensor-bound stages), one bf16 MMA ("bf16 operands, fp32 accumulate": BASELINE configs[3])
@@ -100,6 +106,8 @@ struct G3Args {
   int has_aux;   // D2 += aux
   // MODE_LN_IN: s[n] = sum_k gamma[k] W[n][k] (bias holds b0 = W beta; mean_out / rstd_out (T) optional; eps as above)
   const float* wsum;
+  // MODE_GELU_C (written) / MODE_GELU_GRAD_C (read): g' (T, N) as FP16, row-major; N a multiple of 32
+  uint16_t* gp16;
 };
 
 // instruction descriptor: D = f32, A = B = bf16, both K-major
@@ -157,7 +165,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
              const __grid_constant__ CUtensorMap map_d2, const G3Args a) {
   constexpr bool kAux = (MODE == MODE_ADD || MODE == MODE_GELU_GRAD);
   constexpr int NG = E / 4;                    // epilogue groups (4 warps = the 4 TMEM lane quadrants)
-  constexpr int kStores = (MODE == MODE_GELU) ? 2 : 1;
+  constexpr int kStores = (MODE == MODE_GELU || MODE == MODE_GELU_C) ? 2 : 1;
   constexpr bool kColsumOk = (MODE == MODE_PLAIN || MODE == MODE_ADD);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -225,7 +233,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_d);
     if (kAux || MODE == MODE_LN) tma_prefetch_desc(&map_aux);
-    if (MODE == MODE_GELU || MODE == MODE_LN) tma_prefetch_desc(&map_d2);
+    if (MODE == MODE_GELU || MODE == MODE_GELU_C || MODE == MODE_LN) tma_prefetch_desc(&map_d2);
   }
   tc_fence_before();
   __syncthreads();
@@ -732,13 +740,25 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       for (long long u = 0; u < rw && u < total; ++u) issue_aux(u);
     long long cnt = 0;  // staging-region uses so far
     long long it = 0;
+    // MODE_GELU_GRAD_C: this row's 32 g' values (FP16) of the NEXT slab this warp will process are requested as soon as the
+    // current ones have been consumed (same registers): their latency hides behind the store and the next accumulator wait
+    uint4 gq[MODE == MODE_GELU_GRAD_C ? 4 : 1];
+    auto fetch_gq = [&](long long tile, int s) {
+      const long long row = tile * kBM + q * 32 + lane;
+      const uint4* src = reinterpret_cast<const uint4*>(a.gp16 + row * a.N + n0 + 32 * s);
+#pragma unroll
+      for (int i = 0; i < (MODE == MODE_GELU_GRAD_C ? 4 : 1); ++i)
+        gq[i] = (tile < t_end && s < S && row < a.T) ? __ldcs(src + i) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    if constexpr (MODE == MODE_GELU_GRAD_C) fetch_gq(t0, g);
     for (long long tile = t0; tile < t_end; tile += tstep, ++it) {
       const int as = (int)(it & 1);
       mbar_wait(&acc_full[as], ((uint32_t)(it >> 1)) & 1);
       tc_fence_after();
       const long long grow = tile * kBM + q * 32 + lane;
       uint32_t dkey = 0;
-      if (MODE == MODE_GELU || MODE == MODE_GELU_GRAD) dkey = a.drop_thresh ? hs::drop_row_key(a.seed, grow) : 0u;
+      if (MODE == MODE_GELU || MODE == MODE_GELU_GRAD || MODE == MODE_GELU_C)
+        dkey = a.drop_thresh ? hs::drop_row_key(a.seed, grow) : 0u;
       float ln_mean = 0.f, ln_rstd = 0.f;
       if constexpr (MODE == MODE_LN_IN) {  // the converters' partial row statistics of this tile -> mean, 1 / std
         const float2* st = reinterpret_cast<const float2*>(s_colsum) + (size_t)(it & 3) * 256 + q * 32 + lane;
@@ -765,11 +785,12 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
       };
       if (spw == 0) release_stage();  // more groups than slabs: stay in step with the accumulator stages
       for (int s = g; s < S; s += NG) {
+        const int jc = n0 + 32 * s;
+        uint32_t gpk[MODE == MODE_GELU_C ? 16 : 1];  // g' of this row's 32 columns, packed FP16 pairs
         uint32_t acc[32];
         tmem_ld32(tmem + lane_addr + (uint32_t)as * a.stage_cols + 32 * s, acc);
         tmem_wait_ld();
         if (s + NG >= S) release_stage();  // this thread's last slab of the tile is in registers
-        const int jc = n0 + 32 * s;
 #pragma unroll
         for (int st = 0; st < kStores; ++st, ++cnt) {
           const int reg = (int)(cnt % rw);
@@ -814,6 +835,33 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
                   o.w = hs::drop_keep_elem(dkey, jc + 4 * c + 3, a.drop_thresh) ? o.w * a.drop_scale : 0.f;
                 }
               }
+            } else if (MODE == MODE_GELU_C) {
+              if (st == 0) {
+                // h and g' from ONE evaluation of the erf terms: g' goes out now (packed FP16), h replaces the
+                // accumulator values in registers and goes out in the second pass
+                const float u4[4] = {o.x + bv.x, o.y + bv.y, o.z + bv.z, o.w + bv.w};
+                float g4[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const hs::GeluTerms t = hs::gelu_terms(u4[e]);
+                  float hv = u4[e] * t.cdf;
+                  g4[e] = fmaf(u4[e] * 0.39894228040143267794f, t.e, t.cdf);
+                  if (a.drop_thresh) {
+                    const bool keep = hs::drop_keep_elem(dkey, jc + 4 * c + e, a.drop_thresh);
+                    hv = keep ? hv * a.drop_scale : 0.f;
+                    g4[e] = keep ? g4[e] * a.drop_scale : 0.f;
+                  }
+                  acc[4 * c + e] = __float_as_uint(hv);
+                }
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(gpk[2 * c + 0]) : "f"(g4[1]), "f"(g4[0]));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(gpk[2 * c + 1]) : "f"(g4[3]), "f"(g4[2]));
+                continue;  // (the FP16 rows are written after the loop)
+              }
+            } else if (MODE == MODE_GELU_GRAD_C) {
+              const uint32_t w0 = c & 1 ? gq[c >> 1].z : gq[c >> 1].x, w1 = c & 1 ? gq[c >> 1].w : gq[c >> 1].y;
+              const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+              const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+              o.x *= g01.x; o.y *= g01.y; o.z *= g23.x; o.w *= g23.y;
             } else {  // MODE_GELU_GRAD
               const float4 z = lds_f4(p);
               o.x *= hs::gelu_grad_fast(z.x + bv.x); o.y *= hs::gelu_grad_fast(z.y + bv.y);
@@ -827,10 +875,24 @@ gemm3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
             }
             sts_f4(p, o);
           }
+          if constexpr (MODE == MODE_GELU_GRAD_C) {  // (gq consumed) -> the next slab of this warp: same tile, or the next tile's first
+            if (s + NG < S) fetch_gq(tile, s + NG);
+            else fetch_gq(tile + tstep, g);
+          }
+          if constexpr (MODE == MODE_GELU_C) {
+            if (st == 0) {  // the g' sub-slab: 32 rows of 64 bytes, SWIZZLE_64B (16-byte chunk ^= (row >> 1) & 3)
+              const uint32_t r64 = my_u32 + reg * kRegion + lane * 64;
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                sts_u4(r64 + ((i ^ ((lane >> 1) & 3)) << 4),
+                       make_uint4(gpk[4 * i + 0], gpk[4 * i + 1], gpk[4 * i + 2], gpk[4 * i + 3]));
+            }
+          }
           fence_proxy_async_smem();
           __syncwarp();  // all 32 rows of the sub-slab are in the staging region
           if (lane == 0) {
-            tma_store_2d((MODE == MODE_GELU && st == 1) ? &map_d2 : &map_d, my + reg * kRegion, jc,
+            tma_store_2d(((MODE == MODE_GELU && st == 1) || (MODE == MODE_GELU_C && st == 0)) ? &map_d2 : &map_d,
+                         my + reg * kRegion, jc,
                          (int)(tile * kBM) + 32 * q);
             tma_store_commit();
             if (kAux && cnt + rw < total) {  // refill this region with the aux sub-slab of the use rw ahead
@@ -929,6 +991,20 @@ int make_map_bf16(CUtensorMap* m, const uint16_t* base, long long rows, long lon
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+  return HS_OK;
+}
+
+int make_map_f16(CUtensorMap* m, const uint16_t* base, long long rows, long long cols, int box_cols, int box_rows) {
+  hs::tc::EncodeTiledFn enc = hs::tc::encode_fn();
+  if (!enc) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return hs::fail(HS_ERR_CUDA, "cuTensorMapEncodeTiled (f16) failed with CUresult %d", (int)r);
   return HS_OK;
 }
 
@@ -1080,6 +1156,7 @@ int launch(const float* a_dev, const uint16_t* w_dev, const float* aux_dev, floa
   m.d2 = m.d;
   if (aux_dev && (rc = hs::tc::make_map(&m.aux, aux_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
   if (d2_dev && (rc = hs::tc::make_map(&m.d2, d2_dev, a.T, a.N, CU_TENSOR_MAP_SWIZZLE_128B, 32, 32))) return rc;
+  if (MODE == MODE_GELU_C && (rc = make_map_f16(&m.d2, a.gp16, a.T, a.N, 32, 32))) return rc;  // the FP16 g' tensor
   const size_t smem = smem_bytes<E>(a);
   const int cs = a.cluster;
   int per_chunk = hs::tc::sm_count() / a.n_chunks;
@@ -1124,14 +1201,18 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
              void* stream) {
   HS_REQUIRE(a_dev && wsplit_dev && d_dev && T > 0, "hs_gemm3: bad arguments");
   HS_REQUIRE(precision >= PREC_BF16X3 && precision <= PREC_BF16, "hs_gemm3: unknown precision %d", precision);
-  HS_REQUIRE(mode >= MODE_PLAIN && mode <= MODE_GELU_GRAD, "hs_gemm3: unknown mode %d", mode);
+  HS_REQUIRE((mode >= MODE_PLAIN && mode <= MODE_GELU_GRAD) || mode == MODE_GELU_C || mode == MODE_GELU_GRAD_C,
+             "hs_gemm3: unknown mode %d", mode);
+  HS_REQUIRE(!(mode == MODE_GELU_C || mode == MODE_GELU_GRAD_C) || N % 32 == 0,
+             "hs_gemm3: the compact GELU modes need N to be a multiple of 32, got %d", N);
   HS_REQUIRE(drop >= 0.f && drop < 1.f, "hs_gemm3: drop must be in [0, 1), got %f", drop);
   if (!hs_gemm3_supported(T, N, K))
     return hs::fail(HS_ERR_UNSUPPORTED, "hs_gemm3: shape T=%lld N=%d K=%d is not covered (N, K multiples of 4)",
                     (long long)T, N, K);
   const bool aux = (mode == MODE_ADD || mode == MODE_GELU_GRAD);
   HS_REQUIRE(!aux || aux_dev, "hs_gemm3: mode %d needs the aux tensor", mode);
-  HS_REQUIRE(mode != MODE_GELU || d2_dev, "hs_gemm3: MODE_GELU needs the second output");
+  HS_REQUIRE((mode != MODE_GELU && mode != MODE_GELU_C) || d2_dev, "hs_gemm3: the GELU modes need the second output");
+  HS_REQUIRE(mode != MODE_GELU_GRAD_C || aux_dev, "hs_gemm3: mode 7 needs the FP16 g' tensor (aux)");
   HS_REQUIRE(!colsum_dev || mode == MODE_PLAIN || mode == MODE_ADD, "hs_gemm3: column sums ride with modes 0 and 1 only");
   HS_REQUIRE(!((reinterpret_cast<uintptr_t>(a_dev) | reinterpret_cast<uintptr_t>(wsplit_dev) |
                 reinterpret_cast<uintptr_t>(bias_dev) | reinterpret_cast<uintptr_t>(aux_dev) |
@@ -1147,6 +1228,13 @@ int hs_gemm3(const float* a_dev, const uint16_t* wsplit_dev, const float* bias_d
     case MODE_PLAIN: return launch<8, MODE_PLAIN>(a_dev, wsplit_dev, nullptr, d_dev, nullptr, a, st);
     case MODE_ADD: return launch<8, MODE_ADD>(a_dev, wsplit_dev, aux_dev, d_dev, nullptr, a, st);
     case MODE_GELU: return launch<16, MODE_GELU>(a_dev, wsplit_dev, nullptr, d_dev, d2_dev, a, st);
+    case MODE_GELU_C:  // d_dev: the FP16 g' tensor (written from registers), d2_dev: h (the one TMA-stored output)
+      a.gp16 = reinterpret_cast<uint16_t*>(d_dev);
+      return launch<16, MODE_GELU_C>(a_dev, wsplit_dev, nullptr, d2_dev, nullptr, a, st);
+    case MODE_GELU_GRAD_C:  // aux_dev: the FP16 g' tensor (read straight from global memory)
+      a.gp16 = reinterpret_cast<uint16_t*>(const_cast<float*>(aux_dev));
+      if (K <= 256) return launch<16, MODE_GELU_GRAD_C>(a_dev, wsplit_dev, nullptr, d_dev, nullptr, a, st);
+      return launch<8, MODE_GELU_GRAD_C>(a_dev, wsplit_dev, nullptr, d_dev, nullptr, a, st);
     default:
       // the GELU' arithmetic wants 16 epilogue warps where the launch is HBM-bound (short contraction); with a long
       // contraction it is tensor-bound and the shared memory is better spent on the operand rings

@@ -10,6 +10,13 @@
 //               GELU'(z + b1) on the z slab TMA put in shared memory (and the dropout mask), TMA-store the slab as dz;
 //               two TMEM stages and a ring of slab buffers overlap all of it with the next tile's loads and MMAs
 // Warps: 0-15 epilogue (group = warp / 4, TMEM lane quadrant = warp % 4), 16 dy producer, 17 MMA issuer, 18 z producer.
+//
+// Compact form (flag HS_MLP_GRAD16): the forward (hs_gemm3 mode 6) saved g' = GELU'(z + b1) o dropmask as FP16 instead of z.
+// Then dz = (dy @ W2) o g': every epilogue thread reads its row's 32 g' values (64 bytes, two full sectors) straight
+// from global memory before it waits for the accumulator -- no z slabs through shared memory (a third of this kernel's
+// bytes), no GELU arithmetic, no mask regeneration; the slab buffers are output staging only.
+#include <cuda_fp16.h>
+
 #include "hs_common.h"
 #include "hs_gelu.cuh"
 #include "hs_sm100.cuh"
@@ -28,6 +35,7 @@ constexpr int kEpiWarps = 16;
 constexpr int kThreads = (kEpiWarps + 3) * 32;
 
 struct MdArgs {
+  const uint16_t* gp16;  // compact form: g' (T, J) as FP16, else null
   const float* b1;  // (J) or null
   long long T;
   int C, J;
@@ -42,6 +50,7 @@ struct MdArgs {
 
 __device__ __forceinline__ float gelu_grad_f(float u) { return hs::gelu_grad_fast(u); }
 
+template <bool kCompact>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_dgrad_gelu_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_z, const __grid_constant__ CUtensorMap map_dz, const MdArgs a) {
@@ -135,7 +144,7 @@ mlp_dgrad_gelu_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
       }
     }
   } else if (warp == kEpiWarps + 2) {
-    if (elect_one()) {
+    if (!kCompact && elect_one()) {
       int buf = 0;
       uint32_t ph = 0;
       for (long long tile = t0; tile < a.tiles; tile += tstep)
@@ -152,15 +161,29 @@ mlp_dgrad_gelu_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
     const int r = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const int jc = j0 + 32 * eg;
-    float4 bv[8];
+    float4 bv[kCompact ? 1 : 8];
+    if constexpr (!kCompact) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c)
-      bv[c] = a.b1 ? __ldg(reinterpret_cast<const float4*>(a.b1 + jc + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 8; ++c)
+        bv[c] = a.b1 ? __ldg(reinterpret_cast<const float4*>(a.b1 + jc + 4 * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     long long it = 0;
+    // compact form: this row's 32 g' values of the NEXT tile are requested as soon as the current ones have been consumed
+    // (same registers), a whole tile period before they are needed
+    uint4 gq[kCompact ? 4 : 1];
+    auto fetch_gq = [&](long long tile) {
+      const long long row = tile * kBM + r;
+      const uint4* src = reinterpret_cast<const uint4*>(a.gp16 + row * a.J + jc);
+#pragma unroll
+      for (int i = 0; i < (kCompact ? 4 : 1); ++i)
+        gq[i] = (tile < a.tiles && row < a.T) ? __ldcs(src + i) : make_uint4(0u, 0u, 0u, 0u);
+    };
+    if constexpr (kCompact) fetch_gq(t0);
     for (long long tile = t0; tile < a.tiles; tile += tstep, ++it) {
       const int as = (int)(it & 1);
       const long long g = it * 4 + eg;
       const int buf = (int)(g % R);
+      const long long grow = tile * kBM + r;
       mbar_wait(&acc_full[as], ((uint32_t)(it >> 1)) & 1);
       tc_fence_after();
       uint32_t acc[32];
@@ -168,10 +191,26 @@ mlp_dgrad_gelu_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);  // this thread's part of the accumulator stage is in registers
-      const long long grow = tile * kBM + r;
       const uint32_t dkey = a.drop_thresh ? hs::drop_row_key(a.seed, grow) : 0u;
-      mbar_wait(&z_full[buf], ((uint32_t)(g / R)) & 1);
       uint8_t* zrow = s_z + buf * kSub + r * 128;
+      if constexpr (kCompact) {
+        // the buffer is free once the store that last used it has read it (z_empty; fresh barriers pass the first round)
+        mbar_wait(&z_empty[buf], (((uint32_t)(g / R)) & 1) ^ 1);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t w0 = c & 1 ? gq[c >> 1].z : gq[c >> 1].x, w1 = c & 1 ? gq[c >> 1].w : gq[c >> 1].y;
+          const float2 g01 = __half22float2(*reinterpret_cast<const __half2*>(&w0));
+          const float2 g23 = __half22float2(*reinterpret_cast<const __half2*>(&w1));
+          float4 o;
+          o.x = __uint_as_float(acc[4 * c + 0]) * a.fix * g01.x;
+          o.y = __uint_as_float(acc[4 * c + 1]) * a.fix * g01.y;
+          o.z = __uint_as_float(acc[4 * c + 2]) * a.fix * g23.x;
+          o.w = __uint_as_float(acc[4 * c + 3]) * a.fix * g23.y;
+          *reinterpret_cast<float4*>(zrow + ((c ^ (r & 7)) << 4)) = o;
+        }
+        fetch_gq(tile + tstep);
+      } else {
+      mbar_wait(&z_full[buf], ((uint32_t)(g / R)) & 1);
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float4* p = reinterpret_cast<float4*>(zrow + ((c ^ (r & 7)) << 4));
@@ -188,6 +227,7 @@ mlp_dgrad_gelu_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_c
           o.w = hs::drop_keep_elem(dkey, jc + 4 * c + 3, a.drop_thresh) ? o.w * a.drop_scale : 0.f;
         }
         *p = o;
+      }
       }
       fence_proxy_async_smem();
       named_bar_sync(1 + eg, 128);  // every row of the slab holds dz now
@@ -223,6 +263,11 @@ int hs_mlp_dgrad_gelu(const float* dy, const float* w2, const float* z, const fl
   HS_REQUIRE(!((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(w2) | reinterpret_cast<uintptr_t>(z) |
                 reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(b1)) & 15), "hs_mlp_dgrad_gelu: unaligned tensor");
   MdArgs a{};
+  if (flags & HS_MLP_GRAD16) {  // z_dev is the FP16 g' tensor of hs_gemm3 mode 6: no bias, no mask left to apply
+    a.gp16 = reinterpret_cast<const uint16_t*>(z);
+    b1 = nullptr;
+    drop = 0.f;
+  }
   a.b1 = b1; a.T = T; a.C = C; a.J = J; a.n_chunks = J / kNJ; a.tiles = (T + kBM - 1) / kBM;
   a.fix = (flags & HS_ATTN_NO_TRUNC_COMP) ? 1.0f : hs::tc::kTruncFix2;
   a.drop_thresh = drop > 0.f ? hs::drop_thresh(drop) : 0u;
@@ -232,7 +277,7 @@ int hs_mlp_dgrad_gelu(const float* dy, const float* w2, const float* z, const fl
   int rc;
   if ((rc = hs::tc::make_map(&map_dy, dy, T, C, CU_TENSOR_MAP_SWIZZLE_128B, 32, kBM))) return rc;
   if ((rc = hs::tc::make_map(&map_w, w2, C, J, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, 32, C))) return rc;
-  if ((rc = hs::tc::make_map(&map_z, z, T, J, CU_TENSOR_MAP_SWIZZLE_128B, 32, kBM))) return rc;
+  if (!a.gp16 && (rc = hs::tc::make_map(&map_z, z, T, J, CU_TENSOR_MAP_SWIZZLE_128B, 32, kBM))) return rc;
   if ((rc = hs::tc::make_map(&map_dz, dz, T, J, CU_TENSOR_MAP_SWIZZLE_128B, 32, kBM))) return rc;
   // shared memory plan: resident W2 chunk, dy ring, and as many slab buffers as fit (227 KB per CTA)
   const int avail = 232448 - 1024 - 4 * C * 128;
@@ -241,11 +286,16 @@ int hs_mlp_dgrad_gelu(const float* dy, const float* w2, const float* z, const fl
   if (a.slabs > kMaxSlabs) a.slabs = kMaxSlabs;
   if (a.slabs < 4) return hs::fail(HS_ERR_UNSUPPORTED, "hs_mlp_dgrad_gelu: C=%d leaves no room for the slab buffers", C);
   const size_t smem = (size_t)4 * C * 128 + (size_t)(a.ring + a.slabs) * kSub + 1024;
-  HS_CUDA(cudaFuncSetAttribute(mlp_dgrad_gelu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_chunk = hs::tc::sm_count() / a.n_chunks;
   if (per_chunk < 1) per_chunk = 1;
   if (per_chunk > a.tiles) per_chunk = (int)a.tiles;
-  mlp_dgrad_gelu_kernel<<<a.n_chunks * per_chunk, kThreads, smem, (cudaStream_t)stream>>>(map_dy, map_w, map_z, map_dz, a);
+  if (a.gp16) {
+    HS_CUDA(cudaFuncSetAttribute(mlp_dgrad_gelu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_dgrad_gelu_kernel<true><<<a.n_chunks * per_chunk, kThreads, smem, (cudaStream_t)stream>>>(map_dy, map_w, map_dz, map_dz, a);
+  } else {
+    HS_CUDA(cudaFuncSetAttribute(mlp_dgrad_gelu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mlp_dgrad_gelu_kernel<false><<<a.n_chunks * per_chunk, kThreads, smem, (cudaStream_t)stream>>>(map_dy, map_w, map_z, map_dz, a);
+  }
   HS_LAUNCH_CHECK();
   return HS_OK;
 }

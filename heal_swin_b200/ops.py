@@ -479,6 +479,7 @@ _GEMM_MODE = os.environ.get("HEALSWIN_GEMM", "bf16x3")
 _CUSTOM_WGRAD = os.environ.get("HEALSWIN_CUSTOM_WGRAD", "1") == "1"
 _FUSED_MLP = os.environ.get("HEALSWIN_FUSED_MLP", "1") == "1"
 _TF32_MLP_DGRAD = os.environ.get("HEALSWIN_TF32_MLP_DGRAD", "1") == "1"
+_MLP_COMPACT = os.environ.get("HEALSWIN_MLP_COMPACT", "1")  # "0" off | "1" tensor-bound stages | "all"
 
 
 # Operand precision of the hand-written GEMMs.  "fp32" (default): bf16x3 for every forward product and for the HBM-bound
@@ -664,12 +665,14 @@ def _gemm3(a2, wsplit, N, bias=None, aux=None, mode=_lib.GEMM_PLAIN, drop=0.0, s
     """hs_gemm3 on a (T, K) activation and a split weight; returns d, or (d, d2) for GEMM_GELU.  ``colsum`` (K floats,
     zero or a running sum) receives the column sums of ``a2`` in the same pass."""
     T, K = a2.shape
-    d = torch.empty((T, N), device=a2.device, dtype=torch.float32)
-    d2 = torch.empty_like(d) if mode == _lib.GEMM_GELU else None
+    two = mode in (_lib.GEMM_GELU, _lib.GEMM_GELU_C)
+    # (compact GELU mode: d is the FP16 derivative tensor g', d2 the activation h)
+    d = torch.empty((T, N), device=a2.device, dtype=torch.float16 if mode == _lib.GEMM_GELU_C else torch.float32)
+    d2 = torch.empty((T, N), device=a2.device, dtype=torch.float32) if two else None
     prec = _fwd_prec() if prec is None else prec
     STATS.launch("gemm3", lib.hs_gemm3, ptr(a2), ptr(wsplit), ptr(bias), ptr(aux), ptr(d), ptr(d2), ptr(colsum), T, N, K,
                  mode, prec, C.c_float(drop), C.c_uint64(seed), current_stream(), tag=(T, N, K, mode, prec))
-    return (d, d2) if mode == _lib.GEMM_GELU else d
+    return (d, d2) if two else d
 
 
 _FUSED_LINEAR_LN = os.environ.get("HEALSWIN_FUSED_LINEAR_LN", "1") == "1"
@@ -686,7 +689,7 @@ def _gemm3_ln(a2, wsplit, N, bias, gamma, beta, G, eps, aux=None, save=True):
     prec = _fwd_prec()
     STATS.launch("gemm3", lib.hs_gemm3_ln, ptr(a2), ptr(wsplit), ptr(bias), ptr(gamma), ptr(beta), ptr(aux), ptr(pre), ptr(y),
                  ptr(mean), ptr(rstd), T, N, K, G, C.c_float(eps), prec, current_stream(),
-                 tag=(T, N, K, 4 + (1 if aux is not None else 0) + (2 if save else 0), prec))
+                 tag=(T, N, K, 10 + (1 if aux is not None else 0) + (2 if save else 0), prec))
     return y, pre, mean, rstd
 
 
@@ -811,7 +814,7 @@ class _LnLinearFn(torch.autograd.Function):
         rstd = torch.empty_like(mean) if save else None
         prec = _fwd_prec()
         STATS.launch("gemm3", lib.hs_gemm3_lnin, ptr(x2), ptr(split_weight(wg)), ptr(wsum), ptr(b0), ptr(d), ptr(mean),
-                     ptr(rstd), T, N, K, C.c_float(eps), prec, current_stream(), tag=(T, N, K, 8, prec))
+                     ptr(rstd), T, N, K, C.c_float(eps), prec, current_stream(), tag=(T, N, K, 20, prec))
         if save:
             ctx.save_for_backward(x2, gamma, beta, weight, mean, rstd)
         ctx.meta = (x.shape, float(eps))
@@ -975,7 +978,14 @@ class _MlpFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         K = x.shape[-1]
         x2 = _f32c(x).reshape(-1, K)
-        z, h = _gemm3(x2, split_weight(w1), w1.shape[0], _f32c(b1), None, _lib.GEMM_GELU, drop, seed)
+        # z: the bias-free fc1 output (fp32), or -- compact form -- the FP16 tensor g' = GELU'(z + b1) * dropmask, which is
+        # all the backward needs from it at half the bytes.  Used where it pays (same-box A/B of the N_side=256 step): the
+        # tensor-bound stages (C >= 384), whose backward GEMM then multiplies by g' instead of bringing z in by TMA and
+        # evaluating GELU' (0.27 against 0.38 ms per stage-2 launch).  At stages 0-1 the launches are bound by their
+        # epilogues' issue slots and the per-row FP16 accesses cost more than the bytes they save (HEALSWIN_MLP_COMPACT=all).
+        compact = (_MLP_COMPACT != "0" and w1.shape[0] % 32 == 0 and (_MLP_COMPACT == "all" or w1.shape[1] > 256))
+        z, h = _gemm3(x2, split_weight(w1), w1.shape[0], _f32c(b1), None,
+                      _lib.GEMM_GELU_C if compact else _lib.GEMM_GELU, drop, seed)
         ctx.drop = (float(drop), int(seed))
         ctx.xshape = x.shape
         ctx.ln = gamma is not None
@@ -1016,12 +1026,17 @@ class _MlpFn(torch.autograd.Function):
         # stage 0 (HBM-bound): the dedicated TF32 kernel; from stage 1 on, where one TF32 MMA per product is what
         # _dgrad_prec picks anyway, the general GEMM with the GELU' epilogue is faster (C = 192: 0.54 against 0.65 ms,
         # scripts/mlp_dgrad_s1.py)
+        compact = z.dtype == torch.float16
         if (_TF32_MLP_DGRAD and lib.hs_mlp_dgrad_gelu_supported(T, Cout, J)
                 and not (_GEMM_PRECISION != "bf16" and _dgrad_tensor_bound(J, Cout))):
-            dz = torch.empty_like(z)
+            dz = torch.empty((T, J), device=z.device, dtype=torch.float32)
             STATS.launch("mlp_dgrad_gelu", lib.hs_mlp_dgrad_gelu, ptr(dy2), ptr(w2), ptr(z), ptr(b1),
-                         C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J, _tc_flags(), current_stream(),
-                         tag=(T, Cout, J))
+                         C.c_float(ctx.drop[0]), C.c_uint64(ctx.drop[1]), ptr(dz), T, Cout, J,
+                         _tc_flags() | (_lib.MLP_GRAD16 if compact else 0), current_stream(),
+                         tag=(T, Cout, J, int(compact)))
+        elif compact:
+            prec = _dgrad_prec(T, J, Cout)
+            dz = _gemm3(dy2, split_weight(w2, transposed=True, prec=prec), J, None, z, _lib.GEMM_GELU_GRAD_C, prec=prec)
         else:
             prec = _dgrad_prec(T, J, Cout)
             dz = _gemm3(dy2, split_weight(w2, transposed=True, prec=prec), J, _f32c(b1), z, _lib.GEMM_GELU_GRAD, *ctx.drop,

@@ -52,6 +52,7 @@ extern "C" {
 #define HS_ATTN_COS 1u /* cosine attention, swin_hp_transformer.py:142-147 */
 #define HS_ATTN_NO_TC 2u /* force the exact-fp32 CUDA-core kernels (cross-check of the tcgen05 TF32 path) */
 #define HS_ATTN_NO_TRUNC_COMP 4u /* tcgen05 path: do not compensate the mean TF32 operand-truncation shrink (diagnostics) */
+#define HS_MLP_GRAD16 256u /* hs_mlp_dgrad_gelu: z_dev holds g' = GELU'(z + b1) * dropmask as FP16 (hs_gemm3 mode 6), not z */
 
 const char* hs_last_error(void);
 int hs_version(void);
@@ -204,7 +205,9 @@ int hs_linear_wgrad(const float* dy_dev, const float* x_dev, float* dw_dev, floa
  * dz: (T, J); all fp32 row-major.  The (T, J) hidden gradient dy @ w2 lives only in tensor memory: this replaces the
  * fc2 input-gradient GEMM followed by hs_bias_gelu_bwd.  drop / seed: the mask hs_bias_gelu_fwd used.  TF32 tensor
  * cores.  hs_mlp_dgrad_gelu_supported returns 1 for covered shapes (C a multiple of 32 and <= 192, J a multiple of 128,
- * T >= 1024).  flags: HS_ATTN_NO_TRUNC_COMP only.
+ * T >= 1024).  flags: HS_ATTN_NO_TRUNC_COMP; HS_MLP_GRAD16: z_dev is not z but the FP16 tensor g' = GELU'(z + b1) *
+ * dropmask that hs_gemm3 mode 6 wrote in the forward -- then dz = (dy @ W2) * g' (b1, drop, seed are ignored), read straight
+ * from global memory: a third fewer bytes and no GELU arithmetic in the backward.
  */
 int hs_mlp_dgrad_gelu_supported(int64_t T, int C, int J);
 int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_dev, const float* b1_dev, float drop,
@@ -228,6 +231,11 @@ int hs_mlp_dgrad_gelu(const float* dy_dev, const float* w2_dev, const float* z_d
  *   mode 1 (add)        d = acc + bias + aux                  aux: (T, N) fp32, e.g. the residual-shortcut gradient
  *   mode 2 (gelu)       d = acc,  d2 = dropout(GELU(acc + bias))      Mlp fc1 + act + drop (:39-41); exact erf GELU
  *   mode 3 (gelu grad)  d = acc * GELU'(aux + bias) * dropmask        aux = the bias-free fc1 output z
+ *   mode 6 (gelu, compact)  d2 = dropout(GELU(acc + bias)) as mode 2, but d receives g' = GELU'(acc + bias) * dropmask as
+ *                       FP16 (d_dev is a (T, N) tensor of 2-byte elements): all the backward needs from the activation, at
+ *                       a quarter of the bytes of z and h together; g' lies in [-0.13, 1.13] / (1 - drop); N % 32 == 0
+ *   mode 7 (gelu grad, compact)  d = acc * g'                         aux_dev = that FP16 tensor (no bias, drop, seed)
+ * (modes 4 and 5 are the LayerNorm forms below, with entry points of their own)
  * precision: HS_GEMM_BF16X3 (default: three bf16 MMAs per product, fp32-class) | HS_GEMM_TF32 (one TF32 MMA, A read as fp32
  * without conversion; wsplit must be hs_weight_split format 1 = fp32 rounded to the nearest TF32, same bytes per row: used
  * for the input gradients of the tensor-bound stages, where 5e-3 suffices) | HS_GEMM_BF16 (one bf16 MMA on the hi terms:

@@ -466,3 +466,62 @@ def test_batched_weight_split_equals_individual_splits():
     want.append(ops.split_weight(ws[4], cols=(96, 96)))
     for a_, b_ in zip(got, want):
         assert torch.equal(a_.view(torch.int16), b_.view(torch.int16))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Compact MLP activation record: the forward saves g' = GELU'(fc1(x) + b1) * dropmask as FP16 instead of z (hs_gemm3 mode 6),
+# the backward multiplies by it (mode 7; hs_mlp_dgrad_gelu with HS_MLP_GRAD16: tests/test_gpu_mlp.py)
+
+def _gelu_grad64(u):
+    return 0.5 * (1 + torch.erf(u / math.sqrt(2))) + u * torch.exp(-0.5 * u * u) / math.sqrt(2 * math.pi)
+
+
+def _gemm3_raw(a, ws, N, bias, aux, d, d2, mode, prec=0, drop=0.0, seed=0):
+    from heal_swin_b200._lib import check, current_stream, lib, ptr
+
+    T, K = a.shape
+    check(lib.hs_gemm3(ptr(a), ptr(ws), ptr(bias), ptr(aux), ptr(d), ptr(d2), None, T, N, K, mode, prec, C.c_float(drop),
+                       C.c_uint64(seed), current_stream()))
+
+
+@pytest.mark.parametrize("T,N,K", [(300, 96, 96), (4096, 384, 96), (2048, 768, 192), (1000, 1536, 384), (130, 64, 48)])
+def test_compact_gelu_modes_match_fp64(T, N, K):
+    """mode 6: h as mode 2 (2e-5) and g' to FP16 rounding (2^-11 of its magnitude); mode 7: acc * g' in every precision
+    the input gradients use, ragged token counts included (rows beyond T are neither written nor read)."""
+    a, w, b = _data(T, N, K, seed=11)
+    dev = a.device
+    u = a.double() @ w.double().t() + b.double()
+    gp = torch.full((T + 3, N), float("nan"), device=dev, dtype=torch.float16)  # (guard rows: must stay untouched)
+    h = torch.full((T, N), float("nan"), device=dev)
+    _gemm3_raw(a, _split(w), N, b, None, gp, h, mode=6)
+    assert rel_err(h.cpu(), torch.nn.functional.gelu(u).cpu()) < TOL
+    assert bool(torch.isnan(gp[T:]).all())
+    g64 = _gelu_grad64(u)
+    assert float((gp[:T].double() - g64).abs().max()) < 2.0 ** -11 * 1.2 + 1e-5
+    # mode 7 consumes exactly that tensor
+    for prec, tol in ((0, TOL), (1, 1e-3)):
+        out = torch.full((T, N), float("nan"), device=dev)
+        a2, wz, _ = _data(T, N, K, seed=13)
+        _gemm3_raw(a2, _split(wz, prec=prec), N, None, gp, out, None, mode=7, prec=prec)
+        want = (a2.double() @ wz.double().t()) * gp[:T].double()
+        assert rel_err(out.cpu(), want.cpu()) < tol, (prec, rel_err(out.cpu(), want.cpu()))
+
+
+def test_compact_gelu_dropout_mask_is_shared_by_h_and_the_derivative():
+    """With drop > 0 the mask (and the 1 / (1 - p) scale) is folded into BOTH outputs of mode 6, identically: h == 0 exactly
+    where g' == 0, at the rate p, and the kept entries carry the scale -- the backward needs neither seed nor mask."""
+    T, N, K = 1500, 384, 96
+    a, w, b = _data(T, N, K, seed=2)
+    a = a + 3.0  # GELU and GELU' > 0 almost everywhere: zero <=> dropped
+    w = w.abs()
+    b = b.abs()
+    drop, seed = 0.25, 0x1234_5678_9ABC
+    gp = torch.empty((T, N), device=a.device, dtype=torch.float16)
+    h = torch.empty((T, N), device=a.device)
+    _gemm3_raw(a, _split(w), N, b, None, gp, h, mode=6, drop=drop, seed=seed)
+    z, h2 = _gemm3(a, _split(w), N, b, mode=2, drop=drop, seed=seed)   # the fp32 form with the same seed
+    assert torch.equal(h == 0, h2 == 0) and rel_err(h.cpu(), h2.cpu()) < 1e-6
+    assert torch.equal(h == 0, gp == 0) and 0.2 < float((h == 0).float().mean()) < 0.3
+    u = a.double() @ w.double().t() + b.double()
+    keep = (h != 0).double()
+    assert float((gp.double() - _gelu_grad64(u) * keep / (1 - drop)).abs().max()) < 2.0 ** -10 * 1.6

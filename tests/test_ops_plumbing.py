@@ -92,6 +92,13 @@ class FakeLib:
         elif mode == 2:
             d.copy_(acc)
             d2.copy_(F.gelu(acc + b))
+        elif mode == 6:  # compact: the activation's derivative as FP16 instead of z
+            assert d.dtype == torch.float16
+            d.copy_(_gelu_grad(acc + b))
+            d2.copy_(F.gelu(acc + b))
+        elif mode == 7:
+            assert aux.dtype == torch.float16 and bias is None
+            d.copy_(acc * aux.float())
         else:
             d.copy_(acc * _gelu_grad(aux + b))
         return 0
@@ -103,7 +110,11 @@ class FakeLib:
 
     def hs_mlp_dgrad_gelu(self, dy, w2, z, b1, drop, seed, dz, T, Cc, J, flags, stream):
         self.calls.append("mlp_dgrad_gelu")
-        dz.copy_((dy @ w2) * _gelu_grad(z + b1))
+        if flags & 256:  # HS_MLP_GRAD16: z is the FP16 derivative tensor
+            assert z.dtype == torch.float16
+            dz.copy_((dy @ w2) * z.float())
+        else:
+            dz.copy_((dy @ w2) * _gelu_grad(z + b1))
         return 0
 
     def hs_ln_head_fwd(self, x, gamma, beta, w, hb, logits, mean, rstd, rows, P, Cc, K, eps, stream):
@@ -187,7 +198,10 @@ def test_plain_linear_node_matches_torch(fake):
 
 
 @pytest.mark.parametrize("fork", [False, True])
-def test_fused_mlp_node_matches_torch_autograd(fake, fork):
+@pytest.mark.parametrize("compact", [False, True])
+def test_fused_mlp_node_matches_torch_autograd(fake, fork, compact, monkeypatch):
+    # compact: the forward saves GELU'(z + b1) as FP16 instead of z (hs_gemm3 modes 6 / 7, HS_MLP_GRAD16)
+    monkeypatch.setattr(ops, "_MLP_COMPACT", "all" if compact else "0")
     g = torch.Generator().manual_seed(1)
     x = torch.randn(2, 6, 8, generator=g, requires_grad=True)
     w1 = (torch.randn(32, 8, generator=g) / 3).requires_grad_(True)
@@ -198,7 +212,8 @@ def test_fused_mlp_node_matches_torch_autograd(fake, fork):
     y = out[0] + out[1] if fork else out
     y.backward(gy)
     # fc1 + GELU epilogue, fc2 | wgrad(fc2), fused dgrad + GELU', dgrad (+ shortcut gradient when forked), wgrad(fc1) + bias
-    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "mlp_dgrad_gelu", "gemm3:1" if fork else "gemm3:0", "wgrad"]
+    assert fake.calls == ["gemm3:6" if compact else "gemm3:2", "gemm3:0", "wgrad", "mlp_dgrad_gelu",
+                          "gemm3:1" if fork else "gemm3:0", "wgrad"]
     got = [t.grad.clone() for t in (x, w1, b1, w2)]
     for t in (x, w1, b1, w2):
         t.grad = None
@@ -206,7 +221,7 @@ def test_fused_mlp_node_matches_torch_autograd(fake, fork):
     (ref + x if fork else ref).backward(gy)
     assert _close(y.detach(), (ref + x if fork else ref).detach(), 1e-4)
     for a, t in zip(got, (x, w1, b1, w2)):
-        assert _close(a, t.grad, 1e-4)
+        assert _close(a, t.grad, 1e-3 if compact else 1e-4)  # (FP16 derivative: 2^-12 relative)
 
 
 @pytest.mark.parametrize("bias", [False, True])
@@ -233,7 +248,9 @@ def test_decoder_tail_parameter_gradients_follow_from_s_and_g(fake, bias):
         assert _close(a, t.grad, 1e-4)
 
 
-def test_mlp_node_uses_the_gelu_grad_epilogue_where_the_tf32_kernel_does_not_cover(fake, monkeypatch):
+@pytest.mark.parametrize("compact", [False, True])
+def test_mlp_node_uses_the_gelu_grad_epilogue_where_the_tf32_kernel_does_not_cover(fake, monkeypatch, compact):
+    monkeypatch.setattr(ops, "_MLP_COMPACT", "all" if compact else "0")
     monkeypatch.setattr(fake, "hs_mlp_dgrad_gelu_supported", lambda T, Cc, J: 0)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(5, 8, generator=g, requires_grad=True)
@@ -241,13 +258,14 @@ def test_mlp_node_uses_the_gelu_grad_epilogue_where_the_tf32_kernel_does_not_cov
     b1 = torch.randn(32, generator=g, requires_grad=True)
     w2 = (torch.randn(8, 32, generator=g) / 6).requires_grad_(True)
     ops._MlpFn.apply(x, w1, b1, w2, 0.0, 0, False).sum().backward()
-    assert fake.calls == ["gemm3:2", "gemm3:0", "wgrad", "gemm3:3", "gemm3:0", "wgrad"]
+    assert fake.calls == (["gemm3:6", "gemm3:0", "wgrad", "gemm3:7", "gemm3:0", "wgrad"] if compact else
+                          ["gemm3:2", "gemm3:0", "wgrad", "gemm3:3", "gemm3:0", "wgrad"])
     got = [t.grad.clone() for t in (x, w1, b1, w2)]
     for t in (x, w1, b1, w2):
         t.grad = None
     F.linear(F.gelu(F.linear(x, w1, b1)), w2).sum().backward()
     for a, t in zip(got, (x, w1, b1, w2)):
-        assert _close(a, t.grad, 1e-4)
+        assert _close(a, t.grad, 1e-3 if compact else 1e-4)
 
 
 def test_weight_splits_are_cached_until_the_parameter_changes(fake):
