@@ -807,7 +807,7 @@ class _LnLinearFn(torch.autograd.Function):
         g, b = _f32c(gamma.detach()), _f32c(beta.detach())
         wg = w * g                       # W diag(gamma)
         wsum = wg.sum(1)                 # s = W' 1
-        b0 = w @ b                       # W beta
+        b0 = (w * b).sum(1)              # W beta (elementwise: no library GEMV for a parameter-sized product)
         save = any(ctx.needs_input_grad[:4])
         d = torch.empty((T, N), device=x2.device, dtype=torch.float32)
         mean = torch.empty((T,), device=x2.device, dtype=torch.float32) if save else None
