@@ -103,6 +103,69 @@ class FakeLib:
             d.copy_(acc * _gelu_grad(aux + b))
         return 0
 
+    def _weight_of(self, ws, N, K):
+        o = ws.view(N, -1, 64).float()
+        return (o[:, :, :32] + o[:, :, 32:]).reshape(N, -1)[:, :K]
+
+    def hs_gemm3_ln_supported(self, T, N, K, G):
+        return 1 if (G % 32 == 0 and G <= 192 and N % G == 0) else 0
+
+    def hs_gemm3_ln(self, a, ws, bias, gamma, beta, aux, pre, y, mean, rstd, T, N, K, G, eps, prec, stream):
+        """y = [aux +] LayerNorm over groups of G columns of (a W^T + bias); pre / mean / rstd optional (include/healswin_b200.h)."""
+        self.calls.append("gemm3_ln" + ("+aux" if aux is not None else "") + ("+save" if pre is not None else ""))
+        p = a @ self._weight_of(ws, N, K).t() + (bias if bias is not None else 0)
+        v = p.view(T * (N // G), G)
+        mu, rs = v.mean(1), torch.rsqrt(v.var(1, unbiased=False) + _val(eps))
+        out = (((v - mu[:, None]) * rs[:, None]) * gamma + beta).view(T, N)
+        y.copy_(out + (aux if aux is not None else 0))
+        if pre is not None:
+            pre.copy_(p)
+        if mean is not None:
+            mean.copy_(mu)
+            rstd.copy_(rs)
+        return 0
+
+    def hs_gemm3_lnin_supported(self, T, N, K):
+        return 1 if (K % 32 == 0 and K >= 160) else 0
+
+    def hs_gemm3_lnin(self, a, ws, wsum, b0, d, mean, rstd, T, N, K, eps, prec, stream):
+        """d = rstd (a W'^T - mean wsum) + b0 with the row statistics of a (include/healswin_b200.h)."""
+        self.calls.append("gemm3_lnin")
+        mu, rs = a.mean(1), torch.rsqrt(a.var(1, unbiased=False) + _val(eps))
+        acc = a @ self._weight_of(ws, N, K).t()
+        d.copy_(rs[:, None] * (acc - mu[:, None] * wsum) + (b0 if b0 is not None else 0))
+        if mean is not None:
+            mean.copy_(mu)
+            rstd.copy_(rs)
+        return 0
+
+    def hs_layernorm_fwd(self, x, pb, res, gamma, beta, rsc, rps, in_drop, seed, y, mean, rstd, rows, Cc, eps, stream):
+        self.calls.append("ln_fwd")
+        assert pb is None and res is None and rsc is None and _val(in_drop) == 0.0
+        y.copy_(F.layer_norm(x, (Cc,), gamma, beta, _val(eps)))
+        return 0
+
+    def hs_layernorm_bwd(self, dy, x, pb, mean, rstd, gamma, rsc, rps, in_drop, seed, dx, dw, db, dpb, rows, Cc, stream):
+        """dx of LayerNorm from the saved statistics; dgamma / dbeta / d(pre-bias) ACCUMULATE (the kernel adds atomically)."""
+        self.calls.append("ln_bwd")
+        assert rsc is None and _val(in_drop) == 0.0
+        xv, dyv = x.reshape(rows, Cc) + (pb if pb is not None else 0), dy.reshape(rows, Cc)
+        xh = (xv - mean[:, None]) * rstd[:, None]
+        wv = dyv * gamma
+        out = rstd[:, None] * (wv - wv.mean(1, keepdim=True) - xh * (wv * xh).mean(1, keepdim=True))
+        dx.view(rows, Cc).copy_(out)
+        if dw is not None:
+            dw += (dyv * xh).sum(0)
+        if db is not None:
+            db += dyv.sum(0)
+        if dpb is not None:
+            dpb += out.sum(0)
+        return 0
+
+    def hs_weight_split_batch(self, table, n, total_tiles, stream):
+        self.calls.append(f"split_batch:{n}")
+        return 0
+
     def hs_bias_gelu_fwd(self, z, b, drop, seed, h, rows, Cc, stream):
         assert _val(drop) == 0.0
         h.copy_(F.gelu(z + b))
@@ -311,3 +374,130 @@ def test_bias_gradient_rides_with_the_dgrad_gemm_where_the_wgrad_kernel_cannot_f
     w.grad = b.grad = None
     ops._LinearFn.apply(x2, w, b, False).sum().backward()
     assert fake.calls == ["gemm3:0", "wgrad"] and _close(b.grad, torch.full((12,), 9.0))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerNorm inside the GEMM: autograd plumbing of ops.linear_ln / ops.mlp_ln / ops.ln_linear (hs_gemm3_ln, hs_gemm3_lnin)
+
+@pytest.mark.parametrize("res", [False, True])
+@pytest.mark.parametrize("G", [32, 64])
+def test_linear_ln_node_matches_torch_autograd(fake, res, G):
+    """y = [residual +] LN_G(linear(x)): one fused forward launch, then LayerNorm backward (which also yields the linear's
+    bias gradient when G = N), dgrad, wgrad -- all seven gradients against plain torch."""
+    g = torch.Generator().manual_seed(4)
+    T, K, N = 10, 8, 64
+    x = torch.randn(T, K, generator=g, requires_grad=True)
+    w = (torch.randn(N, K, generator=g) / 3).requires_grad_(True)
+    b = torch.randn(N, generator=g, requires_grad=True)
+    gamma = (1 + 0.3 * torch.randn(G, generator=g)).requires_grad_(True)
+    beta = (0.2 * torch.randn(G, generator=g)).requires_grad_(True)
+    r = torch.randn(T, N, generator=g, requires_grad=True) if res else None
+    gy = torch.randn(T, N, generator=g)
+    params = [x, w, b, gamma, beta] + ([r] if res else [])
+    y = ops._LinearLnFn.apply(x, w, b, gamma, beta, r, 1e-5)
+    y.backward(gy)
+    # forward; LN backward (takes the linear's bias gradient too when G = N, else the weight-gradient kernel does); dgrad; wgrad
+    assert fake.calls == ["gemm3_ln" + ("+aux" if res else "") + "+save", "ln_bwd", "gemm3:0", "wgrad"]
+    got = [t.grad.clone() for t in params]
+    for t in params:
+        t.grad = None
+    ref = F.layer_norm(F.linear(x, w, b).view(T, N // G, G), (G,), gamma, beta, 1e-5).view(T, N)
+    ref = ref + r if res else ref
+    ref.backward(gy)
+    assert _close(y.detach(), ref.detach(), 1e-4)
+    for a, t in zip(got, params):
+        assert _close(a, t.grad, 1e-4)
+
+
+def test_mlp_ln_node_matches_torch_autograd(fake, monkeypatch):
+    """x + LN(fc2(GELU(fc1 x)) + b2): the residual's gradient enters fc1's input-gradient GEMM as its aux operand (mode 1),
+    fc2's bias gradient comes out of the LayerNorm-backward pass."""
+    monkeypatch.setattr(ops, "_MLP_COMPACT", "0")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 6, 32, generator=g, requires_grad=True)
+    w1 = (torch.randn(64, 32, generator=g) / 6).requires_grad_(True)
+    b1 = torch.randn(64, generator=g, requires_grad=True)
+    w2 = (torch.randn(32, 64, generator=g) / 8).requires_grad_(True)
+    b2 = torch.randn(32, generator=g, requires_grad=True)
+    gamma = (1 + 0.3 * torch.randn(32, generator=g)).requires_grad_(True)
+    beta = (0.2 * torch.randn(32, generator=g)).requires_grad_(True)
+    gy = torch.randn(2, 6, 32, generator=g)
+    params = [x, w1, b1, w2, b2, gamma, beta]
+    y = ops._MlpFn.apply(x, w1, b1, w2, 0.0, 0, False, b2, gamma, beta, 1e-5)
+    y.backward(gy)
+    assert fake.calls == ["gemm3:2", "gemm3_ln+aux+save", "ln_bwd", "wgrad", "mlp_dgrad_gelu", "gemm3:1", "wgrad"]
+    got = [t.grad.clone() for t in params]
+    for t in params:
+        t.grad = None
+    ref = x + F.layer_norm(F.linear(F.gelu(F.linear(x, w1, b1)), w2, b2), (32,), gamma, beta, 1e-5)
+    ref.backward(gy)
+    assert _close(y.detach(), ref.detach(), 1e-4)
+    for a, t in zip(got, params):
+        assert _close(a, t.grad, 1e-4)
+
+
+def test_ln_linear_node_matches_torch_autograd(fake):
+    """linear(LN(x)) (PatchMerging): one forward launch on the raw rows; the backward rebuilds the normalised rows for the
+    weight gradient and runs dgrad + LayerNorm backward for x, gamma, beta."""
+    g = torch.Generator().manual_seed(6)
+    T, K, N = 9, 160, 16
+    x = (torch.randn(T, K, generator=g) + 0.5).requires_grad_(True)
+    gamma = (1 + 0.3 * torch.randn(K, generator=g)).requires_grad_(True)
+    beta = (0.2 * torch.randn(K, generator=g)).requires_grad_(True)
+    w = (torch.randn(N, K, generator=g) / 12).requires_grad_(True)
+    gy = torch.randn(T, N, generator=g)
+    params = [x, gamma, beta, w]
+    y = ops._LnLinearFn.apply(x, gamma, beta, w, 1e-5)
+    y.backward(gy)
+    assert fake.calls == ["gemm3_lnin", "ln_fwd", "wgrad", "gemm3:0", "ln_bwd"]
+    got = [t.grad.clone() for t in params]
+    for t in params:
+        t.grad = None
+    ref = F.linear(F.layer_norm(x, (K,), gamma, beta, 1e-5), w)
+    ref.backward(gy)
+    assert _close(y.detach(), ref.detach(), 1e-4)
+    for a, t in zip(got, params):
+        assert _close(a, t.grad, 2e-4)
+
+
+def test_zero_arena_serves_aligned_slices_and_measures_first():
+    ar = ops.ZeroArena("cpu")
+    prev = ops.use_zero_arena(ar)
+    try:
+        ar.begin()
+        a = ops.zeros((3, 5), "cpu")          # first pass: no buffer yet, plain zeros, but the demand is recorded
+        b = ops.zeros(70, "cpu")
+        assert ar.buf is None and ar.need == 64 + 128 and float(a.abs().sum() + b.abs().sum()) == 0.0
+        ar.begin()                            # allocates what the first pass asked for
+        a = ops.zeros((3, 5), "cpu")
+        b = ops.zeros(70, "cpu")
+        assert a.data_ptr() == ar.buf.data_ptr() and b.data_ptr() == ar.buf.data_ptr() + 64 * 4
+        a.add_(1.0)
+        b.add_(2.0)
+        c = ops.zeros(4, "cpu")               # beyond the measured demand: falls back to torch.zeros
+        assert float(c.sum()) == 0.0 and c.data_ptr() != ar.buf.data_ptr()
+        ar.begin()                            # one memset clears every slice
+        assert float(ar.buf.abs().sum()) == 0.0
+    finally:
+        ops.use_zero_arena(prev)
+    assert ops.zeros(3, "cpu").shape == (3,)
+
+
+def test_refresh_weight_splits_marks_the_cache_current(fake, monkeypatch):
+    """One batched launch covers every live cached operand; afterwards split_weight returns the cached buffers without
+    launching, also for parameters that were changed without a version bump."""
+    w1, w2 = torch.nn.Parameter(torch.randn(8, 12)), torch.nn.Parameter(torch.randn(16, 8))
+    a, b, c = ops.split_weight(w1), ops.split_weight(w1, transposed=True), ops.split_weight(w2)
+    assert fake.splits == 3
+    w1.data.mul_(2.0)
+    ops._on_optimizer_step()                  # what a torch optimizer's post-step hook does: a new epoch
+    monkeypatch.setattr(torch.Tensor, "to", lambda self, *a_, **k: self, raising=False)
+    n = ops.refresh_weight_splits("cpu")
+    assert n == 3 and fake.calls[-1] == "split_batch:3"
+    assert ops.split_weight(w1) is a and ops.split_weight(w1, transposed=True) is b and ops.split_weight(w2) is c
+    assert fake.splits == 3                   # no per-matrix launches after the batched refresh
+    del w2
+    import gc
+
+    gc.collect()
+    assert ops.refresh_weight_splits("cpu") == 2
